@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Headline benchmark: particle-segments/s of the MoveToNextLocation hot path.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+  python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port)
+
+A "step" is one MoveToNextLocation over one synthetic batch of BASELINE.json's
+config c2 (998,250-tet Kuhn box, 10M particles per GPU).
+Per-GPU work is fixed as N grows (weak scaling); every rank holds the whole
+mesh (full-buffer picpart) and its own particle stripe, and the per-rank
+tallies are summed once at batch end with ncclAllReduce inside the timed
+region.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle_segments_per_sec"
+UNIT = "segments/s"
+# algorithmic bytes: per tallied segment 96 B tet geometry + 16 B
+# neighbour ids + 16 B flux read-modify-write; per flying track 61 B read + 28 B written
+BYTES_PER_SEGMENT = 128
+BYTES_PER_TRACK = 89
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def workload_description(cfg_name, cfg, n):
+    c = cfg["cells"]
+    return (f"{cfg_name}: Kuhn box {c[0]}x{c[1]}x{c[2]} = {6 * c[0] * c[1] * c[2]} tets, {n} particles/GPU, "
+            f"isotropic exp(mean {cfg['mean_length']}) tracks, 95% flying, weights U[0.5,1]")
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """DRAM bytes per launch of the walk kernel from the committed ncu capture, or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=lambda: self.rows.extend(self.proc.stdout), daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU reference arm
+
+def run_reference(args, rank):
+    """Times the reference algorithm's CPU restatement (oracle, OpenMP, all host threads) on a
+    bounded sample of the same workload.  The real reference cannot be built offline (needs
+    Kokkos/Omega_h/pumi-pic), hence kind = "port"."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle.oracle import OraclePumiTally, num_threads
+    from pumiumtally_b200.mesh import kuhn_box
+    from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
+
+    cfg = CONFIGS[args.config]
+    n = min(args.cpu_sample, cfg["particles"])
+    coords, t2v = kuhn_box(*cfg["cells"])
+    wl = SyntheticWorkload(box=tuple(float(c) for c in cfg["cells"]), num_particles=n,
+                           mean_length=cfg["mean_length"], mu_min=cfg["mu_min"])
+    orc = OraclePumiTally(coords, t2v, n, per_particle=True)
+    orc.CopyInitialPosition(wl.initial_positions().reshape(-1))
+    for _ in range(args.warmup):
+        o, d, f, w = wl.next_step()
+        orc.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
+    batches = [wl.next_step() for _ in range(args.steps)]
+    s0 = orc.n_segments
+    t0 = time.perf_counter()
+    for o, d, f, w in batches:
+        orc.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
+    dt = time.perf_counter() - t0
+    segs = orc.n_segments - s0
+    value = segs / dt
+    sample = (f"first {n} particles of the {args.config} batch per step ({args.steps} steps, "
+              f"{segs} segments) on the full {len(t2v)}-tet mesh")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_description(args.config, cfg, cfg["particles"]),
+                   "note": "reference-algorithm restatement (OpenMP); the Kokkos/pumi-pic reference cannot be built offline"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------- GPU arm
+
+def run_gpu(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+
+    from pumiumtally_b200.tally import PumiTally
+    from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the tally engine has no CPU path "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = CONFIGS[args.config]
+    cells = cfg["cells"]
+    n = args.particles or cfg["particles"]
+    box = tuple(float(c) for c in cells)
+    spec = f"box:{cells[0]},{cells[1]},{cells[2]}"
+    nsteps = args.warmup + args.steps
+
+    def new_engine():
+        e = PumiTally.from_spec(spec, n, device=local_rank)
+        e.set_option("variant", args.variant)
+        e.set_option("block", args.block)
+        return e
+
+    # identical batches for both arms, generated on the device once
+    wl = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], mu_min=cfg["mu_min"],
+                           backend="torch", device=dev, id_offset=rank * n)
+    init = wl.initial_positions().contiguous()
+    batches = [tuple(x.contiguous() for x in wl.next_step()) for _ in range(nsteps)]
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm: `value` ------------------------------
+    eng = new_engine()
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(PumiTally.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        eng.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
+    eng.copy_initial_position_device(init.data_ptr(), stream)
+    for k in range(args.warmup):
+        o, d, f, w = batches[k]
+        eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
+    barrier()
+    st0 = eng.stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for k in range(args.warmup, nsteps):
+        o, d, f, w = batches[k]
+        eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
+    if world > 1:
+        torch.cuda.current_stream().synchronize()
+        eng.allreduce_tally()  # batch-end exchange of the ghost tallies over NVLink
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    st1 = eng.stats()
+    segs = st1["segments"] - st0["segments"]
+    tracks = st1["tracks"] - st0["tracks"]
+    kernel_ms = st1["kernel_ms"] - st0["kernel_ms"]
+    lost = st1["lost"]
+    t_all = torch.tensor([ms], dtype=torch.float64, device=dev)
+    s_all = torch.tensor([float(segs), float(tracks)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s_all, op=dist.ReduceOp.SUM)
+    ms_max = float(t_all[0])
+    total_segs, total_tracks = float(s_all[0]), float(s_all[1])
+    value = total_segs / (ms_max * 1e-3)
+    flux_sum = float(eng.flux.sum())
+    del eng
+
+    # ---------------- end-to-end arm through the host-pointer C ABI: `e2e` ------
+    e2e = None
+    if not args.no_e2e:
+        host = []
+        for (o, d, f, w) in batches:
+            host.append(tuple(torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x) for x in (o, d, f, w)))
+        init_h = init.cpu()
+        eng2 = new_engine()
+        eng2.CopyInitialPosition(init_h.numpy().reshape(-1))
+        for k in range(args.warmup):
+            o, d, f, w = host[k]
+            eng2.move_host_ptr(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr())
+            eng2.stats()
+        barrier()
+        s0 = eng2.stats()["segments"]
+        t0 = time.perf_counter()
+        for k in range(args.warmup, nsteps):
+            o, d, f, w = host[k]
+            eng2.move_host_ptr(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr())
+            s1 = eng2.stats()["segments"]  # device->host read of the step's result
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e_t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        e_s = torch.tensor([float(s1 - s0)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(e_s, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(e_s[0]) / float(e_t[0]), "unit": UNIT,
+               "h2d_bytes_per_step": n * (24 + 24 + 8 + 1), "d2h_bytes_per_step": 56,
+               "ms_per_step": 1e3 * float(e_t[0]) / args.steps,
+               "note": "MoveToNextLocation on pinned host buffers + per-step stats read-back"}
+        del eng2, host
+
+    # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle.oracle import OraclePumiTally, num_threads
+        from pumiumtally_b200.mesh import kuhn_box
+
+        ns = min(args.cpu_sample, n)
+        coords, t2v = kuhn_box(*cells)
+        orc = OraclePumiTally(coords, t2v, ns, per_particle=True)
+        orc.CopyInitialPosition(init[:ns].cpu().numpy().reshape(-1))
+        cpu_steps = min(args.cpu_steps, nsteps)
+        s0, t_cpu = 0, 0.0
+        for k in range(cpu_steps):
+            o, d, f, w = (x[:ns].cpu().numpy() for x in batches[k])
+            f = f.copy()
+            t0 = time.perf_counter()
+            orc.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
+            t_cpu += time.perf_counter() - t0
+        cpu = {"value": orc.n_segments / t_cpu, "unit": UNIT, "cores": num_threads(), "kind": "port",
+               "sample": f"first {ns} particles of the first {cpu_steps} batches ({orc.n_segments} segments, "
+                         f"{t_cpu:.1f} s) on the full mesh; reference-algorithm restatement, OpenMP"}
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    alg_bytes = BYTES_PER_SEGMENT * segs + BYTES_PER_TRACK * tracks  # this rank, whole timed region
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_description(args.config, cfg, n), "variant": args.variant,
+                   "block": args.block, "l2": "inputs larger than L2 (570 MB of fresh particle data per step)",
+                   "parallelism": f"particle stripes x{world}, full-buffer picparts, 1 ncclAllReduce(flux) per batch",
+                   "segments_per_track": total_segs / max(total_tracks, 1.0), "lost": int(lost),
+                   "flux_sum": flux_sum},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": recorded_traffic(),
+                     "kernel": "walk kernel (variant %d), %d launches, %.3f ms each" % (args.variant, args.steps, kernel_ms / max(args.steps, 1)),
+                     "algorithmic_bytes_per_launch": alg_bytes / max(args.steps, 1), "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2")
+    ap.add_argument("--particles", type=int, default=0, help="override particles per GPU (debug only)")
+    ap.add_argument("--variant", type=int, default=env_int("PUMITALLY_VARIANT", 0))
+    ap.add_argument("--block", type=int, default=env_int("PUMITALLY_BLOCK", 128))
+    ap.add_argument("--cpu-sample", type=int, default=500_000)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and args.gpus > 1:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

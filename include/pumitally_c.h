@@ -1,0 +1,131 @@
+/*
+ * pumitally_c.h -- C ABI of libpumitally.so (B200 track-length tally engine).
+ *
+ * Plain pointers and sizes only.  The first five entry points are one-to-one
+ * with the reference's public interface, which is what any FFI for this path
+ * binds (reference: src/pumitally/PumiTally.h, class pumitally::PumiTally);
+ * the C++ facade in include/pumitally/PumiTally.h is a thin wrapper over them.
+ * The rest are additive: accessors the reference's tests obtain by reaching
+ * into PumiTallyImpl members, device-pointer entry points for callers whose
+ * particle data already lives in HBM, and the multi-GPU exchange step.
+ *
+ * Error convention follows the reference (PumiTallyImpl.cpp:444-458, 558-565):
+ * problems are printed to stderr and the call returns; functions that return
+ * int give 0 on success and non-zero on failure so FFI callers can also check.
+ * There is no CPU fallback: without a CUDA device pumitally_create* fails.
+ */
+#ifndef PUMITALLY_C_H
+#define PUMITALLY_C_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pumitally_engine pumitally_engine;
+
+/* ---- reference interface ------------------------------------------------ */
+
+/* PumiTally::PumiTally(mesh_filename, num_particles, argc, argv)
+ * (reference: PumiTally.h:50-51, PumiTallyImpl.cpp:31-52).  mesh_filename: an
+ * Omega_h "<name>.osh" directory, a raw mesh file, or "box:nx,ny,nz[,lx,ly,lz]".
+ * argc/argv may be NULL.  Returns NULL on failure. */
+pumitally_engine *pumitally_create(const char *mesh_filename, int32_t num_particles,
+                                   int *argc, char ***argv);
+
+/* PumiTally::CopyInitialPosition(init_particle_positions, size)
+ * (reference: PumiTally.h:66-67, PumiTallyImpl.cpp:54-64).  Host pointer,
+ * x0,y0,z0,x1,...; size = 3 * num_particles.  Once per engine. */
+int pumitally_copy_initial_position(pumitally_engine *e, const double *init_particle_positions,
+                                    int32_t size);
+
+/* PumiTally::MoveToNextLocation(origin, destinations, flying, weights, size)
+ * (reference: PumiTally.h:87-89, PumiTallyImpl.cpp:66-149).  Host pointers;
+ * size = 3 * num_particles; flying[] is overwritten with zeros
+ * (PumiTallyImpl.cpp:169-172).  Inputs are fully consumed before return. */
+int pumitally_move_to_next_location(pumitally_engine *e, const double *particle_origin,
+                                    const double *particle_destinations, int8_t *flying,
+                                    const double *weights, int32_t size);
+
+/* PumiTally::WriteTallyResults() (reference: PumiTally.h:95,
+ * PumiTallyImpl.cpp:151-157, 382-416): flux/volume -> "fluxresult.vtk". */
+int pumitally_write_tally_results(pumitally_engine *e);
+
+/* PumiTally::~PumiTally() (reference: PumiTally.h:103, PumiTally.cpp:16-19). */
+void pumitally_destroy(pumitally_engine *e);
+
+/* ---- additive: construction from arrays ---------------------------------- */
+
+/* Same engine, mesh given in memory: coords double[3*nverts], tet2vert
+ * int32[4*ntets] (what the reference gets from Omega_h::binary::read,
+ * PumiTallyImpl.cpp:562).  device < 0 selects the current CUDA device. */
+pumitally_engine *pumitally_create_from_arrays(const double *coords, int64_t nverts,
+                                               const int32_t *tet2vert, int64_t ntets,
+                                               int32_t num_particles, int32_t device);
+
+/* ---- additive: accessors (reference tests read Impl members instead:
+ * test_pumi_tally_impl_methods.cpp:153, 163, 232) ------------------------- */
+
+int64_t pumitally_num_elements(const pumitally_engine *e);
+int32_t pumitally_num_particles(const pumitally_engine *e);
+/* raw (un-normalised) flux, double[num_elements] (handler->flux) */
+int pumitally_get_flux(pumitally_engine *e, double *out, int64_t n);
+/* flux / volume and volume (NormalizeFlux, PumiTallyImpl.cpp:382-409); either may be NULL */
+int pumitally_get_normalized_flux(pumitally_engine *e, double *out_flux, double *out_volume,
+                                  int64_t n);
+/* parent element of every particle, int32[num_particles] (tracer->getElementIds()) */
+int pumitally_get_element_ids(pumitally_engine *e, int32_t *out, int64_t n);
+/* current particle positions, double[3*num_particles] AoS (ptcls->get<0>()) */
+int pumitally_get_positions(pumitally_engine *e, double *out, int64_t n3);
+/* face adjacency derived by the engine, int32[4*num_elements], -1 = hull */
+int pumitally_get_adjacency(const pumitally_engine *e, int32_t *out, int64_t n4);
+/* zero the flux and the statistics (new batch) */
+int pumitally_reset_tally(pumitally_engine *e);
+
+typedef struct pumitally_stats {
+  uint64_t segments;      /* tally contributions issued in weighted phases (the metric's unit) */
+  uint64_t tracks;        /* flying particles in weighted phases */
+  uint64_t relocations;   /* tet crossings walked with tallying off (phase 1 + localisation) */
+  uint64_t lost;          /* walks stopped by the iteration limit */
+  uint64_t moves;         /* MoveToNextLocation calls */
+  double kernel_ms;       /* device time of the walk kernels (CUDA events), cumulative */
+  double h2d_bytes;       /* bytes uploaded by the host-pointer entry points, cumulative */
+} pumitally_stats;
+int pumitally_get_stats(pumitally_engine *e, pumitally_stats *out);
+
+/* Per-call output file name for WriteTallyResults (default "fluxresult.vtk"). */
+int pumitally_set_output_name(pumitally_engine *e, const char *filename);
+/* Tuning knobs: name in {"variant","block","sort_every","chunk","aggregate"}. */
+int pumitally_set_option(pumitally_engine *e, const char *name, int64_t value);
+
+/* ---- additive: device-pointer entry points -------------------------------
+ * Same semantics as the host versions, but the arrays already live in device
+ * memory (AoS positions, int8 flying, double weights).  Work is enqueued on
+ * `stream` (a cudaStream_t passed as void*; NULL = the engine's own stream)
+ * and the call returns without synchronising.  d_flying is NOT zeroed. */
+int pumitally_copy_initial_position_device(pumitally_engine *e, const double *d_xyz, int32_t size,
+                                           void *stream);
+int pumitally_move_to_next_location_device(pumitally_engine *e, const double *d_origin,
+                                           const double *d_destinations, const int8_t *d_flying,
+                                           const double *d_weights, int32_t size, void *stream);
+/* device address of the raw flux array (double[num_elements]) */
+double *pumitally_flux_device_ptr(pumitally_engine *e);
+int pumitally_synchronize(pumitally_engine *e);
+
+/* ---- additive: multi-GPU exchange step -----------------------------------
+ * One engine per GPU/process.  Every rank holds a picpart of the mesh and a
+ * slice of the particles; at batch end the per-rank tallies of shared (ghost)
+ * elements are summed with ncclAllReduce over NVLink.  The 128-byte unique id
+ * is produced on rank 0 and distributed by the caller (MPI_Bcast in OpenMC,
+ * torch.distributed in bench.py). */
+int pumitally_nccl_unique_id(uint8_t out_id[128]);
+int pumitally_comm_init(pumitally_engine *e, int32_t rank, int32_t nranks, const uint8_t id[128]);
+int pumitally_allreduce_tally(pumitally_engine *e);
+
+const char *pumitally_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PUMITALLY_C_H */

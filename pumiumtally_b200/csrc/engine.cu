@@ -1,0 +1,379 @@
+// Engine: device state + batch orchestration (see engine.hpp).
+#include "engine.hpp"
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include "vtk_writer.hpp"
+
+namespace ptb {
+
+namespace {
+
+#define PTB_CUDA_OK(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      fprintf(stderr, "[pumitally] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e),    \
+              __FILE__, __LINE__, cudaGetErrorString(_e));                                 \
+      return 1;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+void cuda_or_throw(cudaError_t e, const char *what) {
+  if (e != cudaSuccess)
+    throw std::runtime_error(std::string("[pumitally] ") + what + ": " + cudaGetErrorString(e) +
+                             " (this library has no CPU fallback; a CUDA device is required)");
+}
+
+template <typename T>
+void dev_alloc(T **p, size_t count, const char *what) {
+  cuda_or_throw(cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T)), what);
+}
+
+}  // namespace
+
+Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
+    : mesh_(std::move(mesh)), n_(num_particles) {
+  if (n_ < 0) throw std::runtime_error("[pumitally] num_particles must be >= 0");
+  int ndev = 0;
+  cuda_or_throw(cudaGetDeviceCount(&ndev), "cudaGetDeviceCount");
+  if (ndev <= 0) cuda_or_throw(cudaErrorNoDevice, "no CUDA device");
+  if (device >= 0) {
+    cuda_or_throw(cudaSetDevice(device), "cudaSetDevice");
+    device_ = device;
+  } else {
+    cuda_or_throw(cudaGetDevice(&device_), "cudaGetDevice");
+  }
+  cuda_or_throw(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking), "stream");
+  cuda_or_throw(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking), "stream");
+
+  const size_t E = size_t(mesh_.ntets), N = size_t(n_);
+  dev_alloc(&d_tets_, E, "tet records");
+  dev_alloc(&d_flux_, E, "flux");
+  dev_alloc(&d_volume_, E, "volume");
+  dev_alloc(&d_scratch_, E, "scratch");
+  dev_alloc(&d_px_, N, "px");
+  dev_alloc(&d_py_, N, "py");
+  dev_alloc(&d_pz_, N, "pz");
+  dev_alloc(&d_elem_, N, "elem");
+  // staging buffers (PumiTallyImpl.cpp:36-41; origin and dest get their own so one
+  // upload per array suffices instead of re-using one position buffer twice)
+  dev_alloc(&d_origin_, 3 * N, "origin staging");
+  dev_alloc(&d_dest_, 3 * N, "dest staging");
+  dev_alloc(&d_weights_, N, "weights staging");
+  dev_alloc(&d_flying_, N, "flying staging");
+  dev_alloc(&d_stats_, 1, "stats");
+
+  cuda_or_throw(cudaMemcpy(d_tets_, mesh_.records.data(), E * sizeof(TetRecord), cudaMemcpyHostToDevice), "upload tets");
+  cuda_or_throw(cudaMemcpy(d_volume_, mesh_.volume.data(), E * sizeof(double), cudaMemcpyHostToDevice), "upload volume");
+  cuda_or_throw(cudaMemset(d_flux_, 0, E * sizeof(double)), "memset");
+  cuda_or_throw(cudaMemset(d_stats_, 0, sizeof(DeviceStats)), "memset");
+  // InitializeParticlesInElement0 (PumiTallyImpl.cpp:492-528)
+  cuda_or_throw(launch_init_particles(d_px_, d_py_, d_pz_, d_elem_, n_, mesh_.centroid0[0],
+                                      mesh_.centroid0[1], mesh_.centroid0[2], compute_), "init particles");
+  cuda_or_throw(cudaStreamSynchronize(compute_), "init sync");
+  // the packed records are only needed on the device from here on
+  std::vector<TetRecord>().swap(mesh_.records);
+  printf("[INFO] pumitally-b200: %lld elements, %d particles on CUDA device %d\n",
+         (long long)mesh_.ntets, n_, device_);
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  cudaDeviceSynchronize();
+  if (nccl_comm_) nccl_comm_destroy(nccl_comm_);
+  for (auto &t : timers_free_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (auto &t : timers_busy_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (auto &e : chunk_events_) cudaEventDestroy(e);
+  cudaFree(d_tets_); cudaFree(d_flux_); cudaFree(d_volume_); cudaFree(d_scratch_);
+  cudaFree(d_px_); cudaFree(d_py_); cudaFree(d_pz_); cudaFree(d_elem_);
+  cudaFree(d_origin_); cudaFree(d_dest_); cudaFree(d_weights_); cudaFree(d_flying_);
+  cudaFree(d_stats_);
+  if (compute_) cudaStreamDestroy(compute_);
+  if (copy_) cudaStreamDestroy(copy_);
+}
+
+void Engine::collect_timers(bool wait) {
+  for (size_t k = 0; k < timers_busy_.size();) {
+    TimerPair t = timers_busy_[k];
+    if (wait) cudaEventSynchronize(t.b);
+    if (cudaEventQuery(t.b) == cudaSuccess) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) kernel_ms_ += ms;
+      timers_free_.push_back(t);
+      timers_busy_[k] = timers_busy_.back();
+      timers_busy_.pop_back();
+    } else {
+      ++k;
+    }
+  }
+}
+
+int Engine::launch_range(const double *d_origin, const double *d_dest, const int8_t *d_flying,
+                         const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream,
+                         bool timed) {
+  if (end <= begin) return 0;
+  WalkParams p;
+  p.tets = d_tets_;
+  p.flux = d_flux_;
+  p.px = d_px_; p.py = d_py_; p.pz = d_pz_;
+  p.elem = d_elem_;
+  p.origin = d_origin;
+  p.dest = d_dest;
+  p.flying = d_flying;
+  p.weights = d_weights;
+  p.begin = begin;
+  p.end = end;
+  p.max_iters = int32_t(std::min<int64_t>(mesh_.ntets + 16, INT_MAX));
+  p.stats = d_stats_;
+  TimerPair t{};
+  if (timed) {
+    if (timers_free_.empty()) {
+      PTB_CUDA_OK(cudaEventCreate(&t.a));
+      PTB_CUDA_OK(cudaEventCreate(&t.b));
+    } else {
+      t = timers_free_.back();
+      timers_free_.pop_back();
+    }
+    PTB_CUDA_OK(cudaEventRecord(t.a, stream));
+  }
+  PTB_CUDA_OK(launch_walk(p, variant_, block_, stream));
+  if (timed) {
+    PTB_CUDA_OK(cudaEventRecord(t.b, stream));
+    timers_busy_.push_back(t);
+  }
+  return 0;
+}
+
+bool Engine::host_is_pinned(const void *p) const {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// CopyInitialPositionToBuffer + MoveToInitialLocation (PumiTallyImpl.cpp:54-64, 195-221)
+int Engine::copy_initial_position(const double *xyz, int32_t size) {
+  if (int64_t(size) != 3 * int64_t(n_)) {
+    fprintf(stderr, "[pumitally] ERROR: CopyInitialPosition size %d != 3 * num_particles (%d)\n", size, n_);
+    return 1;
+  }
+  if (initialized_) {
+    fprintf(stderr, "[pumitally] ERROR: CopyInitialPosition may only be called once\n");
+    return 1;
+  }
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  PTB_CUDA_OK(cudaMemcpyAsync(d_origin_, xyz, size_t(size) * sizeof(double), cudaMemcpyHostToDevice, compute_));
+  h2d_bytes_ += double(size) * sizeof(double);
+  if (launch_range(d_origin_, nullptr, nullptr, nullptr, 0, n_, compute_, true)) return 1;
+  PTB_CUDA_OK(cudaStreamSynchronize(compute_));
+  initialized_ = true;
+  return 0;
+}
+
+int Engine::copy_initial_position_device(const double *d_xyz, int32_t size, cudaStream_t stream) {
+  if (int64_t(size) != 3 * int64_t(n_) || initialized_) {
+    fprintf(stderr, "[pumitally] ERROR: CopyInitialPosition: bad size or called twice\n");
+    return 1;
+  }
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  if (launch_range(d_xyz, nullptr, nullptr, nullptr, 0, n_, pick(stream), true)) return 1;
+  initialized_ = true;
+  return 0;
+}
+
+// MoveToNextLocation (PumiTallyImpl.cpp:66-149), host pointers.  The four
+// uploads are cut into particle ranges; range k is walked while range k+1 is
+// still on the wire.
+int Engine::move_to_next_location(const double *origin, const double *dest, int8_t *flying,
+                                  const double *weights, int32_t size) {
+  if (int64_t(size) != 3 * int64_t(n_)) {
+    fprintf(stderr, "[pumitally] ERROR: MoveToNextLocation size %d != 3 * num_particles (%d)\n", size, n_);
+    return 1;
+  }
+  if (!initialized_) {
+    fprintf(stderr, "[pumitally] ERROR: MoveToNextLocation before CopyInitialPosition\n");
+    return 1;
+  }
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  collect_timers(false);
+  const int nchunks = n_ ? (n_ + chunk_ - 1) / chunk_ : 0;
+  while (int(chunk_events_.size()) < nchunks + 2) {
+    cudaEvent_t e;
+    PTB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    chunk_events_.push_back(e);
+  }
+  cudaEvent_t ev_prev_done = chunk_events_[nchunks], ev_fly = chunk_events_[nchunks + 1];
+  // staging buffers are free once the previous move's kernels have finished
+  PTB_CUDA_OK(cudaEventRecord(ev_prev_done, compute_));
+  PTB_CUDA_OK(cudaStreamWaitEvent(copy_, ev_prev_done, 0));
+  PTB_CUDA_OK(cudaMemcpyAsync(d_flying_, flying, size_t(n_), cudaMemcpyHostToDevice, copy_));
+  PTB_CUDA_OK(cudaEventRecord(ev_fly, copy_));
+  for (int k = 0; k < nchunks; ++k) {
+    const int32_t b = int32_t(int64_t(k) * chunk_), e = int32_t(std::min<int64_t>(n_, int64_t(b) + chunk_));
+    const size_t cnt = size_t(e - b);
+    PTB_CUDA_OK(cudaMemcpyAsync(d_origin_ + 3 * size_t(b), origin + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+    PTB_CUDA_OK(cudaMemcpyAsync(d_dest_ + 3 * size_t(b), dest + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+    PTB_CUDA_OK(cudaMemcpyAsync(d_weights_ + b, weights + b, cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+    PTB_CUDA_OK(cudaEventRecord(chunk_events_[k], copy_));
+    PTB_CUDA_OK(cudaStreamWaitEvent(compute_, chunk_events_[k], 0));
+    if (launch_range(d_origin_, d_dest_, d_flying_, d_weights_, b, e, compute_, true)) return 1;
+  }
+  h2d_bytes_ += double(n_) * (2 * 24 + 8 + 1);
+  // reset the caller's flags once they are on the device (PumiTallyImpl.cpp:169-172)
+  PTB_CUDA_OK(cudaEventSynchronize(ev_fly));
+  if (n_) std::memset(flying, 0, size_t(n_));
+  // caller may reuse its buffers on return (reference: blocking deep_copy)
+  PTB_CUDA_OK(cudaStreamSynchronize(copy_));
+  ++moves_;
+  return 0;
+}
+
+int Engine::move_to_next_location_device(const double *d_origin, const double *d_dest,
+                                         const int8_t *d_flying, const double *d_weights,
+                                         int32_t size, cudaStream_t stream) {
+  if (int64_t(size) != 3 * int64_t(n_) || !initialized_) {
+    fprintf(stderr, "[pumitally] ERROR: MoveToNextLocation(device): bad size or not initialised\n");
+    return 1;
+  }
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  collect_timers(false);
+  if (launch_range(d_origin, d_dest, d_flying, d_weights, 0, n_, pick(stream), true)) return 1;
+  ++moves_;
+  return 0;
+}
+
+int Engine::synchronize() {
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  PTB_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int Engine::get_flux(double *out, int64_t n) {
+  if (n != mesh_.ntets) return 1;
+  if (synchronize()) return 1;
+  PTB_CUDA_OK(cudaMemcpy(out, d_flux_, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// NormalizeFlux (PumiTallyImpl.cpp:382-409)
+int Engine::get_normalized_flux(double *out_flux, double *out_volume, int64_t n) {
+  if (n != mesh_.ntets) return 1;
+  if (synchronize()) return 1;
+  if (out_flux) {
+    PTB_CUDA_OK(launch_normalize(d_flux_, d_volume_, d_scratch_, n, compute_));
+    PTB_CUDA_OK(cudaStreamSynchronize(compute_));
+    PTB_CUDA_OK(cudaMemcpy(out_flux, d_scratch_, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (out_volume) std::memcpy(out_volume, mesh_.volume.data(), size_t(n) * sizeof(double));
+  return 0;
+}
+
+int Engine::get_element_ids(int32_t *out, int64_t n) {
+  if (n != n_) return 1;
+  if (synchronize()) return 1;
+  PTB_CUDA_OK(cudaMemcpy(out, d_elem_, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int Engine::get_positions(double *out, int64_t n3) {
+  if (n3 != 3 * int64_t(n_)) return 1;
+  if (synchronize()) return 1;
+  std::vector<double> tmp(size_t(n_) * 3);
+  PTB_CUDA_OK(cudaMemcpy(tmp.data(), d_px_, size_t(n_) * 8, cudaMemcpyDeviceToHost));
+  PTB_CUDA_OK(cudaMemcpy(tmp.data() + n_, d_py_, size_t(n_) * 8, cudaMemcpyDeviceToHost));
+  PTB_CUDA_OK(cudaMemcpy(tmp.data() + 2 * size_t(n_), d_pz_, size_t(n_) * 8, cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n_; ++i) {
+    out[3 * i] = tmp[i];
+    out[3 * i + 1] = tmp[size_t(n_) + i];
+    out[3 * i + 2] = tmp[2 * size_t(n_) + i];
+  }
+  return 0;
+}
+
+int Engine::reset_tally() {
+  if (synchronize()) return 1;
+  collect_timers(true);
+  PTB_CUDA_OK(cudaMemset(d_flux_, 0, size_t(mesh_.ntets) * sizeof(double)));
+  PTB_CUDA_OK(cudaMemset(d_stats_, 0, sizeof(DeviceStats)));
+  kernel_ms_ = 0.0;
+  h2d_bytes_ = 0.0;
+  moves_ = 0;
+  return 0;
+}
+
+int Engine::get_stats(EngineStats *out) {
+  if (synchronize()) return 1;
+  collect_timers(true);
+  DeviceStats s;
+  PTB_CUDA_OK(cudaMemcpy(&s, d_stats_, sizeof(s), cudaMemcpyDeviceToHost));
+  out->segments = s.segments;
+  out->tracks = s.tracks;
+  out->relocations = s.relocations;
+  out->lost = s.lost;
+  out->moves = moves_;
+  out->kernel_ms = kernel_ms_;
+  out->h2d_bytes = h2d_bytes_;
+  if (s.lost)  // reference wording, PumiTallyImpl.cpp:455-458
+    printf("ERROR: Not all particles are found. May need more loops in search\n");
+  return 0;
+}
+
+int Engine::set_option(const std::string &name, int64_t v) {
+  if (name == "variant") {
+    if (v < 0 || v >= kNumVariants) return 1;
+    variant_ = int(v);
+  } else if (name == "block") {
+    if (v != 64 && v != 128 && v != 256) return 1;
+    block_ = int(v);
+  } else if (name == "chunk") {
+    if (v < 1024) return 1;
+    chunk_ = int32_t(std::min<int64_t>(v, INT_MAX));
+  } else {
+    return 1;
+  }
+  return 0;
+}
+
+// FinalizeTallies (PumiTallyImpl.cpp:411-416)
+int Engine::write_tally_results() {
+  std::vector<double> nf(size_t(mesh_.ntets));
+  if (get_normalized_flux(nf.data(), nullptr, mesh_.ntets)) return 1;
+  std::string err;
+  if (!write_vtk_dataset(output_name_, mesh_, nf, mesh_.volume, rank_, nranks_, &err)) {
+    fprintf(stderr, "[pumitally] ERROR: %s\n", err.c_str());
+    return 1;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ multi-GPU
+
+int Engine::comm_init(int rank, int nranks, const uint8_t id[128]) {
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  if (nccl_comm_) return 1;
+  if (nccl_comm_init_rank(&nccl_comm_, nranks, id, rank)) return 1;
+  rank_ = rank;
+  nranks_ = nranks;
+  return 0;
+}
+
+// Batch-end exchange: sum the per-rank tallies.  Every rank holds a full-buffer
+// picpart (all elements are ghosts of every other rank), so the ghost-layer
+// array is the whole flux array.
+int Engine::allreduce_tally() {
+  if (!nccl_comm_) return nranks_ == 1 ? 0 : 1;
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  PTB_CUDA_OK(cudaDeviceSynchronize());
+  if (nccl_allreduce_sum_f64(nccl_comm_, d_flux_, size_t(mesh_.ntets), compute_)) return 1;
+  PTB_CUDA_OK(cudaStreamSynchronize(compute_));
+  return 0;
+}
+
+}  // namespace ptb

@@ -1,0 +1,108 @@
+// Batch orchestration of the tally engine: owns the device-resident mesh
+// tables, particle state, staging buffers, streams and the optional NCCL
+// communicator.  Plays the role of the reference's PumiTallyImpl
+// (reference: src/pumitally/PumiTallyImpl.h:154-221) minus everything Kokkos /
+// pumi-pic / Omega_h.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "tet_mesh.hpp"
+#include "walk_kernels.hpp"
+
+namespace ptb {
+
+struct EngineStats {
+  uint64_t segments = 0, tracks = 0, relocations = 0, lost = 0, moves = 0;
+  double kernel_ms = 0.0;
+  double h2d_bytes = 0.0;
+};
+
+class Engine {
+ public:
+  // Throws std::runtime_error when no CUDA device is usable: there is no CPU path.
+  Engine(HostMesh &&mesh, int32_t num_particles, int device);
+  ~Engine();
+  Engine(const Engine &) = delete;
+  Engine &operator=(const Engine &) = delete;
+
+  int64_t num_elements() const { return mesh_.ntets; }
+  int32_t num_particles() const { return n_; }
+  const HostMesh &mesh() const { return mesh_; }
+
+  // Host-pointer entry points (reference semantics; block until inputs are consumed).
+  int copy_initial_position(const double *xyz, int32_t size);
+  int move_to_next_location(const double *origin, const double *dest, int8_t *flying,
+                            const double *weights, int32_t size);
+  // Device-pointer entry points (enqueue only).
+  int copy_initial_position_device(const double *d_xyz, int32_t size, cudaStream_t stream);
+  int move_to_next_location_device(const double *d_origin, const double *d_dest,
+                                   const int8_t *d_flying, const double *d_weights, int32_t size,
+                                   cudaStream_t stream);
+
+  int get_flux(double *out, int64_t n);
+  int get_normalized_flux(double *out_flux, double *out_volume, int64_t n);
+  int get_element_ids(int32_t *out, int64_t n);
+  int get_positions(double *out, int64_t n3);
+  int reset_tally();
+  int get_stats(EngineStats *out);
+  int synchronize();
+  double *flux_device_ptr() { return d_flux_; }
+  int set_option(const std::string &name, int64_t value);
+  void set_output_name(const std::string &s) { output_name_ = s; }
+  int write_tally_results();
+
+  // multi-GPU exchange step
+  int comm_init(int rank, int nranks, const uint8_t id[128]);
+  int allreduce_tally();
+
+ private:
+  cudaStream_t pick(cudaStream_t s) const { return s ? s : compute_; }
+  int launch_range(const double *d_origin, const double *d_dest, const int8_t *d_flying,
+                   const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream,
+                   bool timed);
+  bool host_is_pinned(const void *p) const;
+  void collect_timers(bool wait);
+
+  HostMesh mesh_;
+  int32_t n_ = 0;
+  int device_ = 0;
+  bool initialized_ = false;  // is_pumipic_initialized (PumiTallyImpl.h:168)
+  uint64_t moves_ = 0;        // iter_count (PumiTallyImpl.h:169)
+  std::string output_name_ = "fluxresult.vtk";
+
+  // options
+  int variant_ = kVariantLdg;
+  int block_ = 128;
+  int32_t chunk_ = 1 << 20;  // particles per H2D/compute pipeline stage
+
+  // device memory
+  TetRecord *d_tets_ = nullptr;
+  double *d_flux_ = nullptr, *d_volume_ = nullptr, *d_scratch_ = nullptr;
+  double *d_px_ = nullptr, *d_py_ = nullptr, *d_pz_ = nullptr;
+  int32_t *d_elem_ = nullptr;
+  double *d_origin_ = nullptr, *d_dest_ = nullptr, *d_weights_ = nullptr;  // staging
+  int8_t *d_flying_ = nullptr;
+  DeviceStats *d_stats_ = nullptr;
+
+  cudaStream_t compute_ = nullptr, copy_ = nullptr;
+  struct TimerPair { cudaEvent_t a, b; };
+  std::vector<TimerPair> timers_free_, timers_busy_;
+  std::vector<cudaEvent_t> chunk_events_;
+  double kernel_ms_ = 0.0, h2d_bytes_ = 0.0;
+
+  // NCCL (resolved with dlopen at comm_init time)
+  void *nccl_comm_ = nullptr;
+  int rank_ = 0, nranks_ = 1;
+};
+
+// NCCL entry points resolved with dlopen at run time (nccl_dl.cpp)
+int nccl_get_unique_id(uint8_t out[128]);
+int nccl_comm_init_rank(void **comm, int nranks, const uint8_t id[128], int rank);
+int nccl_allreduce_sum_f64(void *comm, double *buf, size_t count, cudaStream_t stream);
+void nccl_comm_destroy(void *comm);
+
+}  // namespace ptb

@@ -1,0 +1,80 @@
+// pumitally::PumiTally -- the C++ class the OpenMC fork links against,
+// implemented over the C ABI (include/pumitally_c.h).  Mirrors the reference
+// facade's behaviour: forward each call, accumulate wall-clock time per phase,
+// print the [TIME] block after WriteTallyResults
+// (reference: src/pumitally/PumiTally.cpp:16-60, PumiTallyImpl.cpp:22-29).
+#include "pumitally/PumiTally.h"
+
+#include <chrono>
+#include <cstdio>
+
+#include "pumitally_c.h"
+
+namespace pumitally {
+
+// reference: TallyTimes, PumiTallyImpl.h:18-27
+struct TallyTimes {
+  double initialization_time = 0.0;
+  double total_time_to_tally = 0.0;
+  double vtk_file_write_time = 0.0;
+  void PrintTimes() const {
+    printf("\n");
+    printf("[TIME] Initialization time     : %f seconds\n", initialization_time);
+    printf("[TIME] Total time to tally     : %f seconds\n", total_time_to_tally);
+    printf("[TIME] VTK file write time     : %f seconds\n", vtk_file_write_time);
+    printf("[TIME] Total PUMI-Tally time   : %f seconds\n",
+           initialization_time + total_time_to_tally + vtk_file_write_time);
+  }
+};
+
+struct PumiTallyImpl {
+  pumitally_engine *engine = nullptr;
+  TallyTimes tally_times;
+  ~PumiTallyImpl() { pumitally_destroy(engine); }
+};
+
+namespace {
+struct ScopedTimer {
+  double &acc;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit ScopedTimer(double &a) : acc(a) {}
+  ~ScopedTimer() {
+    acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+}  // namespace
+
+PumiTally::PumiTally(const std::string &mesh_filename, const int32_t num_particles, int &argc,
+                     char **&argv)
+    : pimpl_(std::make_unique<PumiTallyImpl>()) {
+  pimpl_->engine = pumitally_create(mesh_filename.c_str(), num_particles, &argc, &argv);
+  if (!pimpl_->engine)
+    fprintf(stderr, "[ERROR] pumitally: engine construction failed; every later call is a no-op\n");
+}
+
+PumiTally::~PumiTally() { pimpl_.reset(nullptr); }
+
+void PumiTally::CopyInitialPosition(double *init_particle_positions, const std::int32_t size) const {
+  ScopedTimer t(pimpl_->tally_times.initialization_time);
+  pumitally_copy_initial_position(pimpl_->engine, init_particle_positions, size);
+}
+
+void PumiTally::MoveToNextLocation(double *particle_origin, double *particle_destinations,
+                                   int8_t *flying, double *weights, const std::int32_t size) const {
+  ScopedTimer t(pimpl_->tally_times.total_time_to_tally);
+  pumitally_move_to_next_location(pimpl_->engine, particle_origin, particle_destinations, flying,
+                                  weights, size);
+  // kernels of the last particle range may still be in flight here; the time
+  // they take is charged to the next call that waits on them, as with the
+  // reference's un-fenced Kokkos launches (PumiTallyImpl.cpp:146-148).
+}
+
+void PumiTally::WriteTallyResults() const {
+  {
+    ScopedTimer t(pimpl_->tally_times.vtk_file_write_time);
+    pumitally_write_tally_results(pimpl_->engine);
+  }
+  pimpl_->tally_times.PrintTimes();
+}
+
+}  // namespace pumitally

@@ -1,0 +1,242 @@
+// Host-side mesh preparation: generators, raw-file reader, face adjacency,
+// volumes and the packed 128-byte tet records the walk kernels consume.
+#include "tet_mesh.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <sys/stat.h>
+
+namespace ptb {
+
+namespace {
+
+inline void sort3(int32_t &a, int32_t &b, int32_t &c) {
+  if (a > b) std::swap(a, b);
+  if (b > c) std::swap(b, c);
+  if (a > b) std::swap(a, b);
+}
+
+inline uint64_t dbits(double x) {
+  uint64_t u;
+  std::memcpy(&u, &x, 8);
+  return u;
+}
+inline double bdouble(uint64_t u) {
+  double x;
+  std::memcpy(&x, &u, 8);
+  return x;
+}
+
+struct FaceKey {
+  int32_t a, b, c;
+  int32_t slot;  // 4*tet + face
+  bool operator<(const FaceKey &o) const {
+    if (a != o.a) return a < o.a;
+    if (b != o.b) return b < o.b;
+    return c < o.c;
+  }
+  bool same(const FaceKey &o) const { return a == o.a && b == o.b && c == o.c; }
+};
+
+}  // namespace
+
+// Hex corner numbering and the six tets around the 0-6 diagonal; local element
+// k takes entry (k+1)%6 of the cyclic list so that element 0 is {y>=x>=z}, the
+// ordering the reference's known-answer test pins for Omega_h::build_box
+// (test/test_pumi_tally_impl_methods.cpp:34-35, 83).
+void build_kuhn_box(int nx, int ny, int nz, double lx, double ly, double lz,
+                    std::vector<double> *coords, std::vector<int32_t> *t2v) {
+  static const int corner[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0},
+                                   {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+  static const int cyc[6][4] = {{0, 1, 2, 6}, {0, 2, 3, 6}, {0, 3, 7, 6},
+                                {0, 7, 4, 6}, {0, 4, 5, 6}, {0, 5, 1, 6}};
+  const int64_t nvx = nx + 1, nvy = ny + 1, nvz = nz + 1;
+  coords->resize(3 * nvx * nvy * nvz);
+  for (int64_t k = 0; k < nvz; ++k)
+    for (int64_t j = 0; j < nvy; ++j)
+      for (int64_t i = 0; i < nvx; ++i) {
+        int64_t v = (k * nvy + j) * nvx + i;
+        (*coords)[3 * v + 0] = (i == nx) ? lx : double(i) * (lx / nx);
+        (*coords)[3 * v + 1] = (j == ny) ? ly : double(j) * (ly / ny);
+        (*coords)[3 * v + 2] = (k == nz) ? lz : double(k) * (lz / nz);
+      }
+  t2v->resize(size_t(24) * nx * ny * nz);
+  size_t w = 0;
+  for (int64_t k = 0; k < nz; ++k)
+    for (int64_t j = 0; j < ny; ++j)
+      for (int64_t i = 0; i < nx; ++i) {
+        int32_t c[8];
+        for (int q = 0; q < 8; ++q)
+          c[q] = int32_t(((k + corner[q][2]) * nvy + (j + corner[q][1])) * nvx + (i + corner[q][0]));
+        for (int t = 0; t < 6; ++t) {
+          const int *tt = cyc[(t + 1) % 6];
+          for (int q = 0; q < 4; ++q) (*t2v)[w++] = c[tt[q]];
+        }
+      }
+}
+
+bool read_raw_mesh(const std::string &path, std::vector<double> *coords,
+                   std::vector<int32_t> *t2v, std::string *err) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) { *err = "cannot open " + path; return false; }
+  char magic[8];
+  f.read(magic, 8);
+  if (!f || std::memcmp(magic, "PUMITB2\0", 8) != 0) { *err = "not a raw mesh file: " + path; return false; }
+  int64_t n[2];
+  f.read(reinterpret_cast<char *>(n), 16);
+  if (!f || n[0] <= 0 || n[1] <= 0) { *err = "bad raw mesh header"; return false; }
+  coords->resize(size_t(3) * n[0]);
+  t2v->resize(size_t(4) * n[1]);
+  f.read(reinterpret_cast<char *>(coords->data()), std::streamsize(coords->size() * 8));
+  f.read(reinterpret_cast<char *>(t2v->data()), std::streamsize(t2v->size() * 4));
+  if (!f) { *err = "truncated raw mesh file"; return false; }
+  return true;
+}
+
+bool HostMesh::load(const std::string &spec, std::string *err) {
+  coords.clear();
+  t2v.clear();
+  if (spec.empty()) {
+    // reference wording: PumiTallyImpl.cpp:558-561
+    *err = "Omega_h mesh for PumiPIC is not given. Provide --ohMesh = <osh file>";
+    return false;
+  }
+  if (spec.rfind("box:", 0) == 0) {
+    double v[6] = {0, 0, 0, -1, -1, -1};
+    int n = 0;
+    std::stringstream ss(spec.substr(4));
+    std::string tok;
+    while (n < 6 && std::getline(ss, tok, ',')) v[n++] = std::atof(tok.c_str());
+    if (n != 3 && n != 6) { *err = "box spec is box:nx,ny,nz[,lx,ly,lz]"; return false; }
+    int nx = int(v[0]), ny = int(v[1]), nz = int(v[2]);
+    if (nx < 1 || ny < 1 || nz < 1) { *err = "box spec needs nx,ny,nz >= 1"; return false; }
+    if (int64_t(nx) * ny * nz * 6 > int64_t(2000000000)) { *err = "box too large for int32 element ids"; return false; }
+    double lx = n == 6 ? v[3] : nx, ly = n == 6 ? v[4] : ny, lz = n == 6 ? v[5] : nz;
+    build_kuhn_box(nx, ny, nz, lx, ly, lz, &coords, &t2v);
+  } else {
+    struct stat st;
+    if (stat(spec.c_str(), &st) != 0) { *err = "mesh not found: " + spec; return false; }
+    bool ok = S_ISDIR(st.st_mode) ? read_osh_mesh(spec, &coords, &t2v, err)
+                                  : read_raw_mesh(spec, &coords, &t2v, err);
+    if (!ok) return false;
+  }
+  nverts = int64_t(coords.size() / 3);
+  ntets = int64_t(t2v.size() / 4);
+  return finalize(err);
+}
+
+bool HostMesh::from_arrays(const double *c, int64_t nv, const int32_t *t, int64_t nt,
+                           std::string *err) {
+  if (!c || !t || nv < 4 || nt < 1) { *err = "empty mesh"; return false; }
+  coords.assign(c, c + 3 * nv);
+  t2v.assign(t, t + 4 * nt);
+  nverts = nv;
+  ntets = nt;
+  return finalize(err);
+}
+
+bool HostMesh::finalize(std::string *err) {
+  if (ntets >= int64_t(0x7fffffff) / 4) { *err = "too many tets for int32 face slots"; return false; }
+  for (size_t i = 0; i < t2v.size(); ++i)
+    if (t2v[i] < 0 || t2v[i] >= nverts) { *err = "tet2vert index out of range"; return false; }
+
+  for (int d = 0; d < 3; ++d) { bbox_lo[d] = coords[d]; bbox_hi[d] = coords[d]; }
+  for (int64_t v = 0; v < nverts; ++v)
+    for (int d = 0; d < 3; ++d) {
+      bbox_lo[d] = std::min(bbox_lo[d], coords[3 * v + d]);
+      bbox_hi[d] = std::max(bbox_hi[d], coords[3 * v + d]);
+    }
+  for (int d = 0; d < 3; ++d) {
+    double s = 0;
+    for (int i = 0; i < 4; ++i) s += coords[3 * size_t(t2v[i]) + d];
+    centroid0[d] = s / 4.0;
+  }
+
+  // ---- face adjacency: sort the 4E (sorted vertex triple, slot) keys --------
+  const size_t nf = size_t(4) * ntets;
+  t2t.assign(nf, -1);
+  {
+    std::vector<FaceKey> keys(nf);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < ntets; ++e)
+      for (int f = 0; f < 4; ++f) {
+        int32_t v[3];
+        int k = 0;
+        for (int i = 0; i < 4; ++i)
+          if (i != f) v[k++] = t2v[4 * e + i];
+        sort3(v[0], v[1], v[2]);
+        keys[4 * e + f] = FaceKey{v[0], v[1], v[2], int32_t(4 * e + f)};
+      }
+    std::sort(keys.begin(), keys.end());
+    for (size_t i = 0; i < nf;) {
+      size_t j = i + 1;
+      while (j < nf && keys[i].same(keys[j])) ++j;
+      if (j - i == 2) {
+        t2t[keys[i].slot] = keys[i + 1].slot / 4;
+        t2t[keys[i + 1].slot] = keys[i].slot / 4;
+      } else if (j - i > 2) {
+        *err = "non-manifold mesh: a face is shared by more than two tets";
+        return false;
+      }
+      i = j;
+    }
+  }
+
+  // ---- volumes + packed records ----------------------------------------------
+  volume.resize(ntets);
+  records.resize(ntets);
+  bool degenerate = false;
+#pragma omp parallel for schedule(static) reduction(|| : degenerate)
+  for (int64_t e = 0; e < ntets; ++e) {
+    const double *V[4];
+    for (int i = 0; i < 4; ++i) V[i] = &coords[3 * size_t(t2v[4 * e + i])];
+    {
+      double a[3], b[3], c[3];
+      for (int d = 0; d < 3; ++d) { a[d] = V[1][d] - V[0][d]; b[d] = V[2][d] - V[0][d]; c[d] = V[3][d] - V[0][d]; }
+      double det = a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) +
+                   a[2] * (b[0] * c[1] - b[1] * c[0]);
+      volume[e] = std::fabs(det) / 6.0;
+      if (!(volume[e] > 0.0)) degenerate = true;
+    }
+    TetRecord &r = records[e];
+    for (int f = 0; f < 4; ++f) {
+      int32_t v[3];
+      int k = 0;
+      for (int i = 0; i < 4; ++i)
+        if (i != f) v[k++] = t2v[4 * e + i];
+      sort3(v[0], v[1], v[2]);
+      const double *A = &coords[3 * size_t(v[0])], *B = &coords[3 * size_t(v[1])],
+                   *C = &coords[3 * size_t(v[2])];
+      double ab[3], ac[3], n[3];
+      for (int d = 0; d < 3; ++d) { ab[d] = B[d] - A[d]; ac[d] = C[d] - A[d]; }
+      n[0] = ab[1] * ac[2] - ab[2] * ac[1];
+      n[1] = ab[2] * ac[0] - ab[0] * ac[2];
+      n[2] = ab[0] * ac[1] - ab[1] * ac[0];
+      double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      if (!(len > 0.0)) { degenerate = true; len = 1.0; }
+      double p[4];
+      p[0] = n[0] / len; p[1] = n[1] / len; p[2] = n[2] / len;
+      p[3] = p[0] * A[0] + p[1] * A[1] + p[2] * A[2];
+      // canonical truncation: identical for both tets sharing the face
+      for (int q = 0; q < 4; ++q) p[q] = bdouble(dbits(p[q]) & ~uint64_t(0xff));
+      // orient outward: the opposite vertex must satisfy n.x < c
+      const double *P = V[f];
+      double side = p[0] * P[0] + p[1] * P[1] + p[2] * P[2] - p[3];
+      if (side > 0.0)
+        for (int q = 0; q < 4; ++q) p[q] = -p[q];
+      else if (side == 0.0)
+        degenerate = true;
+      uint32_t nb = uint32_t(t2t[4 * e + f]);
+      for (int q = 0; q < 4; ++q)
+        r.d[4 * f + q] = bdouble(dbits(p[q]) | uint64_t((nb >> (8 * q)) & 0xffu));
+    }
+  }
+  if (degenerate) { *err = "mesh contains a degenerate (zero-volume) tet"; return false; }
+  return true;
+}
+
+}  // namespace ptb

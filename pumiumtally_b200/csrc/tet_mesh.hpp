@@ -1,0 +1,60 @@
+// Host-side tet mesh container and the packed device record format.
+//
+// Replaces what the reference obtains from Omega_h (mesh read
+// PumiTallyImpl.cpp:553-568, coords / tet->vert adjacency
+// PumiTallyImpl.cpp:384-385, 495-496) and from pumi-pic (face adjacency used by
+// the external tracer).  Nothing here is on the per-step hot path.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace ptb {
+
+// One tet = one 128-byte, 128-byte-aligned record = exactly one L2 line and
+// one cp.async.bulk transfer:
+//
+//   d[4f+0..2] = outward normal of the face opposite local vertex f
+//   d[4f+3]    = plane offset c  (n.x == c on the face, n.x < c inside)
+//
+// Both tets that share a face carry the *same* plane up to an exact sign flip
+// (it is built once from the three face vertices in ascending global id), so
+// the ray parameter of a crossing is bit-identical seen from either side and
+// the walk is watertight.  The low 8 bits of each of the 16 mantissas do not
+// hold geometry: the four low bytes of face f's four doubles spell the int32
+// id of the neighbour across face f (-1 = hull).  The kernel masks them off
+// (2^-44 relative truncation, applied before the sign flip so both sides still
+// agree bit for bit).
+struct alignas(128) TetRecord {
+  double d[16];
+};
+static_assert(sizeof(TetRecord) == 128, "TetRecord must be one 128-byte line");
+
+struct HostMesh {
+  int64_t nverts = 0;
+  int64_t ntets = 0;
+  std::vector<double> coords;    // [3*nverts]
+  std::vector<int32_t> t2v;      // [4*ntets]
+  std::vector<int32_t> t2t;      // [4*ntets], neighbour across face opposite vertex f, -1 hull
+  std::vector<double> volume;    // [ntets]
+  std::vector<TetRecord> records;  // [ntets]
+  double centroid0[3] = {0, 0, 0};  // centroid of element 0 (PumiTallyImpl.cpp:500-509)
+  double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};
+
+  // "box:nx,ny,nz[,lx,ly,lz]" | raw mesh file | Omega_h .osh directory.
+  bool load(const std::string &spec, std::string *err);
+  bool from_arrays(const double *coords, int64_t nverts, const int32_t *tet2vert, int64_t ntets,
+                   std::string *err);
+  // adjacency + volumes + packed records; called by load()/from_arrays().
+  bool finalize(std::string *err);
+};
+
+// Generators / readers (tet_mesh.cpp, osh_reader.cpp)
+void build_kuhn_box(int nx, int ny, int nz, double lx, double ly, double lz,
+                    std::vector<double> *coords, std::vector<int32_t> *t2v);
+bool read_raw_mesh(const std::string &path, std::vector<double> *coords,
+                   std::vector<int32_t> *t2v, std::string *err);
+bool read_osh_mesh(const std::string &dir, std::vector<double> *coords,
+                   std::vector<int32_t> *t2v, std::string *err);
+
+}  // namespace ptb

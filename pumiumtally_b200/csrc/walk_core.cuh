@@ -1,0 +1,232 @@
+// Per-tet step of the adjacency walk: decode a packed TetRecord, find the exit
+// face of the ray, decide reached / crossed / left-the-hull.
+//
+// This is the arithmetic the reference delegates to the external pumi-pic
+// tracer (call site PumiTallyImpl.cpp:454; contract PumiTallyImpl.h:74-85)
+// fused with the reference's own per-iteration functor
+// (PumiTallyImpl.cpp:297-316): tally the piece inside the current tet
+// (EvaluateFlux :352-380), clip at the hull (ApplyVacuumBC :256-286), advance
+// (UpdateCurrentElement :243-254).  prev_xpoint (:322-350) is the register
+// `tcur`.
+//
+// The functions are __host__ __device__ only so that tests/ can compile them
+// with g++ and check the logic on a machine without a GPU; the library never
+// runs them on the host.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define PTB_HD __host__ __device__ __forceinline__
+#define PTB_UNROLL _Pragma("unroll")
+#else
+#define PTB_HD inline
+#define PTB_UNROLL
+#include <cmath>
+#include <cstring>
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define PTB_LDG(p) __ldg(p)
+#define PTB_TALLY_ADD(ptr, v) atomicAdd((ptr), (v))  // RED.E.ADD.F64 (Kokkos::atomic_add, Impl.cpp:376)
+#else
+#define PTB_LDG(p) (*(p))
+#define PTB_TALLY_ADD(ptr, v) (*(ptr) += (v))  // test-only host build is single threaded
+#endif
+
+namespace ptb {
+
+// low/high 32-bit halves of a double, portable between nvcc device code and g++
+PTB_HD uint32_t dlo(double x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__double2loint(x);
+#else
+  uint64_t u; memcpy(&u, &x, 8); return (uint32_t)u;
+#endif
+}
+PTB_HD double dmask(double x) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(x), __double2loint(x) & (int)0xffffff00);
+#else
+  uint64_t u; memcpy(&u, &x, 8); u &= ~uint64_t(0xff); memcpy(&x, &u, 8); return x;
+#endif
+}
+
+// Decoded face planes of one tet.
+struct TetPlanes {
+  double nx[4], ny[4], nz[4], c[4];
+  int32_t nbr[4];
+};
+
+// r = the 16 raw doubles of a TetRecord.
+PTB_HD void decode_record(const double (&r)[16], TetPlanes &t) {
+PTB_UNROLL
+  for (int f = 0; f < 4; ++f) {
+    uint32_t b0 = dlo(r[4 * f + 0]) & 0xffu, b1 = dlo(r[4 * f + 1]) & 0xffu;
+    uint32_t b2 = dlo(r[4 * f + 2]) & 0xffu, b3 = dlo(r[4 * f + 3]) & 0xffu;
+    t.nbr[f] = (int32_t)(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
+    t.nx[f] = dmask(r[4 * f + 0]);
+    t.ny[f] = dmask(r[4 * f + 1]);
+    t.nz[f] = dmask(r[4 * f + 2]);
+    t.c[f] = dmask(r[4 * f + 3]);
+  }
+}
+
+// Ray x(t) = o + t*u, t in [0,1].  Returns the smallest exit parameter over
+// the faces the ray leaves through (n.u > 0) and that face's neighbour; texit
+// = +inf when no face qualifies (zero-length ray).  Numerator and denominator
+// depend only on the plane and the ray, never on the tet, so both tets sharing
+// a face compute the identical quotient.
+//
+// The minimum is selected by cross-multiplication (num_a*den_b < num_b*den_a,
+// both den > 0) so a crossing costs one fp64 division instead of four; ties
+// within rounding pick either face, which only reorders a zero-length piece.
+PTB_HD void exit_face(const TetPlanes &t, double ox, double oy, double oz, double ux, double uy,
+                      double uz, double &texit, int32_t &next) {
+  double bnum = 1.0, bden = 0.0;  // t = +inf
+  int32_t nb = -2;
+PTB_UNROLL
+  for (int f = 0; f < 4; ++f) {
+    const double den = t.nx[f] * ux + t.ny[f] * uy + t.nz[f] * uz;
+    const double num = t.c[f] - (t.nx[f] * ox + t.ny[f] * oy + t.nz[f] * oz);
+    const bool take = (den > 0.0) && (num * bden < bnum * den);
+    bnum = take ? num : bnum;
+    bden = take ? den : bden;
+    nb = take ? t.nbr[f] : nb;
+  }
+  // bnum >= bden  <=>  t >= 1: destination lies in this tet, no division needed
+  texit = (bnum < bden) ? bnum / bden : __builtin_huge_val();
+  next = nb;
+}
+
+
+// ---------------------------------------------------------------------------
+// Per-ray state machine shared by every kernel variant.
+// ---------------------------------------------------------------------------
+
+struct DeviceStats {
+  unsigned long long segments;     // tally contributions (weighted phase, flying particles)
+  unsigned long long tracks;       // flying particles in weighted phases
+  unsigned long long relocations;  // crossings walked with tallying off
+  unsigned long long lost;         // walks stopped by the iteration limit
+};
+
+struct TetRecord;
+
+// One launch = one particle range of one MoveToNextLocation / CopyInitialPosition.
+struct WalkParams {
+  const TetRecord *tets;   // [E] packed records
+  double *flux;            // [E] raw tally
+  double *px, *py, *pz;    // [N] persistent particle position (SoA)
+  int32_t *elem;           // [N] persistent parent element
+  const double *origin;    // [3N] AoS relocation target (phase 1), nullptr = skip phase
+  const double *dest;      // [3N] AoS flight target (phase 2), nullptr = skip phase
+  const int8_t *flying;    // [N], nullptr = every particle flies (localisation)
+  const double *weights;   // [N]
+  int32_t begin, end;      // particle range
+  int32_t max_iters;       // crossing limit per walk ("May need more loops in search")
+  DeviceStats *stats;
+};
+
+constexpr int kStageReloc = 0;  // phase 1: move to caller's origin, tally off
+constexpr int kStageTally = 1;  // phase 2: fly to destination, tally on
+constexpr int kStageDone = 2;
+
+struct Ray {
+  double ox, oy, oz;  // ray origin (fixed for the whole walk)
+  double ux, uy, uz;  // target - origin
+  double tcur;        // parameter of the last crossing (the reference's prev_xpoint)
+  double wl;          // weight * |u|  (tally phase)
+  int32_t e;          // current tet
+  int32_t stage;
+  int32_t iters;
+};
+
+struct Counters {
+  unsigned segs = 0, tracks = 0, relocs = 0, lost = 0;
+};
+
+PTB_HD void set_ray(Ray &r, double x, double y, double z, double tx, double ty, double tz) {
+  r.ox = x; r.oy = y; r.oz = z;
+  r.ux = tx - x; r.uy = ty - y; r.uz = tz - z;
+  r.tcur = 0.0;
+  r.iters = 0;
+}
+
+PTB_HD void start_tally(const WalkParams &P, int i, Ray &r, double x, double y, double z,
+                        Counters &c, bool writer) {
+  const double tx = PTB_LDG(P.dest + 3 * (size_t)i), ty = PTB_LDG(P.dest + 3 * (size_t)i + 1),
+               tz = PTB_LDG(P.dest + 3 * (size_t)i + 2);
+  set_ray(r, x, y, z, tx, ty, tz);
+  const double len = sqrt(r.ux * r.ux + r.uy * r.uy + r.uz * r.uz);
+  r.wl = PTB_LDG(P.weights + i) * len;
+  r.stage = kStageTally;
+  if (writer) c.tracks++;
+}
+
+// K1/K2/K3 of the reference folded into the prologue: pick the walk target.
+PTB_HD void begin_particle(const WalkParams &P, int i, Ray &r, Counters &c, bool writer) {
+  r.stage = kStageDone;
+  const bool fly = P.flying ? (P.flying[i] == 1) : true;  // only the value 1 flies (Impl.cpp:95)
+  if (!fly) return;  // dest := own origin => zero-length walk, nothing changes (Impl.cpp:100-102)
+  const double x = P.px[i], y = P.py[i], z = P.pz[i];
+  r.e = P.elem[i];
+  if (P.origin) {
+    const double tx = PTB_LDG(P.origin + 3 * (size_t)i), ty = PTB_LDG(P.origin + 3 * (size_t)i + 1),
+                 tz = PTB_LDG(P.origin + 3 * (size_t)i + 2);
+    if (tx != x || ty != y || tz != z) {
+      set_ray(r, x, y, z, tx, ty, tz);
+      r.wl = 0.0;  // p_wgt = 0 during relocation (Impl.cpp:105)
+      r.stage = kStageReloc;
+      return;
+    }
+  }
+  if (P.dest) start_tally(P, i, r, x, y, z, c, writer);
+}
+
+// The current ray ended (target reached, hull hit, or iteration limit).
+PTB_HD void end_ray(const WalkParams &P, int i, Ray &r, bool reached, double tnew, Counters &c,
+                    bool writer) {
+  double x, y, z;
+  if (reached) {  // tracer commit: origin <- dest, exactly (test lines 323-346)
+    const double *tgt = (r.stage == kStageReloc) ? P.origin : P.dest;
+    x = PTB_LDG(tgt + 3 * (size_t)i); y = PTB_LDG(tgt + 3 * (size_t)i + 1); z = PTB_LDG(tgt + 3 * (size_t)i + 2);
+  } else {  // vacuum BC: dest <- intersection point (Impl.cpp:275-281)
+    x = fma(tnew, r.ux, r.ox); y = fma(tnew, r.uy, r.oy); z = fma(tnew, r.uz, r.oz);
+  }
+  if (r.stage == kStageReloc && P.dest) {
+    start_tally(P, i, r, x, y, z, c, writer);  // phase 2 starts where phase 1 ended
+  } else {
+    if (writer) {
+      P.px[i] = x; P.py[i] = y; P.pz[i] = z;
+      P.elem[i] = r.e;
+    }
+    r.stage = kStageDone;
+  }
+}
+
+// Functor body for one crossing, given the tracer's answer (texit, next).
+PTB_HD void advance(const WalkParams &P, int i, Ray &r, double texit, int32_t next, Counters &c,
+                    bool writer) {
+  const bool reached = !(texit < 1.0);  // last_exit == -1: destination inside this tet
+  const double tnew = reached ? 1.0 : fmax(texit, r.tcur);
+  if (r.stage == kStageTally) {  // EvaluateFlux (Impl.cpp:362-379)
+    if (writer) {
+      PTB_TALLY_ADD(P.flux + r.e, (tnew - r.tcur) * r.wl);
+      c.segs++;
+    }
+  } else if (writer) {
+    c.relocs++;
+  }
+  const bool hull = !reached && next < 0;  // next_elems == -1 (Impl.cpp:270-271)
+  r.iters++;
+  const bool over = r.iters >= P.max_iters;
+  if (reached || hull || over) {
+    if (over && !reached && !hull && writer) c.lost++;
+    end_ray(P, i, r, reached, tnew, c, writer);
+  } else {
+    r.e = next;  // UpdateCurrentElement (Impl.cpp:247-253)
+    r.tcur = tnew;
+  }
+}
+
+}  // namespace ptb

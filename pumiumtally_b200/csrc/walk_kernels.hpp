@@ -1,0 +1,24 @@
+// Launch interface of the sm_100a walk/tally kernels (walk_kernels.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "tet_mesh.hpp"
+#include "walk_core.cuh"
+
+namespace ptb {
+
+enum WalkVariant : int {
+  kVariantLdg = 0,   // thread per particle, 4 x 256-bit loads of the tet record
+  kVariantBulk = 1,  // thread per particle, record staged in smem by cp.async.bulk + mbarrier
+  kVariantQuad = 2,  // 4 lanes per particle (lane per face), coalesced 32 B loads
+  kNumVariants = 3
+};
+
+cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_t stream);
+cudaError_t launch_init_particles(double *px, double *py, double *pz, int32_t *elem, int32_t n,
+                                  double cx, double cy, double cz, cudaStream_t stream);
+cudaError_t launch_normalize(const double *flux, const double *volume, double *out, int64_t n,
+                             cudaStream_t stream);
+
+}  // namespace ptb

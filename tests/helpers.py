@@ -1,0 +1,198 @@
+"""Shared parity-test plumbing: run the same seeded batches through an engine
+under test and through the oracle, then compare with the tolerances of
+SURVEY.md section 8c."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle.oracle import OraclePumiTally
+from pumiumtally_b200.mesh import kuhn_box
+from pumiumtally_b200.workload import SyntheticWorkload
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+# flux parity (north_star: 1e-6 relative, element for element; the absolute
+# floor only guards empty / nearly empty tets)
+FLUX_RTOL = 1e-6
+FLUX_ATOL_FRACTION = 1e-12
+POS_RTOL = 1e-12
+
+
+def assert_flux_close(got, want, label=""):
+    got, want = np.asarray(got), np.asarray(want)
+    tol = FLUX_RTOL * np.abs(want) + FLUX_ATOL_FRACTION * np.abs(want).sum()
+    bad = np.abs(got - want) > tol
+    assert not bad.any(), (
+        f"{label}: {int(bad.sum())} of {bad.size} elements differ; worst rel "
+        f"{np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)):.3e}")
+
+
+def assert_positions_close(got, want, label=""):
+    scale = np.maximum(np.abs(want).max(), 1.0)
+    err = np.abs(np.asarray(got) - np.asarray(want)).max() if len(want) else 0.0
+    assert err <= POS_RTOL * scale, f"{label}: position error {err:.3e}"
+
+
+def run_workload(engine, oracle, workload, steps, check_each_step=True, label=""):
+    """Drive engine and oracle with identical batches; assert parity after each move."""
+    init = workload.initial_positions()
+    engine.CopyInitialPosition(init.reshape(-1).copy())
+    oracle.CopyInitialPosition(init.reshape(-1).copy())
+    np.testing.assert_array_equal(engine.elem_ids, oracle.elem_ids, err_msg=f"{label} parent elems after localisation")
+    assert not engine.flux.any(), "flux must stay zero during localisation"
+    for s in range(steps):
+        o, d, f, w = workload.next_step()
+        f1, f2 = f.copy(), f.copy()
+        engine.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f1, w.copy())
+        oracle.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f2, w.copy())
+        assert not f1.any() and not f2.any(), "flying[] must be zeroed on return"
+        if check_each_step or s == steps - 1:
+            assert_flux_close(engine.flux, oracle.flux, f"{label} step {s}")
+            np.testing.assert_array_equal(engine.elem_ids, oracle.elem_ids, err_msg=f"{label} elems step {s}")
+            assert_positions_close(engine.positions, oracle.positions, f"{label} step {s}")
+
+
+# ---------------------------------------------------------------------------
+# test-only host build of the device walk logic (tests/host_emul/emul_walk.cpp)
+# ---------------------------------------------------------------------------
+_EMUL = None
+
+
+def emul_lib():
+    global _EMUL
+    if _EMUL is None:
+        so = os.path.join(HERE, "host_emul", "libptb_emul.so")
+        srcs = [os.path.join(HERE, "host_emul", "emul_walk.cpp"),
+                os.path.join(ROOT, "pumiumtally_b200", "csrc", "tet_mesh.cpp"),
+                os.path.join(ROOT, "pumiumtally_b200", "csrc", "osh_reader.cpp")]
+        deps = srcs + [os.path.join(ROOT, "pumiumtally_b200", "csrc", h) for h in ("walk_core.cuh", "tet_mesh.hpp")]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp",
+                                   "-I", os.path.join(ROOT, "pumiumtally_b200", "csrc"),
+                                   "-I", os.path.join(ROOT, "include"), *srcs, "-o", so])
+        L = C.CDLL(so)
+        L.ptb_emul_create.restype = C.c_void_p
+        L.ptb_emul_create.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int]
+        L.ptb_emul_create_spec.restype = C.c_void_p
+        L.ptb_emul_create_spec.argtypes = [C.c_char_p, C.c_int]
+        L.ptb_emul_destroy.argtypes = [C.c_void_p]
+        L.ptb_emul_localize.argtypes = [C.c_void_p, C.c_void_p]
+        L.ptb_emul_move.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ptb_emul_get.argtypes = [C.c_void_p] * 6
+        L.ptb_emul_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        L.ptb_emul_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _EMUL = L
+    return _EMUL
+
+
+class HostEmulTally:
+    """The CUDA kernels' per-ray state machine compiled for the host (tests only)."""
+
+    def __init__(self, coords=None, tet2vert=None, num_particles=0, spec=None):
+        self._L = emul_lib()
+        self.num_particles = int(num_particles)
+        if spec is not None:
+            self._h = self._L.ptb_emul_create_spec(spec.encode(), self.num_particles)
+        else:
+            coords = np.ascontiguousarray(coords, dtype=np.float64)
+            t2v = np.ascontiguousarray(tet2vert, dtype=np.int32)
+            self._h = self._L.ptb_emul_create(coords.ctypes.data, coords.shape[0], t2v.ctypes.data, t2v.shape[0],
+                                              self.num_particles)
+        assert self._h, "mesh rejected"
+        sz = np.zeros(2, dtype=np.int64)
+        self._L.ptb_emul_sizes(self._h, sz.ctypes.data)
+        self.num_verts, self.num_elements = int(sz[0]), int(sz[1])
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.ptb_emul_destroy(self._h)
+
+    def CopyInitialPosition(self, xyz, size=None):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        self._L.ptb_emul_localize(self._h, xyz.ctypes.data)
+
+    def MoveToNextLocation(self, o, d, flying, w, size=None):
+        o, d, w = (np.ascontiguousarray(a, dtype=np.float64) for a in (o, d, w))
+        self._L.ptb_emul_move(self._h, o.ctypes.data, d.ctypes.data, flying.ctypes.data, w.ctypes.data)
+
+    def _get(self):
+        flux = np.empty(self.num_elements)
+        elem = np.empty(self.num_particles, dtype=np.int32)
+        pos = np.empty((self.num_particles, 3))
+        stats = np.zeros(4, dtype=np.uint64)
+        adj = np.empty((self.num_elements, 4), dtype=np.int32)
+        self._L.ptb_emul_get(self._h, flux.ctypes.data, elem.ctypes.data, pos.ctypes.data, stats.ctypes.data,
+                             adj.ctypes.data)
+        return flux, elem, pos, stats, adj
+
+    flux = property(lambda s: s._get()[0])
+    elem_ids = property(lambda s: s._get()[1])
+    positions = property(lambda s: s._get()[2])
+    adjacency = property(lambda s: s._get()[4])
+
+    def stats(self):
+        st = self._get()[3]
+        return dict(segments=int(st[0]), tracks=int(st[1]), relocations=int(st[2]), lost=int(st[3]))
+
+    def mesh_arrays(self):
+        c = np.empty((self.num_verts, 3))
+        t = np.empty((self.num_elements, 4), dtype=np.int32)
+        v = np.empty(self.num_elements)
+        self._L.ptb_emul_mesh(self._h, c.ctypes.data, t.ctypes.data, v.ctypes.data)
+        return c, t, v
+
+
+def box_case(cells, n, **kw):
+    coords, t2v = kuhn_box(*cells)
+    wl = SyntheticWorkload(box=tuple(float(c) for c in cells), num_particles=n, **kw)
+    return coords, t2v, wl
+
+
+def edge_case_scenario(make_engine):
+    """Clipping at the hull, zero-length and non-flying particles, relocation, zero weight."""
+    coords, t2v = kuhn_box(2, 2, 2)
+    n = 6
+    eng, orc = make_engine(coords, t2v, n), OraclePumiTally(coords, t2v, n)
+    init = np.array([[0.3, 0.2, 0.1], [1.7, 1.2, 0.4], [0.5, 1.5, 1.9], [1.1, 0.9, 0.3], [0.2, 0.2, 1.7], [1.9, 1.9, 1.9]])
+    for e in (eng, orc):
+        e.CopyInitialPosition(init.reshape(-1).copy())
+    np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+    origin = init.copy()
+    dest = init.copy()
+    dest[0] = [5.0, 0.2, 0.1]       # leaves through +x: clipped at x = 2
+    dest[1] = init[1]               # zero-length flight
+    dest[2] = [0.5, 1.5, -3.0]      # leaves through z = 0
+    origin[3] = [0.4, 1.6, 1.2]     # re-sampled: relocation without tally, then flight
+    dest[3] = [0.6, 1.1, 0.2]
+    dest[4] = [1.3, 1.4, 0.2]       # not flying: must not move or tally
+    dest[5] = [1.2, 1.1, 1.3]
+    fly = np.array([1, 1, 1, 1, 0, 1], dtype=np.int8)
+    w = np.array([1.0, 2.0, 0.5, 0.25, 9.0, 0.0])  # zero weight still moves
+    for e in (eng, orc):
+        e.MoveToNextLocation(origin.reshape(-1).copy(), dest.reshape(-1).copy(), fly.copy(), w.copy())
+    assert_flux_close(eng.flux, orc.flux, "edge")
+    np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+    np.testing.assert_allclose(eng.positions, orc.positions, atol=1e-13)
+    p = eng.positions
+    np.testing.assert_allclose(p[0], [2.0, 0.2, 0.1], atol=1e-13)
+    np.testing.assert_allclose(p[2], [0.5, 1.5, 0.0], atol=1e-13)
+    np.testing.assert_array_equal(p[4], init[4])
+    # total tally = sum of weighted in-mesh track lengths
+    want = 1.0 * 1.7 + 0.5 * 1.9 + 0.25 * np.linalg.norm(dest[3] - origin[3])
+    np.testing.assert_allclose(eng.flux.sum(), want, rtol=1e-13)
+    # a second move starting on the hull, heading further out: nothing to tally
+    o2 = eng.positions.copy()
+    d2 = o2.copy()
+    d2[0] = [9.0, 0.2, 0.1]
+    fly2 = np.array([1, 0, 0, 0, 0, 0], dtype=np.int8)
+    before = eng.flux.sum()
+    for e in (eng, orc):
+        e.MoveToNextLocation(o2.reshape(-1).copy(), d2.reshape(-1).copy(), fly2.copy(), np.ones(n))
+    np.testing.assert_allclose(eng.flux.sum(), before, atol=1e-13)
+    np.testing.assert_allclose(eng.positions[0], [2.0, 0.2, 0.1], atol=1e-13)
+    np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)

@@ -1,0 +1,110 @@
+// TEST-ONLY host build of the device walk logic.
+//
+// Compiles pumiumtally_b200/csrc/walk_core.cuh (the per-ray state machine the
+// CUDA kernels run) and tet_mesh.cpp (the record packer) with g++ so that the
+// arithmetic can be checked against the oracle on a machine without a GPU.
+// It is never linked into libpumitally.so and is not a fallback: the product
+// refuses to construct an engine without a CUDA device.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tet_mesh.hpp"
+#include "walk_core.cuh"
+
+using namespace ptb;
+
+namespace {
+struct Emul {
+  HostMesh mesh;
+  std::vector<TetRecord> recs;
+  std::vector<double> flux, px, py, pz;
+  std::vector<int32_t> elem;
+  DeviceStats stats{};
+  int n = 0;
+  void run(const double *origin, const double *dest, const int8_t *flying, const double *weights) {
+    WalkParams P{};
+    P.tets = recs.data();
+    P.flux = flux.data();
+    P.px = px.data(); P.py = py.data(); P.pz = pz.data();
+    P.elem = elem.data();
+    P.origin = origin; P.dest = dest; P.flying = flying; P.weights = weights;
+    P.begin = 0; P.end = n;
+    P.max_iters = int32_t(mesh.ntets + 16);
+    P.stats = &stats;
+    for (int i = 0; i < n; ++i) {
+      Counters c;
+      Ray r;
+      begin_particle(P, i, r, c, true);
+      while (r.stage != kStageDone) {
+        double raw[16];
+        std::memcpy(raw, recs[r.e].d, 128);
+        TetPlanes t;
+        decode_record(raw, t);
+        double texit;
+        int32_t next;
+        exit_face(t, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, texit, next);
+        advance(P, i, r, texit, next, c, true);
+      }
+      stats.segments += c.segs; stats.tracks += c.tracks;
+      stats.relocations += c.relocs; stats.lost += c.lost;
+    }
+  }
+};
+}  // namespace
+
+extern "C" {
+void *ptb_emul_create(const double *coords, int64_t nverts, const int32_t *t2v, int64_t ntets, int n) {
+  auto *e = new Emul;
+  std::string err;
+  if (!e->mesh.from_arrays(coords, nverts, t2v, ntets, &err)) { delete e; return nullptr; }
+  e->recs = e->mesh.records;
+  e->n = n;
+  e->flux.assign(size_t(ntets), 0.0);
+  e->px.assign(size_t(n), e->mesh.centroid0[0]);
+  e->py.assign(size_t(n), e->mesh.centroid0[1]);
+  e->pz.assign(size_t(n), e->mesh.centroid0[2]);
+  e->elem.assign(size_t(n), 0);
+  return e;
+}
+void *ptb_emul_create_spec(const char *spec, int n) {
+  auto *e = new Emul;
+  std::string err;
+  if (!e->mesh.load(spec, &err)) { delete e; return nullptr; }
+  e->recs = e->mesh.records;
+  e->n = n;
+  e->flux.assign(size_t(e->mesh.ntets), 0.0);
+  e->px.assign(size_t(n), e->mesh.centroid0[0]);
+  e->py.assign(size_t(n), e->mesh.centroid0[1]);
+  e->pz.assign(size_t(n), e->mesh.centroid0[2]);
+  e->elem.assign(size_t(n), 0);
+  return e;
+}
+void ptb_emul_sizes(void *h, int64_t *out) {
+  auto *e = static_cast<Emul *>(h);
+  out[0] = e->mesh.nverts; out[1] = e->mesh.ntets;
+}
+void ptb_emul_mesh(void *h, double *coords, int32_t *t2v, double *vol) {
+  auto *e = static_cast<Emul *>(h);
+  std::memcpy(coords, e->mesh.coords.data(), e->mesh.coords.size() * 8);
+  std::memcpy(t2v, e->mesh.t2v.data(), e->mesh.t2v.size() * 4);
+  std::memcpy(vol, e->mesh.volume.data(), e->mesh.volume.size() * 8);
+}
+void ptb_emul_destroy(void *h) { delete static_cast<Emul *>(h); }
+void ptb_emul_localize(void *h, const double *xyz) { static_cast<Emul *>(h)->run(xyz, nullptr, nullptr, nullptr); }
+void ptb_emul_move(void *h, const double *origin, const double *dest, int8_t *flying, const double *w) {
+  auto *e = static_cast<Emul *>(h);
+  e->run(origin, dest, flying, w);
+  std::memset(flying, 0, size_t(e->n));
+}
+void ptb_emul_get(void *h, double *flux, int32_t *elem, double *pos, unsigned long long *stats, int32_t *adj) {
+  auto *e = static_cast<Emul *>(h);
+  if (flux) std::memcpy(flux, e->flux.data(), e->flux.size() * 8);
+  if (elem) std::memcpy(elem, e->elem.data(), e->elem.size() * 4);
+  if (pos)
+    for (int i = 0; i < e->n; ++i) { pos[3 * i] = e->px[i]; pos[3 * i + 1] = e->py[i]; pos[3 * i + 2] = e->pz[i]; }
+  if (stats) { stats[0] = e->stats.segments; stats[1] = e->stats.tracks; stats[2] = e->stats.relocations; stats[3] = e->stats.lost; }
+  if (adj) std::memcpy(adj, e->mesh.t2t.data(), e->mesh.t2t.size() * 4);
+}
+}

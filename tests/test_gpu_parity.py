@@ -1,0 +1,269 @@
+"""Parity tests proper: the CUDA path, called through the C ABI of
+libpumitally.so, against the CPU oracle on the same seeded inputs
+(tolerances: helpers.FLUX_RTOL = 1e-6 relative on flux, exact parent
+elements, 1e-12 relative positions), plus size-independent properties at the
+full BASELINE.json sizes."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import (ROOT, assert_flux_close, box_case, edge_case_scenario, run_workload)
+from oracle.oracle import OraclePumiTally
+from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, save_raw_mesh, tet_volumes
+from pumiumtally_b200.tally import PumiTally
+from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
+from test_oracle_golden import golden_scenario
+
+pytestmark = pytest.mark.gpu
+VARIANTS = [0, 1, 2]
+
+
+def gpu_engine(variant, block=128, chunk=None):
+    def make(coords, t2v, n):
+        e = PumiTally.from_arrays(coords, t2v, n)
+        e.set_option("variant", variant)
+        e.set_option("block", block)
+        if chunk:
+            e.set_option("chunk", chunk)
+        return e
+    return make
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_reference_known_answers(variant):
+    eng = golden_scenario(gpu_engine(variant))
+    st = eng.stats()
+    assert st["segments"] == 18 and st["tracks"] == 7 and st["lost"] == 0 and st["moves"] == 2
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_edge_cases(variant):
+    edge_case_scenario(gpu_engine(variant))
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("block", [64, 256])
+def test_config_c1_parity(variant, block):
+    coords, t2v, wl = box_case(CONFIGS["c1"]["cells"], CONFIGS["c1"]["particles"])
+    eng = gpu_engine(variant, block)(coords, t2v, wl.n)
+    orc = OraclePumiTally(coords, t2v, wl.n)
+    run_workload(eng, orc, wl, steps=4, label=f"c1 v{variant}")
+    st = eng.stats()
+    assert st["segments"] == orc.n_segments and st["tracks"] == orc.n_tracks and st["lost"] == 0
+    assert st["kernel_ms"] > 0
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("mesh", ["jitter", "delaunay"])
+def test_unstructured_parity(variant, mesh):
+    if mesh == "jitter":
+        c, t = jitter_interior(*kuhn_box(8, 7, 6), amplitude=0.18)
+        box = (8.0, 7.0, 6.0)
+    else:
+        c, t = delaunay_box(3000)
+        box = (1.0, 1.0, 1.0)
+    n = 50_000
+    wl = SyntheticWorkload(box=box, num_particles=n, mean_length=0.4 * min(box), seed=3)
+    eng, orc = gpu_engine(variant)(c, t, n), OraclePumiTally(c, t, n)
+    run_workload(eng, orc, wl, steps=3, label=f"{mesh} v{variant}")
+    assert eng.stats()["segments"] == orc.n_segments
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_long_axial_tracks(variant):
+    coords, t2v, wl = box_case((8, 8, 80), 20_000, mean_length=120.0, mu_min=0.9)
+    eng, orc = gpu_engine(variant)(coords, t2v, wl.n), OraclePumiTally(coords, t2v, wl.n)
+    run_workload(eng, orc, wl, steps=2, label="c4-mini")
+    assert eng.stats()["segments"] == orc.n_segments
+
+
+def test_contention_many_particles_few_tets():
+    """Config c3 in miniature: thousands of particles per tet hammer the same flux words."""
+    coords, t2v, wl = box_case((3, 3, 3), 400_000, mean_length=1.5)
+    eng, orc = gpu_engine(0)(coords, t2v, wl.n), OraclePumiTally(coords, t2v, wl.n)
+    run_workload(eng, orc, wl, steps=2, check_each_step=False, label="c3-mini")
+
+
+def test_chunked_upload_pipeline_equals_single_range():
+    coords, t2v, wl = box_case((6, 6, 5), 50_000)
+    a = gpu_engine(0, chunk=4096)(coords, t2v, wl.n)
+    orc = OraclePumiTally(coords, t2v, wl.n)
+    run_workload(a, orc, wl, steps=3, label="chunked")
+
+
+def test_error_behaviour():
+    coords, t2v = kuhn_box(1, 1, 1)
+    e = PumiTally.from_arrays(coords, t2v, 5)
+    xyz = np.tile([0.1, 0.4, 0.5], 5)
+    fly = np.ones(5, dtype=np.int8)
+    with pytest.raises(RuntimeError):  # move before CopyInitialPosition (assert Impl.cpp:437)
+        e.MoveToNextLocation(xyz, xyz, fly, np.ones(5))
+    with pytest.raises(RuntimeError):  # size must be 3N (assert Impl.cpp:57)
+        e.CopyInitialPosition(xyz, 5)
+    e.CopyInitialPosition(xyz, 15)
+    with pytest.raises(RuntimeError):  # only once (PumiTally.h:63-64)
+        e.CopyInitialPosition(xyz, 15)
+    with pytest.raises(RuntimeError):
+        e.MoveToNextLocation(xyz, xyz, fly, np.ones(5), 5)
+    with pytest.raises(RuntimeError):
+        PumiTally("does/not/exist.osh", 5)
+    with pytest.raises(RuntimeError):  # degenerate tet
+        PumiTally.from_arrays(np.zeros((4, 3)), np.array([[0, 1, 2, 3]], dtype=np.int32), 1)
+
+
+def test_raw_mesh_file_and_box_spec(tmp_path):
+    coords, t2v = kuhn_box(3, 2, 2)
+    path = str(tmp_path / "mesh.ptm")
+    save_raw_mesh(path, coords, t2v)
+    a, b = PumiTally(path, 100), PumiTally("box:3,2,2", 100)
+    assert a.num_elements == b.num_elements == 72
+    np.testing.assert_array_equal(a.adjacency, b.adjacency)
+    wl = SyntheticWorkload(box=(3.0, 2.0, 2.0), num_particles=100, mean_length=1.0)
+    init = wl.initial_positions().reshape(-1)
+    o, d, f, w = wl.next_step()
+    for e in (a, b):
+        e.CopyInitialPosition(init.copy())
+        e.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy())
+    np.testing.assert_allclose(a.flux, b.flux, rtol=1e-13)
+
+
+def test_device_pointer_entry_points_match_host_path():
+    import torch
+
+    coords, t2v, wl = box_case((6, 6, 5), 30_000)
+    host = gpu_engine(0)(coords, t2v, wl.n)
+    dev = gpu_engine(0)(coords, t2v, wl.n)
+    init = wl.initial_positions()
+    host.CopyInitialPosition(init.reshape(-1).copy())
+    d_init = torch.from_numpy(init).cuda()
+    dev.copy_initial_position_device(d_init.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        o, d, f, w = wl.next_step()
+        host.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy())
+        t = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (o, d, f, w)]
+        dev.move_device(*(x.data_ptr() for x in t), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    np.testing.assert_allclose(dev.flux, host.flux, rtol=1e-12)
+    np.testing.assert_array_equal(dev.elem_ids, host.elem_ids)
+    np.testing.assert_array_equal(dev.positions, host.positions)
+
+
+def test_normalized_flux_reset_and_vtk_output(tmp_path):
+    coords, t2v, wl = box_case((4, 3, 2), 5000)
+    e = gpu_engine(0)(coords, t2v, wl.n)
+    e.CopyInitialPosition(wl.initial_positions().reshape(-1))
+    o, d, f, w = wl.next_step()
+    e.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
+    nf, vol = e.normalized_flux()
+    np.testing.assert_allclose(vol, tet_volumes(coords, t2v), rtol=1e-13)
+    np.testing.assert_allclose(nf, e.flux / vol, rtol=1e-14)
+    out = str(tmp_path / "fluxresult.vtk")
+    e.WriteTallyResults(out)
+    from vtk_reader import read_vtu_cell_data
+
+    cells = read_vtu_cell_data(os.path.join(out, "pieces", "piece_0.vtu"))
+    np.testing.assert_array_equal(cells["flux"], nf)
+    np.testing.assert_array_equal(cells["volume"], vol)
+    np.testing.assert_array_equal(cells["connectivity"].reshape(-1, 4), t2v)
+    assert os.path.exists(os.path.join(out, "pieces.pvtu"))
+    e.reset_tally()
+    assert not e.flux.any() and e.stats()["segments"] == 0
+
+
+def test_cxx_facade_program(tmp_path):
+    """Link a C++ caller against include/pumitally/PumiTally.h + libpumitally.so, the way the
+    OpenMC fork does, and replay the reference's known-answer scenario."""
+    from pumiumtally_b200 import build as pbuild
+
+    lib = pbuild.build_library()
+    exe = str(tmp_path / "facade_demo")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "facade_demo.cpp"), "-o", exe,
+                           "-L", os.path.dirname(lib), "-lpumitally", "-Wl,-rpath," + os.path.dirname(lib)])
+    out = subprocess.check_output([exe], cwd=str(tmp_path), text=True)
+    assert "[TIME] Total PUMI-Tally time" in out
+    assert "FACADE_OK" in out
+    from vtk_reader import read_vtu_cell_data
+
+    cells = read_vtu_cell_data(str(tmp_path / "fluxresult.vtk" / "pieces" / "piece_0.vtu"))
+    np.testing.assert_allclose(cells["flux"] * cells["volume"], [0, 0, 1.5, 0.5, 2.5, 0], atol=1e-8)
+
+
+# ---------------------------------------------------------------- full sizes
+
+def _box_clip_length(o, d, box):
+    """Length of segment o->d inside [0,box] (torch, on device)."""
+    import torch
+
+    u = d - o
+    t1 = torch.ones(o.shape[0], dtype=torch.float64, device=o.device)
+    for k in range(3):
+        uk = u[:, k]
+        hi = torch.where(uk > 0, (box[k] - o[:, k]) / uk, torch.where(uk < 0, (0.0 - o[:, k]) / uk, t1 * float("inf")))
+        t1 = torch.minimum(t1, hi)
+    return t1.clamp(min=0.0) * u.norm(dim=1)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_config_c2_full_size_properties(variant):
+    """BASELINE.json configs[1] (998,250 tets, 10M particles): too big for the oracle in
+    seconds, so check what must hold at any size: total tally == sum of weighted in-box
+    track lengths (conservation), every particle ends inside its parent tet, final
+    positions equal the clipped destinations, and one variant-0 run is the cross-check
+    for the other variants."""
+    import torch
+
+    cfg = CONFIGS["c2"]
+    cells, n = cfg["cells"], cfg["particles"]
+    box = tuple(float(c) for c in cells)
+    eng = PumiTally(f"box:{cells[0]},{cells[1]},{cells[2]}", n)
+    eng.set_option("variant", variant)
+    wl = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], backend="torch", device="cuda")
+    init = wl.initial_positions().contiguous()
+    s = torch.cuda.current_stream().cuda_stream
+    eng.copy_initial_position_device(init.data_ptr(), s)
+    expect_total = 0.0
+    for step in range(2):
+        o, d, f, w = (x.contiguous() for x in wl.next_step())
+        eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), s)
+        fly = f == 1
+        expect_total += float((_box_clip_length(o[fly], d[fly], box) * w[fly]).sum())
+    torch.cuda.synchronize()
+    flux = eng.flux
+    st = eng.stats()
+    assert st["lost"] == 0 and st["tracks"] > 0.9 * 2 * n
+    np.testing.assert_allclose(flux.sum(), expect_total, rtol=1e-9)
+    assert (flux >= 0).all()
+    # containment of a 200k-particle sample: barycentric coordinates of the stored position
+    # in the stored parent tet are all >= -1e-9
+    coords, t2v = kuhn_box(*cells)
+    elem, pos = eng.elem_ids, eng.positions
+    assert elem.min() >= 0 and elem.max() < len(t2v)
+    idx = np.random.default_rng(0).choice(n, 200_000, replace=False)
+    v = coords[t2v[elem[idx]]]
+    T = np.transpose(v[:, 1:] - v[:, :1], (0, 2, 1))
+    lam = np.linalg.solve(T, (pos[idx] - v[:, 0])[..., None])[..., 0]
+    lam0 = 1.0 - lam.sum(1)
+    assert min(lam.min(), lam0.min()) > -1e-9
+    # final positions: destination if it is inside the box, else on the hull
+    d_np, fly_np = d.cpu().numpy(), fly.cpu().numpy()
+    inside = ((d_np >= 0) & (d_np <= np.array(box))).all(1)
+    sel = idx[fly_np[idx] & inside[idx]]
+    np.testing.assert_array_equal(pos[sel], d_np[sel])
+    out = idx[fly_np[idx] & ~inside[idx]]
+    on_hull = (np.isclose(pos[out], 0.0, atol=1e-9) | np.isclose(pos[out], np.array(box), atol=1e-9)).any(1)
+    assert on_hull.all()
+    if variant != 0:
+        ref = PumiTally(f"box:{cells[0]},{cells[1]},{cells[2]}", n)
+        wl2 = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], backend="torch", device="cuda")
+        i2 = wl2.initial_positions().contiguous()
+        ref.copy_initial_position_device(i2.data_ptr(), s)
+        for step in range(2):
+            o, d, f, w = (x.contiguous() for x in wl2.next_step())
+            ref.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), s)
+        torch.cuda.synchronize()
+        assert_flux_close(flux, ref.flux, f"variant {variant} vs 0")
+        np.testing.assert_array_equal(elem, ref.elem_ids)
+        assert st["segments"] == ref.stats()["segments"]

@@ -1,0 +1,83 @@
+"""The CUDA kernels' arithmetic (record packing, plane decode, exit-face rule,
+per-ray state machine), compiled for the host by g++ as a TEST-ONLY build,
+checked against the oracle.  This is what can be verified without a GPU; the
+`-m gpu` tests repeat the same comparisons through libpumitally.so."""
+import numpy as np
+import pytest
+
+from helpers import HostEmulTally, assert_flux_close, box_case, edge_case_scenario, run_workload
+from oracle.oracle import OraclePumiTally
+from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, tet_volumes
+from pumiumtally_b200.workload import SyntheticWorkload
+from test_oracle_golden import golden_scenario
+
+
+def test_reference_known_answers_device_logic():
+    eng = golden_scenario(lambda c, t, n: HostEmulTally(c, t, n))
+    st = eng.stats()
+    assert st["lost"] == 0 and st["tracks"] == 7 and st["segments"] == 18
+
+
+def test_box_spec_matches_numpy_generator():
+    e = HostEmulTally(spec="box:3,2,4,1.5,1.0,2.0", num_particles=1)
+    c, t, v = e.mesh_arrays()
+    cn, tn = kuhn_box(3, 2, 4, 1.5, 1.0, 2.0)
+    np.testing.assert_array_equal(t, tn)
+    np.testing.assert_allclose(c, cn, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(v, tet_volumes(cn, tn), rtol=1e-13)
+
+
+@pytest.mark.parametrize("mesh", ["kuhn", "jitter", "delaunay"])
+def test_adjacency_matches_oracle(mesh):
+    if mesh == "kuhn":
+        c, t = kuhn_box(4, 3, 2)
+    elif mesh == "jitter":
+        c, t = jitter_interior(*kuhn_box(4, 3, 3), amplitude=0.15)
+    else:
+        c, t = delaunay_box(200)
+    e = HostEmulTally(c, t, 1)
+    o = OraclePumiTally(c, t, 1)
+    np.testing.assert_array_equal(e.adjacency, o.adjacency)
+    adj = e.adjacency
+    # symmetry: if b is a's neighbour then a is b's neighbour
+    for a in range(len(t)):
+        for b in adj[a]:
+            if b >= 0:
+                assert a in adj[b]
+
+
+def test_config_c1_parity():
+    """BASELINE.json configs[0]: ~1k-tet cube, 10k particles (plumbing config)."""
+    coords, t2v, wl = box_case((6, 6, 5), 10_000)
+    eng = HostEmulTally(coords, t2v, wl.n)
+    orc = OraclePumiTally(coords, t2v, wl.n)
+    run_workload(eng, orc, wl, steps=4, label="c1")
+    st = eng.stats()
+    assert st["segments"] == orc.n_segments and st["tracks"] == orc.n_tracks and st["lost"] == 0
+
+
+@pytest.mark.parametrize("mesh", ["jitter", "delaunay"])
+def test_unstructured_parity(mesh):
+    if mesh == "jitter":
+        c, t = jitter_interior(*kuhn_box(6, 5, 4), amplitude=0.18)
+        box = (6.0, 5.0, 4.0)
+    else:
+        c, t = delaunay_box(600)
+        box = (1.0, 1.0, 1.0)
+    n = 4000
+    wl = SyntheticWorkload(box=box, num_particles=n, mean_length=0.5 * min(box), seed=3)
+    eng, orc = HostEmulTally(c, t, n), OraclePumiTally(c, t, n)
+    run_workload(eng, orc, wl, steps=3, label=mesh)
+    assert eng.stats()["segments"] == orc.n_segments
+
+
+def test_long_axial_tracks():
+    """Config c4 in miniature: forward-peaked tracks crossing many tets."""
+    coords, t2v, wl = box_case((4, 4, 40), 1500, mean_length=60.0, mu_min=0.9)
+    eng, orc = HostEmulTally(coords, t2v, wl.n), OraclePumiTally(coords, t2v, wl.n)
+    run_workload(eng, orc, wl, steps=2, label="c4-mini")
+    assert eng.stats()["segments"] / max(eng.stats()["tracks"], 1) > 15
+
+
+def test_edge_cases():
+    edge_case_scenario(lambda c, t, n: HostEmulTally(c, t, n))

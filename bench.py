@@ -201,11 +201,9 @@ def run_gpu(args, rank, local_rank, world):
     # ---------------- device-resident arm: `value` ------------------------------
     eng = new_engine()
     if world > 1:
-        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(PumiTally.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        eng.comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
+        from pumiumtally_b200.distributed import broadcast_unique_id
+
+        eng.comm_init(rank, world, broadcast_unique_id(dist, PumiTally.nccl_unique_id, device=dev))
     eng.copy_initial_position_device(init.data_ptr(), stream)
     for k in range(args.warmup):
         o, d, f, w = batches[k]
@@ -333,7 +331,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--particles", type=int, default=0, help="override particles per GPU (debug only)")
-    ap.add_argument("--variant", type=int, default=env_int("PUMITALLY_VARIANT", 0))
+    ap.add_argument("--variant", type=int, default=env_int("PUMITALLY_VARIANT", 3))
     ap.add_argument("--block", type=int, default=env_int("PUMITALLY_BLOCK", 128))
     ap.add_argument("--cpu-sample", type=int, default=500_000)
     ap.add_argument("--cpu-steps", type=int, default=3)

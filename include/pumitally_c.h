@@ -102,8 +102,9 @@ int pumitally_set_option(pumitally_engine *e, const char *name, int64_t value);
 /* ---- additive: device-pointer entry points -------------------------------
  * Same semantics as the host versions, but the arrays already live in device
  * memory (AoS positions, int8 flying, double weights).  Work is enqueued on
- * `stream` (a cudaStream_t passed as void*; NULL = the engine's own stream)
- * and the call returns without synchronising.  d_flying is NOT zeroed. */
+ * `stream` (a cudaStream_t passed as void*; NULL = the CUDA default stream,
+ * which is also what PyTorch's default stream is) and the call returns
+ * without synchronising.  d_flying is NOT zeroed. */
 int pumitally_copy_initial_position_device(pumitally_engine *e, const double *d_xyz, int32_t size,
                                            void *stream);
 int pumitally_move_to_next_location_device(pumitally_engine *e, const double *d_origin,

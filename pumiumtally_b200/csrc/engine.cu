@@ -29,6 +29,8 @@ void cuda_or_throw(cudaError_t e, const char *what) {
                              " (this library has no CPU fallback; a CUDA device is required)");
 }
 
+constexpr unsigned kTicketRing = 256;
+
 template <typename T>
 void dev_alloc(T **p, size_t count, const char *what) {
   cuda_or_throw(cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T)), what);
@@ -67,6 +69,7 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
   dev_alloc(&d_weights_, N, "weights staging");
   dev_alloc(&d_flying_, N, "flying staging");
   dev_alloc(&d_stats_, 1, "stats");
+  dev_alloc(&d_tickets_, kTicketRing, "tickets");
 
   cuda_or_throw(cudaMemcpy(d_tets_, mesh_.records.data(), E * sizeof(TetRecord), cudaMemcpyHostToDevice), "upload tets");
   cuda_or_throw(cudaMemcpy(d_volume_, mesh_.volume.data(), E * sizeof(double), cudaMemcpyHostToDevice), "upload volume");
@@ -93,6 +96,7 @@ Engine::~Engine() {
   cudaFree(d_px_); cudaFree(d_py_); cudaFree(d_pz_); cudaFree(d_elem_);
   cudaFree(d_origin_); cudaFree(d_dest_); cudaFree(d_weights_); cudaFree(d_flying_);
   cudaFree(d_stats_);
+  cudaFree(d_tickets_);
   if (compute_) cudaStreamDestroy(compute_);
   if (copy_) cudaStreamDestroy(copy_);
 }
@@ -130,6 +134,10 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   p.end = end;
   p.max_iters = int32_t(std::min<int64_t>(mesh_.ntets + 16, INT_MAX));
   p.stats = d_stats_;
+  p.work_counter = d_tickets_ + (ticket_next_++ % kTicketRing);
+  auto aligned16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  p.bulk_ok = (begin % 16 == 0) && aligned16(d_origin) && aligned16(d_dest) && aligned16(d_flying) &&
+              aligned16(d_weights);
   TimerPair t{};
   if (timed) {
     if (timers_free_.empty()) {
@@ -183,7 +191,7 @@ int Engine::copy_initial_position_device(const double *d_xyz, int32_t size, cuda
     return 1;
   }
   PTB_CUDA_OK(cudaSetDevice(device_));
-  if (launch_range(d_xyz, nullptr, nullptr, nullptr, 0, n_, pick(stream), true)) return 1;
+  if (launch_range(d_xyz, nullptr, nullptr, nullptr, 0, n_, stream, true)) return 1;
   initialized_ = true;
   return 0;
 }
@@ -244,7 +252,7 @@ int Engine::move_to_next_location_device(const double *d_origin, const double *d
   }
   PTB_CUDA_OK(cudaSetDevice(device_));
   collect_timers(false);
-  if (launch_range(d_origin, d_dest, d_flying, d_weights, 0, n_, pick(stream), true)) return 1;
+  if (launch_range(d_origin, d_dest, d_flying, d_weights, 0, n_, stream, true)) return 1;
   ++moves_;
   return 0;
 }

@@ -60,7 +60,6 @@ class Engine {
   int allreduce_tally();
 
  private:
-  cudaStream_t pick(cudaStream_t s) const { return s ? s : compute_; }
   int launch_range(const double *d_origin, const double *d_dest, const int8_t *d_flying,
                    const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream,
                    bool timed);
@@ -75,7 +74,7 @@ class Engine {
   std::string output_name_ = "fluxresult.vtk";
 
   // options
-  int variant_ = kVariantLdg;
+  int variant_ = kVariantPersist;
   int block_ = 128;
   int32_t chunk_ = 1 << 20;  // particles per H2D/compute pipeline stage
 
@@ -87,6 +86,8 @@ class Engine {
   double *d_origin_ = nullptr, *d_dest_ = nullptr, *d_weights_ = nullptr;  // staging
   int8_t *d_flying_ = nullptr;
   DeviceStats *d_stats_ = nullptr;
+  unsigned int *d_tickets_ = nullptr;  // ring of chunk counters for the persistent kernel
+  unsigned ticket_next_ = 0;
 
   cudaStream_t compute_ = nullptr, copy_ = nullptr;
   struct TimerPair { cudaEvent_t a, b; };

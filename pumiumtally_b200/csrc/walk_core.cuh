@@ -124,6 +124,8 @@ struct WalkParams {
   const double *weights;   // [N]
   int32_t begin, end;      // particle range
   int32_t max_iters;       // crossing limit per walk ("May need more loops in search")
+  int32_t bulk_ok;         // all particle arrays 16-byte aligned: cp.async.bulk staging allowed
+  unsigned int *work_counter;  // chunk ticket of the persistent kernel (zeroed per launch)
   DeviceStats *stats;
 };
 
@@ -134,6 +136,7 @@ constexpr int kStageDone = 2;
 struct Ray {
   double ox, oy, oz;  // ray origin (fixed for the whole walk)
   double ux, uy, uz;  // target - origin
+  double tx, ty, tz;  // target (stored exactly as given: it becomes the position when reached)
   double tcur;        // parameter of the last crossing (the reference's prev_xpoint)
   double wl;          // weight * |u|  (tally phase)
   int32_t e;          // current tet
@@ -148,6 +151,7 @@ struct Counters {
 PTB_HD void set_ray(Ray &r, double x, double y, double z, double tx, double ty, double tz) {
   r.ox = x; r.oy = y; r.oz = z;
   r.ux = tx - x; r.uy = ty - y; r.uz = tz - z;
+  r.tx = tx; r.ty = ty; r.tz = tz;
   r.tcur = 0.0;
   r.iters = 0;
 }
@@ -188,8 +192,7 @@ PTB_HD void end_ray(const WalkParams &P, int i, Ray &r, bool reached, double tne
                     bool writer) {
   double x, y, z;
   if (reached) {  // tracer commit: origin <- dest, exactly (test lines 323-346)
-    const double *tgt = (r.stage == kStageReloc) ? P.origin : P.dest;
-    x = PTB_LDG(tgt + 3 * (size_t)i); y = PTB_LDG(tgt + 3 * (size_t)i + 1); z = PTB_LDG(tgt + 3 * (size_t)i + 2);
+    x = r.tx; y = r.ty; z = r.tz;
   } else {  // vacuum BC: dest <- intersection point (Impl.cpp:275-281)
     x = fma(tnew, r.ux, r.ox); y = fma(tnew, r.uy, r.oy); z = fma(tnew, r.uz, r.oz);
   }

@@ -12,6 +12,7 @@
 // per-ray state machine below so they produce identical results.
 #include "walk_kernels.hpp"
 
+#include <algorithm>
 #include <cstdint>
 
 #include "walk_core.cuh"
@@ -193,6 +194,186 @@ __global__ void __launch_bounds__(256) walk_quad_kernel(const WalkParams P) {
   flush_counters(P, c);
 }
 
+// ---------------------------------------------------------------- variant 3
+// Persistent warps with per-lane refill.  Track lengths are roughly geometric
+// and relocation walks are ~10x longer than tally walks, so with one particle
+// per thread a warp idles most of its lanes (measured: 3.9 of 32 lanes active
+// per instruction).  Here every warp owns two shared-memory stages of 32
+// particles each, filled asynchronously by the TMA unit (cp.async.bulk of the
+// SoA/AoS slices, completion on an mbarrier); a lane that finishes its particle
+// takes the next slot of the current stage in the same loop iteration, and
+// chunks of 32 particles are claimed from a global counter so long walks never
+// hold back the rest of the range.
+
+constexpr int kChunk = 32;
+
+struct __align__(16) ParticleStage {
+  double origin[3 * kChunk];
+  double dest[3 * kChunk];
+  double px[kChunk], py[kChunk], pz[kChunk], w[kChunk];
+  int32_t elem[kChunk];
+  int8_t fly[kChunk];
+};
+static_assert(sizeof(ParticleStage) == 2720, "stage layout");
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void stage_load(const WalkParams &P, int chunk, ParticleStage *st,
+                                           uint32_t bar, int lane) {
+  const long long base = (long long)P.begin + (long long)chunk * kChunk;
+  const int count = (int)min((long long)kChunk, (long long)P.end - base);
+  if (count == kChunk && P.bulk_ok) {
+    if (lane == 0) {
+      const uint32_t bytes = 3u * 256u + 128u + (P.origin ? 768u : 0u) + (P.dest ? 768u + 256u : 0u) +
+                             (P.flying ? 32u : 0u);
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(smem_u32(st->px), P.px + base, 256u, bar);
+      bulk_g2s(smem_u32(st->py), P.py + base, 256u, bar);
+      bulk_g2s(smem_u32(st->pz), P.pz + base, 256u, bar);
+      bulk_g2s(smem_u32(st->elem), P.elem + base, 128u, bar);
+      if (P.origin) bulk_g2s(smem_u32(st->origin), P.origin + 3 * base, 768u, bar);
+      if (P.dest) {
+        bulk_g2s(smem_u32(st->dest), P.dest + 3 * base, 768u, bar);
+        bulk_g2s(smem_u32(st->w), P.weights + base, 256u, bar);
+      }
+      if (P.flying) bulk_g2s(smem_u32(st->fly), P.flying + base, 32u, bar);
+    }
+  } else {
+    // ragged last chunk, or caller pointers that are not 16-byte aligned
+    if (lane < count) {
+      const long long i = base + lane;
+      st->px[lane] = P.px[i]; st->py[lane] = P.py[i]; st->pz[lane] = P.pz[i];
+      st->elem[lane] = P.elem[i];
+      if (P.origin)
+        for (int k = 0; k < 3; ++k) st->origin[3 * lane + k] = P.origin[3 * i + k];
+      if (P.dest) {
+        for (int k = 0; k < 3; ++k) st->dest[3 * lane + k] = P.dest[3 * i + k];
+        st->w[lane] = P.weights[i];
+      }
+      if (P.flying) st->fly[lane] = P.flying[i];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+  }
+}
+
+// begin_particle() reading the staged copy instead of global memory
+__device__ __forceinline__ void begin_from_stage(const WalkParams &P, const ParticleStage *st, int s,
+                                                 Ray &r, Counters &c) {
+  r.stage = kStageDone;
+  const bool fly = P.flying ? (st->fly[s] == 1) : true;
+  if (!fly) return;
+  const double x = st->px[s], y = st->py[s], z = st->pz[s];
+  r.e = st->elem[s];
+  if (P.origin) {
+    const double tx = st->origin[3 * s], ty = st->origin[3 * s + 1], tz = st->origin[3 * s + 2];
+    if (tx != x || ty != y || tz != z) {
+      set_ray(r, x, y, z, tx, ty, tz);
+      r.wl = 0.0;
+      r.stage = kStageReloc;
+      return;
+    }
+  }
+  if (P.dest) {
+    set_ray(r, x, y, z, st->dest[3 * s], st->dest[3 * s + 1], st->dest[3 * s + 2]);
+    const double len = sqrt(r.ux * r.ux + r.uy * r.uy + r.uz * r.uz);
+    r.wl = st->w[s] * len;
+    r.stage = kStageTally;
+    c.tracks++;
+  }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) walk_persist_kernel(const WalkParams P) {
+  constexpr int WARPS = BLOCK / 32;
+  __shared__ ParticleStage stages[WARPS][2];
+  __shared__ __align__(8) unsigned long long bars[WARPS][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t bar0 = smem_u32(&bars[warp][0]);
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int total = P.end - P.begin;
+  const int nchunks = (total + kChunk - 1) / kChunk;
+  auto claim = [&]() -> int {
+    int c = 0;
+    if (lane == 0) c = (int)atomicAdd(P.work_counter, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    return c < nchunks ? c : -1;
+  };
+
+  int cur = 0, cursor = 0, cur_count = 0;
+  uint32_t parity = 0;  // bit b = phase parity of stage b
+  int chunk_cur = claim();
+  if (chunk_cur >= 0) stage_load(P, chunk_cur, &stages[warp][0], bar0, lane);
+  int chunk_next = chunk_cur >= 0 ? claim() : -1;
+  if (chunk_next >= 0) stage_load(P, chunk_next, &stages[warp][1], bar0 + 8, lane);
+  if (chunk_cur >= 0) {
+    mbar_wait(bar0, 0);
+    parity ^= 1u;
+    cur_count = min(kChunk, total - chunk_cur * kChunk);
+  }
+
+  Counters c;
+  Ray r;
+  r.stage = kStageDone;
+  int my_i = 0;
+  for (;;) {
+    unsigned idle = __ballot_sync(0xffffffffu, r.stage == kStageDone);
+    while (idle != 0u && cur_count > 0) {
+      const int slot = cursor + __popc(idle & ((1u << lane) - 1u));
+      if (r.stage == kStageDone && slot < cur_count) {
+        my_i = P.begin + chunk_cur * kChunk + slot;
+        begin_from_stage(P, &stages[warp][cur], slot, r, c);
+      }
+      __syncwarp();
+      cursor += __popc(idle);
+      if (cursor >= cur_count) {
+        // every slot of this stage has been handed out: recycle it for the chunk after next
+        const int recycled = cur;
+        chunk_cur = chunk_next;
+        cur ^= 1;
+        cursor = 0;
+        cur_count = 0;
+        chunk_next = -1;
+        if (chunk_cur >= 0) {
+          mbar_wait(bar0 + 8 * cur, (parity >> cur) & 1u);
+          parity ^= 1u << cur;
+          cur_count = min(kChunk, total - chunk_cur * kChunk);
+          chunk_next = claim();
+          if (chunk_next >= 0) {
+            if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            stage_load(P, chunk_next, &stages[warp][recycled], bar0 + 8 * recycled, lane);
+          }
+        }
+      }
+      idle = __ballot_sync(0xffffffffu, r.stage == kStageDone);
+    }
+    if (idle == 0xffffffffu) break;  // no lane active and nothing left to hand out
+    if (r.stage != kStageDone) {
+      const double *rec = P.tets[r.e].d;
+      double raw[16];
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        load_face_256(rec + 4 * f, raw[4 * f], raw[4 * f + 1], raw[4 * f + 2], raw[4 * f + 3]);
+      TetPlanes t;
+      decode_record(raw, t);
+      double texit;
+      int32_t next;
+      exit_face(t, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, texit, next);
+      advance(P, my_i, r, texit, next, c, true);
+    }
+  }
+  flush_counters(P, c);
+}
+
 // ------------------------------------------------------------ small kernels
 
 // K14-K16 of SURVEY.md 2b (PumiTallyImpl.cpp:492-528): every particle starts
@@ -234,6 +415,30 @@ cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_
     case kVariantQuad: {
       const unsigned grid = (unsigned)((4 * n + block - 1) / block);
       walk_quad_kernel<<<grid, block, 0, stream>>>(p);
+      break;
+    }
+    case kVariantPersist: {
+      static int sms = 0, occ[3] = {0, 0, 0};
+      const int bi = block == 64 ? 0 : (block == 128 ? 1 : 2);
+      if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      }
+      if (!occ[bi]) {
+        if (block == 64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[bi], walk_persist_kernel<64>, 64, 0);
+        else if (block == 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[bi], walk_persist_kernel<128>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[bi], walk_persist_kernel<256>, 256, 0);
+        if (occ[bi] < 1) occ[bi] = 1;
+      }
+      const long long nchunks = (n + kChunk - 1) / kChunk;
+      const long long want = (nchunks + block / 32 - 1) / (block / 32);
+      const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * occ[bi]);
+      cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream);
+      if (e != cudaSuccess) return e;
+      if (block == 64) walk_persist_kernel<64><<<grid, 64, 0, stream>>>(p);
+      else if (block == 128) walk_persist_kernel<128><<<grid, 128, 0, stream>>>(p);
+      else walk_persist_kernel<256><<<grid, 256, 0, stream>>>(p);
       break;
     }
     default:

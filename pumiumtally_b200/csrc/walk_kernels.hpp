@@ -12,7 +12,8 @@ enum WalkVariant : int {
   kVariantLdg = 0,   // thread per particle, 4 x 256-bit loads of the tet record
   kVariantBulk = 1,  // thread per particle, record staged in smem by cp.async.bulk + mbarrier
   kVariantQuad = 2,  // 4 lanes per particle (lane per face), coalesced 32 B loads
-  kNumVariants = 3
+  kVariantPersist = 3,  // persistent warps, TMA-staged particle chunks, per-lane refill
+  kNumVariants = 4
 };
 
 cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_t stream);

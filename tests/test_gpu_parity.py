@@ -17,7 +17,7 @@ from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
 from test_oracle_golden import golden_scenario
 
 pytestmark = pytest.mark.gpu
-VARIANTS = [0, 1, 2]
+VARIANTS = [0, 1, 2, 3]
 
 
 def gpu_engine(variant, block=128, chunk=None):

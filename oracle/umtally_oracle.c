@@ -313,7 +313,7 @@ static int search(um_oracle *o, int initial, int weighted) {
   if (o->per_particle) {
     long long lost = 0;
 #ifdef _OPENMP
-#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : segs, cross, lost)
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : segs, cross, lost)
 #endif
     for (int p = 0; p < n; ++p) {
       int loops = 0;

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <stdexcept>
 
+#include "seed_grid.hpp"
 #include "vtk_writer.hpp"
 
 namespace ptb {
@@ -79,6 +80,7 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
   cuda_or_throw(launch_init_particles(d_px_, d_py_, d_pz_, d_elem_, n_, mesh_.centroid0[0],
                                       mesh_.centroid0[1], mesh_.centroid0[2], compute_), "init particles");
   cuda_or_throw(cudaStreamSynchronize(compute_), "init sync");
+  build_seed_grid();
   // the packed records are only needed on the device from here on
   std::vector<TetRecord>().swap(mesh_.records);
   printf("[INFO] pumitally-b200: %lld elements, %d particles on CUDA device %d\n",
@@ -97,8 +99,45 @@ Engine::~Engine() {
   cudaFree(d_origin_); cudaFree(d_dest_); cudaFree(d_weights_); cudaFree(d_flying_);
   cudaFree(d_stats_);
   cudaFree(d_tickets_);
+  cudaFree(d_grid_);
   if (compute_) cudaStreamDestroy(compute_);
   if (copy_) cudaStreamDestroy(copy_);
+}
+
+// Localise the seed point of every grid cell with the walk kernel itself (from the centroid of
+// element 0, like any particle) and keep the tet for cells whose seed point lies in the mesh.
+void Engine::build_seed_grid() {
+  grid_ = choose_seed_grid(mesh_);
+  const int32_t ncell = grid_.nx * grid_.ny * grid_.nz;
+  double *xyz = nullptr, *tx = nullptr, *ty = nullptr, *tz = nullptr;
+  int32_t *te = nullptr;
+  dev_alloc(&d_grid_, size_t(ncell), "seed grid");
+  dev_alloc(&xyz, 3 * size_t(ncell), "seed points");
+  dev_alloc(&tx, size_t(ncell), "seed tmp");
+  dev_alloc(&ty, size_t(ncell), "seed tmp");
+  dev_alloc(&tz, size_t(ncell), "seed tmp");
+  dev_alloc(&te, size_t(ncell), "seed tmp");
+  cuda_or_throw(launch_seed_points(grid_, xyz, compute_), "seed points");
+  cuda_or_throw(launch_init_particles(tx, ty, tz, te, ncell, mesh_.centroid0[0], mesh_.centroid0[1],
+                                      mesh_.centroid0[2], compute_), "seed init");
+  WalkParams p{};
+  p.tets = d_tets_;
+  p.flux = d_flux_;
+  p.px = tx; p.py = ty; p.pz = tz;
+  p.elem = te;
+  p.origin = xyz;
+  p.begin = 0;
+  p.end = ncell;
+  p.max_iters = int32_t(std::min<int64_t>(mesh_.ntets + 16, INT_MAX));
+  p.bulk_ok = 1;
+  p.work_counter = d_tickets_;
+  p.stats = d_stats_;
+  cuda_or_throw(launch_walk(p, kVariantPersist, 128, compute_), "seed walk");
+  cuda_or_throw(launch_seed_finalize(xyz, tx, ty, tz, te, d_grid_, ncell, compute_), "seed finalize");
+  cuda_or_throw(cudaStreamSynchronize(compute_), "seed sync");
+  cuda_or_throw(cudaMemset(d_stats_, 0, sizeof(DeviceStats)), "memset");
+  cudaFree(xyz); cudaFree(tx); cudaFree(ty); cudaFree(tz); cudaFree(te);
+  grid_.cell_tet = d_grid_;
 }
 
 void Engine::collect_timers(bool wait) {
@@ -134,6 +173,8 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   p.end = end;
   p.max_iters = int32_t(std::min<int64_t>(mesh_.ntets + 16, INT_MAX));
   p.stats = d_stats_;
+  p.grid = grid_;
+  if (!use_seed_grid_) p.grid.cell_tet = nullptr;
   p.work_counter = d_tickets_ + (ticket_next_++ % kTicketRing);
   auto aligned16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   p.bulk_ok = (begin % 16 == 0) && aligned16(d_origin) && aligned16(d_dest) && aligned16(d_flying) &&
@@ -342,7 +383,9 @@ int Engine::set_option(const std::string &name, int64_t v) {
     block_ = int(v);
   } else if (name == "chunk") {
     if (v < 1024) return 1;
-    chunk_ = int32_t(std::min<int64_t>(v, INT_MAX));
+    chunk_ = int32_t(std::min<int64_t>(v, INT_MAX)) & ~1023;  // keeps every range 16-byte aligned
+  } else if (name == "seed_grid") {
+    use_seed_grid_ = v != 0;
   } else {
     return 1;
   }

@@ -65,6 +65,7 @@ class Engine {
                    bool timed);
   bool host_is_pinned(const void *p) const;
   void collect_timers(bool wait);
+  void build_seed_grid();
 
   HostMesh mesh_;
   int32_t n_ = 0;
@@ -77,6 +78,7 @@ class Engine {
   int variant_ = kVariantPersist;
   int block_ = 128;
   int32_t chunk_ = 1 << 20;  // particles per H2D/compute pipeline stage
+  bool use_seed_grid_ = true;
 
   // device memory
   TetRecord *d_tets_ = nullptr;
@@ -88,6 +90,8 @@ class Engine {
   DeviceStats *d_stats_ = nullptr;
   unsigned int *d_tickets_ = nullptr;  // ring of chunk counters for the persistent kernel
   unsigned ticket_next_ = 0;
+  SeedGrid grid_{};              // relocation seed grid (grid_.cell_tet lives in d_grid_)
+  int32_t *d_grid_ = nullptr;
 
   cudaStream_t compute_ = nullptr, copy_ = nullptr;
   struct TimerPair { cudaEvent_t a, b; };

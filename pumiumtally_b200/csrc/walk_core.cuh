@@ -112,6 +112,31 @@ struct DeviceStats {
 
 struct TetRecord;
 
+// Uniform background grid over the mesh bounding box: cell -> the tet that
+// contains the cell centre (-1 if the centre is outside the mesh).  A far
+// relocation (re-sampled particle, initial localisation) starts its tally-off
+// walk at the centre of the target's cell instead of at the particle's old
+// position.  For a target inside the mesh both walks end in the tet that
+// contains it, so the result is the reference's; if the seeded walk meets the
+// hull the kernel falls back to the reference walk from the old position,
+// which also reproduces the clip point of an out-of-mesh target.
+struct SeedGrid {
+  const int32_t *cell_tet;  // [nx*ny*nz]; nullptr = grid disabled
+  double x0, y0, z0;        // low corner of the bounding box
+  double h, inv_h;          // cell edge and its reciprocal
+  double far2;              // seed only when |target - position|^2 exceeds this
+  int32_t nx, ny, nz;
+};
+
+// Seed point of cell (cx,cy,cz): deliberately off-centre so that structured
+// meshes whose cell centres lie on tet faces/edges do not start every seeded
+// walk in a degenerate position.  Explicit fma: identical on host and device.
+PTB_HD void seed_point(const SeedGrid &g, int cx, int cy, int cz, double &x, double &y, double &z) {
+  x = fma(cx + 0.41421356237, g.h, g.x0);
+  y = fma(cy + 0.57735026919, g.h, g.y0);
+  z = fma(cz + 0.31830988618, g.h, g.z0);
+}
+
 // One launch = one particle range of one MoveToNextLocation / CopyInitialPosition.
 struct WalkParams {
   const TetRecord *tets;   // [E] packed records
@@ -127,11 +152,13 @@ struct WalkParams {
   int32_t bulk_ok;         // all particle arrays 16-byte aligned: cp.async.bulk staging allowed
   unsigned int *work_counter;  // chunk ticket of the persistent kernel (zeroed per launch)
   DeviceStats *stats;
+  SeedGrid grid;
 };
 
 constexpr int kStageReloc = 0;  // phase 1: move to caller's origin, tally off
 constexpr int kStageTally = 1;  // phase 2: fly to destination, tally on
 constexpr int kStageDone = 2;
+constexpr int kStageSeed = 3;   // phase 1 started from a seed-grid cell centre
 
 struct Ray {
   double ox, oy, oz;  // ray origin (fixed for the whole walk)
@@ -167,6 +194,32 @@ PTB_HD void start_tally(const WalkParams &P, int i, Ray &r, double x, double y, 
   if (writer) c.tracks++;
 }
 
+// Phase 1 for a particle at (x,y,z) in tet r.e whose caller-side origin is (tx,ty,tz).
+PTB_HD void start_reloc(const WalkParams &P, Ray &r, double x, double y, double z, double tx,
+                        double ty, double tz) {
+  r.wl = 0.0;  // p_wgt = 0 during relocation (Impl.cpp:105)
+  const SeedGrid &g = P.grid;
+  if (g.cell_tet) {
+    const double dx = tx - x, dy = ty - y, dz = tz - z;
+    const double fx = (tx - g.x0) * g.inv_h, fy = (ty - g.y0) * g.inv_h, fz = (tz - g.z0) * g.inv_h;
+    if (dx * dx + dy * dy + dz * dz > g.far2 && fx >= 0.0 && fy >= 0.0 && fz >= 0.0 &&
+        fx < (double)g.nx && fy < (double)g.ny && fz < (double)g.nz) {
+      const int cx = (int)fx, cy = (int)fy, cz = (int)fz;
+      const int32_t seed = PTB_LDG(g.cell_tet + ((size_t)cz * g.ny + cy) * g.nx + cx);
+      if (seed >= 0) {
+        double sx, sy, sz;
+        seed_point(g, cx, cy, cz, sx, sy, sz);
+        set_ray(r, sx, sy, sz, tx, ty, tz);
+        r.e = seed;
+        r.stage = kStageSeed;
+        return;
+      }
+    }
+  }
+  set_ray(r, x, y, z, tx, ty, tz);
+  r.stage = kStageReloc;
+}
+
 // K1/K2/K3 of the reference folded into the prologue: pick the walk target.
 PTB_HD void begin_particle(const WalkParams &P, int i, Ray &r, Counters &c, bool writer) {
   r.stage = kStageDone;
@@ -178,9 +231,7 @@ PTB_HD void begin_particle(const WalkParams &P, int i, Ray &r, Counters &c, bool
     const double tx = PTB_LDG(P.origin + 3 * (size_t)i), ty = PTB_LDG(P.origin + 3 * (size_t)i + 1),
                  tz = PTB_LDG(P.origin + 3 * (size_t)i + 2);
     if (tx != x || ty != y || tz != z) {
-      set_ray(r, x, y, z, tx, ty, tz);
-      r.wl = 0.0;  // p_wgt = 0 during relocation (Impl.cpp:105)
-      r.stage = kStageReloc;
+      start_reloc(P, r, x, y, z, tx, ty, tz);
       return;
     }
   }
@@ -191,12 +242,21 @@ PTB_HD void begin_particle(const WalkParams &P, int i, Ray &r, Counters &c, bool
 PTB_HD void end_ray(const WalkParams &P, int i, Ray &r, bool reached, double tnew, Counters &c,
                     bool writer) {
   double x, y, z;
+  if (r.stage == kStageSeed && !reached) {
+    // the target is not reachable from the seed inside the mesh (it lies outside the hull):
+    // redo phase 1 exactly as the reference does, from the particle's stored position
+    x = P.px[i]; y = P.py[i]; z = P.pz[i];
+    r.e = P.elem[i];
+    set_ray(r, x, y, z, r.tx, r.ty, r.tz);
+    r.stage = kStageReloc;
+    return;
+  }
   if (reached) {  // tracer commit: origin <- dest, exactly (test lines 323-346)
     x = r.tx; y = r.ty; z = r.tz;
   } else {  // vacuum BC: dest <- intersection point (Impl.cpp:275-281)
     x = fma(tnew, r.ux, r.ox); y = fma(tnew, r.uy, r.oy); z = fma(tnew, r.uz, r.oz);
   }
-  if (r.stage == kStageReloc && P.dest) {
+  if (r.stage != kStageTally && P.dest) {
     start_tally(P, i, r, x, y, z, c, writer);  // phase 2 starts where phase 1 ended
   } else {
     if (writer) {
@@ -224,7 +284,7 @@ PTB_HD void advance(const WalkParams &P, int i, Ray &r, double texit, int32_t ne
   r.iters++;
   const bool over = r.iters >= P.max_iters;
   if (reached || hull || over) {
-    if (over && !reached && !hull && writer) c.lost++;
+    if (over && !reached && !hull && writer && r.stage != kStageSeed) c.lost++;
     end_ray(P, i, r, reached, tnew, c, writer);
   } else {
     r.e = next;  // UpdateCurrentElement (Impl.cpp:247-253)

@@ -270,9 +270,7 @@ __device__ __forceinline__ void begin_from_stage(const WalkParams &P, const Part
   if (P.origin) {
     const double tx = st->origin[3 * s], ty = st->origin[3 * s + 1], tz = st->origin[3 * s + 2];
     if (tx != x || ty != y || tz != z) {
-      set_ray(r, x, y, z, tx, ty, tz);
-      r.wl = 0.0;
-      r.stage = kStageReloc;
+      start_reloc(P, r, x, y, z, tx, ty, tz);
       return;
     }
   }
@@ -285,20 +283,96 @@ __device__ __forceinline__ void begin_from_stage(const WalkParams &P, const Part
   }
 }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) walk_persist_kernel(const WalkParams P) {
+// Fetch modes of the persistent kernel (how a lane gets its 128-byte tet record):
+//   0  four plain 256-bit loads
+//   1  as 0, tet loads carry an L2 evict_last policy and skip L1; the particle stream
+//      (staging copies, state stores) is evict_first -- keeps the tet table L2-resident
+//   2  as 1, plus the L2::128B prefetch size (first sector miss pulls the whole line)
+//   3  one cp.async.bulk of 128 B per lane into a shared-memory row (policies as 1)
+enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3 };
+
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+  uint64_t p;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes,
+                                              uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], "
+      "%2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+      : "memory");
+}
+template <int FETCH>
+__device__ __forceinline__ void load_face(const double *p, uint64_t pol, double &a, double &b,
+                                          double &c, double &d) {
+  if constexpr (FETCH == kFetchPolicy)
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+        : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
+  else if constexpr (FETCH == kFetchPolicy128)
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::128B.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+        : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
+  else
+    load_face_256(p, a, b, c, d);
+}
+
+// stage_load() with an L2 policy on the streamed particle data
+__device__ __forceinline__ void stage_load_hint(const WalkParams &P, int chunk, ParticleStage *st,
+                                                uint32_t bar, int lane, uint64_t pol) {
+  const long long base = (long long)P.begin + (long long)chunk * kChunk;
+  const int count = (int)min((long long)kChunk, (long long)P.end - base);
+  if (count == kChunk && P.bulk_ok) {
+    if (lane == 0) {
+      const uint32_t bytes = 3u * 256u + 128u + (P.origin ? 768u : 0u) + (P.dest ? 768u + 256u : 0u) +
+                             (P.flying ? 32u : 0u);
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s_hint(smem_u32(st->px), P.px + base, 256u, bar, pol);
+      bulk_g2s_hint(smem_u32(st->py), P.py + base, 256u, bar, pol);
+      bulk_g2s_hint(smem_u32(st->pz), P.pz + base, 256u, bar, pol);
+      bulk_g2s_hint(smem_u32(st->elem), P.elem + base, 128u, bar, pol);
+      if (P.origin) bulk_g2s_hint(smem_u32(st->origin), P.origin + 3 * base, 768u, bar, pol);
+      if (P.dest) {
+        bulk_g2s_hint(smem_u32(st->dest), P.dest + 3 * base, 768u, bar, pol);
+        bulk_g2s_hint(smem_u32(st->w), P.weights + base, 256u, bar, pol);
+      }
+      if (P.flying) bulk_g2s_hint(smem_u32(st->fly), P.flying + base, 32u, bar, pol);
+    }
+  } else {
+    stage_load(P, chunk, st, bar, lane);  // ragged / unaligned: plain path
+  }
+}
+
+template <int BLOCK, int FETCH, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkParams P) {
   constexpr int WARPS = BLOCK / 32;
+  constexpr bool kBulkTets = FETCH == kFetchBulk;
   __shared__ ParticleStage stages[WARPS][2];
-  __shared__ __align__(8) unsigned long long bars[WARPS][2];
+  __shared__ __align__(8) unsigned long long bars[WARPS][3];
+  __shared__ __align__(128) unsigned char rows[kBulkTets ? WARPS : 1][kBulkTets ? 32 * kRowBytes : 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t bar0 = smem_u32(&bars[warp][0]);
+  const uint32_t bar_row = bar0 + 16;
+  const uint32_t row = smem_u32(&rows[kBulkTets ? warp : 0][kBulkTets ? lane * kRowBytes : 0]);
   if (lane == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
+    mbar_init(bar_row, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncwarp();
+  const uint64_t keep = FETCH != kFetchPlain ? l2_policy_keep() : 0;
+  const uint64_t strm = FETCH != kFetchPlain ? l2_policy_stream() : 0;
+  auto load_stage = [&](int chunk, ParticleStage *st, uint32_t bar) {
+    if constexpr (FETCH == kFetchPlain) stage_load(P, chunk, st, bar, lane);
+    else stage_load_hint(P, chunk, st, bar, lane, strm);
+  };
 
   const int total = P.end - P.begin;
   const int nchunks = (total + kChunk - 1) / kChunk;
@@ -310,11 +384,11 @@ __global__ void __launch_bounds__(BLOCK) walk_persist_kernel(const WalkParams P)
   };
 
   int cur = 0, cursor = 0, cur_count = 0;
-  uint32_t parity = 0;  // bit b = phase parity of stage b
+  uint32_t parity = 0;  // bit b = phase parity of barrier b (0,1 particle stages; 2 tet rows)
   int chunk_cur = claim();
-  if (chunk_cur >= 0) stage_load(P, chunk_cur, &stages[warp][0], bar0, lane);
+  if (chunk_cur >= 0) load_stage(chunk_cur, &stages[warp][0], bar0);
   int chunk_next = chunk_cur >= 0 ? claim() : -1;
-  if (chunk_next >= 0) stage_load(P, chunk_next, &stages[warp][1], bar0 + 8, lane);
+  if (chunk_next >= 0) load_stage(chunk_next, &stages[warp][1], bar0 + 8);
   if (chunk_cur >= 0) {
     mbar_wait(bar0, 0);
     parity ^= 1u;
@@ -350,19 +424,34 @@ __global__ void __launch_bounds__(BLOCK) walk_persist_kernel(const WalkParams P)
           chunk_next = claim();
           if (chunk_next >= 0) {
             if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            stage_load(P, chunk_next, &stages[warp][recycled], bar0 + 8 * recycled, lane);
+            load_stage(chunk_next, &stages[warp][recycled], bar0 + 8 * recycled);
           }
         }
       }
       idle = __ballot_sync(0xffffffffu, r.stage == kStageDone);
     }
     if (idle == 0xffffffffu) break;  // no lane active and nothing left to hand out
+    double raw[16];
+    if constexpr (kBulkTets) {
+      const unsigned act = ~idle;
+      if (lane == __ffs(act) - 1) mbar_expect_tx(bar_row, 128u * __popc(act));
+      if (r.stage != kStageDone) bulk_g2s_hint(row, P.tets + r.e, 128u, bar_row, keep);
+      mbar_wait(bar_row, (parity >> 2) & 1u);
+      parity ^= 4u;
+    }
     if (r.stage != kStageDone) {
-      const double *rec = P.tets[r.e].d;
-      double raw[16];
+      if constexpr (kBulkTets) {
 #pragma unroll
-      for (int f = 0; f < 4; ++f)
-        load_face_256(rec + 4 * f, raw[4 * f], raw[4 * f + 1], raw[4 * f + 2], raw[4 * f + 3]);
+        for (int j = 0; j < 8; ++j)
+          asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];"
+                       : "=d"(raw[2 * j]), "=d"(raw[2 * j + 1])
+                       : "r"(row + 16 * j));
+      } else {
+        const double *rec = P.tets[r.e].d;
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+          load_face<FETCH>(rec + 4 * f, keep, raw[4 * f], raw[4 * f + 1], raw[4 * f + 2], raw[4 * f + 3]);
+      }
       TetPlanes t;
       decode_record(raw, t);
       double texit;
@@ -372,6 +461,28 @@ __global__ void __launch_bounds__(BLOCK) walk_persist_kernel(const WalkParams P)
     }
   }
   flush_counters(P, c);
+}
+
+template <int BLOCK, int FETCH, int MINB>
+cudaError_t launch_persist(const WalkParams &p, long long n, cudaStream_t stream) {
+  static int sms = 0, occ = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // leave as much of the unified L1/smem array to shared memory as the kernel can use
+    cudaFuncSetAttribute(walk_persist_kernel<BLOCK, FETCH, MINB>,
+                         cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_persist_kernel<BLOCK, FETCH, MINB>, BLOCK, 0);
+    if (occ < 1) occ = 1;
+  }
+  const long long nchunks = (n + kChunk - 1) / kChunk;
+  const long long want = (nchunks + BLOCK / 32 - 1) / (BLOCK / 32);
+  const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * occ);
+  cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return e;
+  walk_persist_kernel<BLOCK, FETCH, MINB><<<grid, BLOCK, 0, stream>>>(p);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------ small kernels
@@ -384,6 +495,30 @@ __global__ void init_particles_kernel(double *px, double *py, double *pz, int32_
   if (i < n) {
     px[i] = cx; py[i] = cy; pz[i] = cz;
     elem[i] = 0;
+  }
+}
+
+// Seed grid construction: the seed points are written as "particles to
+// localise", walked with the ordinary kernel, and a cell keeps the tet only if
+// its seed point was reached (i.e. lies inside the mesh).
+__global__ void seed_points_kernel(SeedGrid g, double *xyz, int32_t ncell) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ncell) {
+    const int cx = i % g.nx, cy = (i / g.nx) % g.ny, cz = i / (g.nx * g.ny);
+    double x, y, z;
+    seed_point(g, cx, cy, cz, x, y, z);
+    xyz[3 * (size_t)i] = x; xyz[3 * (size_t)i + 1] = y; xyz[3 * (size_t)i + 2] = z;
+  }
+}
+
+__global__ void seed_finalize_kernel(const double *xyz, const double *px, const double *py,
+                                     const double *pz, const int32_t *elem, int32_t *cell_tet,
+                                     int32_t ncell) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ncell) {
+    const bool reached = px[i] == xyz[3 * (size_t)i] && py[i] == xyz[3 * (size_t)i + 1] &&
+                         pz[i] == xyz[3 * (size_t)i + 2];
+    cell_tet[i] = reached ? elem[i] : -1;
   }
 }
 
@@ -417,30 +552,18 @@ cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_
       walk_quad_kernel<<<grid, block, 0, stream>>>(p);
       break;
     }
-    case kVariantPersist: {
-      static int sms = 0, occ[3] = {0, 0, 0};
-      const int bi = block == 64 ? 0 : (block == 128 ? 1 : 2);
-      if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      }
-      if (!occ[bi]) {
-        if (block == 64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[bi], walk_persist_kernel<64>, 64, 0);
-        else if (block == 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[bi], walk_persist_kernel<128>, 128, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[bi], walk_persist_kernel<256>, 256, 0);
-        if (occ[bi] < 1) occ[bi] = 1;
-      }
-      const long long nchunks = (n + kChunk - 1) / kChunk;
-      const long long want = (nchunks + block / 32 - 1) / (block / 32);
-      const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * occ[bi]);
-      cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream);
-      if (e != cudaSuccess) return e;
-      if (block == 64) walk_persist_kernel<64><<<grid, 64, 0, stream>>>(p);
-      else if (block == 128) walk_persist_kernel<128><<<grid, 128, 0, stream>>>(p);
-      else walk_persist_kernel<256><<<grid, 256, 0, stream>>>(p);
-      break;
-    }
+    case kVariantPersist:
+      if (block == 64) return launch_persist<64, kFetchPlain, 14>(p, n, stream);
+      if (block == 256) return launch_persist<256, kFetchPlain, 3>(p, n, stream);
+      return launch_persist<128, kFetchPlain, 7>(p, n, stream);
+    case kVariantPersistPolicy:
+      return launch_persist<128, kFetchPolicy, 7>(p, n, stream);
+    case kVariantPersistPolicy128:
+      return launch_persist<128, kFetchPolicy128, 7>(p, n, stream);
+    case kVariantPersistBulk:
+      return launch_persist<128, kFetchBulk, 5>(p, n, stream);
+    case kVariantPersistPolicy128Occ8:
+      return launch_persist<128, kFetchPolicy128, 8>(p, n, stream);
     default:
       return cudaErrorInvalidValue;
   }
@@ -451,6 +574,19 @@ cudaError_t launch_init_particles(double *px, double *py, double *pz, int32_t *e
                                   double cx, double cy, double cz, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   init_particles_kernel<<<(n + 255) / 256, 256, 0, stream>>>(px, py, pz, elem, n, cx, cy, cz);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_seed_points(const SeedGrid &g, double *xyz, cudaStream_t stream) {
+  const int32_t ncell = g.nx * g.ny * g.nz;
+  seed_points_kernel<<<(ncell + 255) / 256, 256, 0, stream>>>(g, xyz, ncell);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_seed_finalize(const double *xyz, const double *px, const double *py,
+                                 const double *pz, const int32_t *elem, int32_t *cell_tet,
+                                 int32_t ncell, cudaStream_t stream) {
+  seed_finalize_kernel<<<(ncell + 255) / 256, 256, 0, stream>>>(xyz, px, py, pz, elem, cell_tet, ncell);
   return cudaGetLastError();
 }
 

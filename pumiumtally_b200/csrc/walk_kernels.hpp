@@ -13,10 +13,18 @@ enum WalkVariant : int {
   kVariantBulk = 1,  // thread per particle, record staged in smem by cp.async.bulk + mbarrier
   kVariantQuad = 2,  // 4 lanes per particle (lane per face), coalesced 32 B loads
   kVariantPersist = 3,  // persistent warps, TMA-staged particle chunks, per-lane refill
-  kNumVariants = 4
+  kVariantPersistPolicy = 4,         // 3 + L2 evict_last on tets / evict_first on the particle stream
+  kVariantPersistPolicy128 = 5,      // 4 + L2::128B prefetch size on tet loads
+  kVariantPersistBulk = 6,           // 4 with tet records fetched by cp.async.bulk into smem rows
+  kVariantPersistPolicy128Occ8 = 7,  // 5 compiled for 8 resident blocks (64 registers)
+  kNumVariants = 8
 };
 
 cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_t stream);
+cudaError_t launch_seed_points(const SeedGrid &g, double *xyz, cudaStream_t stream);
+cudaError_t launch_seed_finalize(const double *xyz, const double *px, const double *py,
+                                 const double *pz, const int32_t *elem, int32_t *cell_tet,
+                                 int32_t ncell, cudaStream_t stream);
 cudaError_t launch_init_particles(double *px, double *py, double *pz, int32_t *elem, int32_t n,
                                   double cx, double cy, double cz, cudaStream_t stream);
 cudaError_t launch_normalize(const double *flux, const double *volume, double *out, int64_t n,

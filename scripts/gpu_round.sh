@@ -16,7 +16,7 @@ tests)
   timeout 1500 python -m pytest tests -m gpu -q --timeout=600 > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/summary.txt"
   tail -15 "$OUT/pytest_gpu.log";;
 bench)
-  for v in 0 1 2 3; do for b in 128 256; do
+  for v in ${VARIANTS:-3 4 5 6 7}; do for b in 128; do
     timeout 600 python bench.py --steps 5 --warmup 3 --variant $v --block $b --no-cpu --no-e2e > "$OUT/bench_v${v}_b${b}.json" 2> "$OUT/bench_v${v}_b${b}.err"
     echo "bench v$v b$b rc=$? $(python - "$OUT/bench_v${v}_b${b}.json" <<'PY'
 import json,sys

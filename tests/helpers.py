@@ -70,7 +70,7 @@ def emul_lib():
         srcs = [os.path.join(HERE, "host_emul", "emul_walk.cpp"),
                 os.path.join(ROOT, "pumiumtally_b200", "csrc", "tet_mesh.cpp"),
                 os.path.join(ROOT, "pumiumtally_b200", "csrc", "osh_reader.cpp")]
-        deps = srcs + [os.path.join(ROOT, "pumiumtally_b200", "csrc", h) for h in ("walk_core.cuh", "tet_mesh.hpp")]
+        deps = srcs + [os.path.join(ROOT, "pumiumtally_b200", "csrc", h) for h in ("walk_core.cuh", "tet_mesh.hpp", "seed_grid.hpp")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp",
                                    "-I", os.path.join(ROOT, "pumiumtally_b200", "csrc"),
@@ -85,6 +85,8 @@ def emul_lib():
         L.ptb_emul_move.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ptb_emul_get.argtypes = [C.c_void_p] * 6
         L.ptb_emul_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        L.ptb_emul_build_grid.argtypes = [C.c_void_p]
+        L.ptb_emul_grid_dims.argtypes = [C.c_void_p, C.c_void_p]
         L.ptb_emul_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _EMUL = L
     return _EMUL
@@ -93,8 +95,9 @@ def emul_lib():
 class HostEmulTally:
     """The CUDA kernels' per-ray state machine compiled for the host (tests only)."""
 
-    def __init__(self, coords=None, tet2vert=None, num_particles=0, spec=None):
+    def __init__(self, coords=None, tet2vert=None, num_particles=0, spec=None, seed_grid=False):
         self._L = emul_lib()
+        self._want_grid = seed_grid
         self.num_particles = int(num_particles)
         if spec is not None:
             self._h = self._L.ptb_emul_create_spec(spec.encode(), self.num_particles)
@@ -107,6 +110,12 @@ class HostEmulTally:
         sz = np.zeros(2, dtype=np.int64)
         self._L.ptb_emul_sizes(self._h, sz.ctypes.data)
         self.num_verts, self.num_elements = int(sz[0]), int(sz[1])
+        self.grid_valid_cells = self._L.ptb_emul_build_grid(self._h) if seed_grid else 0
+
+    def grid_dims(self):
+        d = np.zeros(3, dtype=np.int32)
+        self._L.ptb_emul_grid_dims(self._h, d.ctypes.data)
+        return tuple(int(x) for x in d)
 
     def __del__(self):
         if getattr(self, "_h", None):

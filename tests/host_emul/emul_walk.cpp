@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "seed_grid.hpp"
 #include "tet_mesh.hpp"
 #include "walk_core.cuh"
 
@@ -23,16 +24,44 @@ struct Emul {
   std::vector<int32_t> elem;
   DeviceStats stats{};
   int n = 0;
+  SeedGrid grid{};
+  std::vector<int32_t> cell_tet;
+  // same construction as Engine::build_seed_grid(): localise every seed point from the
+  // centroid of element 0, keep the tet where the point was reached
+  void build_grid() {
+    grid = choose_seed_grid(mesh);
+    const int nc = grid.nx * grid.ny * grid.nz;
+    std::vector<double> xyz(3 * size_t(nc)), tx(nc, mesh.centroid0[0]), ty(nc, mesh.centroid0[1]),
+        tz(nc, mesh.centroid0[2]);
+    std::vector<int32_t> te(nc, 0);
+    for (int i = 0; i < nc; ++i)
+      seed_point(grid, i % grid.nx, (i / grid.nx) % grid.ny, i / (grid.nx * grid.ny), xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    DeviceStats scratch{};
+    walk(tx.data(), ty.data(), tz.data(), te.data(), nc, xyz.data(), nullptr, nullptr, nullptr, &scratch, nullptr);
+    cell_tet.resize(nc);
+    for (int i = 0; i < nc; ++i)
+      cell_tet[i] = (tx[i] == xyz[3 * i] && ty[i] == xyz[3 * i + 1] && tz[i] == xyz[3 * i + 2]) ? te[i] : -1;
+    grid.cell_tet = cell_tet.data();
+  }
   void run(const double *origin, const double *dest, const int8_t *flying, const double *weights) {
+    walk(px.data(), py.data(), pz.data(), elem.data(), n, origin, dest, flying, weights, &stats,
+         grid.cell_tet ? &grid : nullptr);
+  }
+  void walk(double *qx, double *qy, double *qz, int32_t *qe, int count, const double *origin,
+            const double *dest, const int8_t *flying, const double *weights, DeviceStats *st,
+            const SeedGrid *g) {
     WalkParams P{};
     P.tets = recs.data();
     P.flux = flux.data();
-    P.px = px.data(); P.py = py.data(); P.pz = pz.data();
-    P.elem = elem.data();
+    P.px = qx; P.py = qy; P.pz = qz;
+    P.elem = qe;
     P.origin = origin; P.dest = dest; P.flying = flying; P.weights = weights;
-    P.begin = 0; P.end = n;
+    P.begin = 0; P.end = count;
     P.max_iters = int32_t(mesh.ntets + 16);
-    P.stats = &stats;
+    P.stats = st;
+    if (g) P.grid = *g;
+    DeviceStats &stats = *st;
+    const int n = count;
     for (int i = 0; i < n; ++i) {
       Counters c;
       Ray r;
@@ -80,6 +109,17 @@ void *ptb_emul_create_spec(const char *spec, int n) {
   e->pz.assign(size_t(n), e->mesh.centroid0[2]);
   e->elem.assign(size_t(n), 0);
   return e;
+}
+int ptb_emul_build_grid(void *h) {
+  auto *e = static_cast<Emul *>(h);
+  e->build_grid();
+  int valid = 0;
+  for (int32_t t : e->cell_tet) valid += t >= 0;
+  return valid;
+}
+void ptb_emul_grid_dims(void *h, int32_t *out) {
+  auto *e = static_cast<Emul *>(h);
+  out[0] = e->grid.nx; out[1] = e->grid.ny; out[2] = e->grid.nz;
 }
 void ptb_emul_sizes(void *h, int64_t *out) {
   auto *e = static_cast<Emul *>(h);

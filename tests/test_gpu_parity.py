@@ -17,14 +17,16 @@ from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
 from test_oracle_golden import golden_scenario
 
 pytestmark = pytest.mark.gpu
-VARIANTS = [0, 1, 2, 3]
+VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7]
+BIG_VARIANTS = [0, 3, 5, 6]
 
 
-def gpu_engine(variant, block=128, chunk=None):
+def gpu_engine(variant, block=128, chunk=None, seed_grid=True):
     def make(coords, t2v, n):
         e = PumiTally.from_arrays(coords, t2v, n)
         e.set_option("variant", variant)
         e.set_option("block", block)
+        e.set_option("seed_grid", 1 if seed_grid else 0)
         if chunk:
             e.set_option("chunk", chunk)
         return e
@@ -41,6 +43,47 @@ def test_reference_known_answers(variant):
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_edge_cases(variant):
     edge_case_scenario(gpu_engine(variant))
+
+
+@pytest.mark.parametrize("seed_grid", [False, True])
+def test_out_of_mesh_origin_falls_back_to_reference_walk(seed_grid):
+    """Relocation targets outside the hull: clipped along the line from the OLD position
+    (reference semantics); the seeded walk must detect this and fall back."""
+    coords, t2v = kuhn_box(4, 4, 4)
+    n = 4096
+    rng = np.random.default_rng(5)
+    init = rng.uniform(0.2, 3.8, size=(n, 3))
+    eng, orc = gpu_engine(3, seed_grid=seed_grid)(coords, t2v, n), OraclePumiTally(coords, t2v, n)
+    for e in (eng, orc):
+        e.CopyInitialPosition(init.reshape(-1).copy())
+    np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+    origin = rng.uniform(-3.0, 7.0, size=(n, 3))
+    dest = rng.uniform(0.2, 3.8, size=(n, 3))
+    w = rng.uniform(0.5, 1.0, size=n)
+    for e in (eng, orc):
+        e.MoveToNextLocation(origin.reshape(-1).copy(), dest.reshape(-1).copy(), np.ones(n, dtype=np.int8), w.copy())
+    assert_flux_close(eng.flux, orc.flux, "outside-origin")
+    np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+    np.testing.assert_allclose(eng.positions, orc.positions, atol=1e-12)
+    assert eng.stats()["lost"] == 0
+
+
+def test_seed_grid_cuts_relocation_work_not_results():
+    coords, t2v, wl = box_case((12, 12, 12), 100_000)
+    res = []
+    for sg in (False, True):
+        wl_i = SyntheticWorkload(box=(12.0, 12.0, 12.0), num_particles=wl.n)
+        e = gpu_engine(3, seed_grid=sg)(coords, t2v, wl.n)
+        e.CopyInitialPosition(wl_i.initial_positions().reshape(-1))
+        for _ in range(3):
+            o, d, f, w = wl_i.next_step()
+            e.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
+        res.append((e.flux, e.elem_ids, e.positions, e.stats()))
+    assert_flux_close(res[1][0], res[0][0], "seeded vs reference walk")
+    np.testing.assert_array_equal(res[1][1], res[0][1])
+    np.testing.assert_array_equal(res[1][2], res[0][2])
+    assert res[1][3]["segments"] == res[0][3]["segments"]
+    assert res[1][3]["relocations"] < 0.3 * res[0][3]["relocations"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -206,7 +249,7 @@ def _box_clip_length(o, d, box):
     return t1.clamp(min=0.0) * u.norm(dim=1)
 
 
-@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("variant", BIG_VARIANTS)
 def test_config_c2_full_size_properties(variant):
     """BASELINE.json configs[1] (998,250 tets, 10M particles): too big for the oracle in
     seconds, so check what must hold at any size: total tally == sum of weighted in-box

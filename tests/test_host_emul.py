@@ -1,7 +1,8 @@
 """The CUDA kernels' arithmetic (record packing, plane decode, exit-face rule,
-per-ray state machine), compiled for the host by g++ as a TEST-ONLY build,
-checked against the oracle.  This is what can be verified without a GPU; the
-`-m gpu` tests repeat the same comparisons through libpumitally.so."""
+per-ray state machine, seed-grid relocation), compiled for the host by g++ as a
+TEST-ONLY build, checked against the oracle.  This is what can be verified
+without a GPU; the `-m gpu` tests repeat the same comparisons through
+libpumitally.so."""
 import numpy as np
 import pytest
 
@@ -11,9 +12,12 @@ from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, tet_v
 from pumiumtally_b200.workload import SyntheticWorkload
 from test_oracle_golden import golden_scenario
 
+SEED = [False, True]
 
-def test_reference_known_answers_device_logic():
-    eng = golden_scenario(lambda c, t, n: HostEmulTally(c, t, n))
+
+@pytest.mark.parametrize("seed", SEED)
+def test_reference_known_answers_device_logic(seed):
+    eng = golden_scenario(lambda c, t, n: HostEmulTally(c, t, n, seed_grid=seed))
     st = eng.stats()
     assert st["lost"] == 0 and st["tracks"] == 7 and st["segments"] == 18
 
@@ -39,25 +43,39 @@ def test_adjacency_matches_oracle(mesh):
     o = OraclePumiTally(c, t, 1)
     np.testing.assert_array_equal(e.adjacency, o.adjacency)
     adj = e.adjacency
-    # symmetry: if b is a's neighbour then a is b's neighbour
-    for a in range(len(t)):
+    for a in range(len(t)):  # symmetry
         for b in adj[a]:
             if b >= 0:
                 assert a in adj[b]
 
 
-def test_config_c1_parity():
+def test_seed_grid_covers_a_box_mesh():
+    c, t = kuhn_box(6, 5, 4)
+    e = HostEmulTally(c, t, 1, seed_grid=True)
+    nx, ny, nz = e.grid_dims()
+    assert nx * ny * nz >= len(t) // 8
+    assert e.grid_valid_cells == nx * ny * nz  # every seed point of a box mesh is inside it
+
+
+@pytest.mark.parametrize("seed", SEED)
+def test_config_c1_parity(seed):
     """BASELINE.json configs[0]: ~1k-tet cube, 10k particles (plumbing config)."""
     coords, t2v, wl = box_case((6, 6, 5), 10_000)
-    eng = HostEmulTally(coords, t2v, wl.n)
+    eng = HostEmulTally(coords, t2v, wl.n, seed_grid=seed)
     orc = OraclePumiTally(coords, t2v, wl.n)
     run_workload(eng, orc, wl, steps=4, label="c1")
     st = eng.stats()
     assert st["segments"] == orc.n_segments and st["tracks"] == orc.n_tracks and st["lost"] == 0
+    if seed:  # the seeded walks are the point: far fewer tally-off crossings than the reference walk
+        plain = HostEmulTally(coords, t2v, wl.n)
+        wl2 = SyntheticWorkload(box=(6.0, 6.0, 5.0), num_particles=wl.n)
+        run_workload(plain, OraclePumiTally(coords, t2v, wl.n), wl2, steps=4, check_each_step=False)
+        assert st["relocations"] < 0.6 * plain.stats()["relocations"]
 
 
+@pytest.mark.parametrize("seed", SEED)
 @pytest.mark.parametrize("mesh", ["jitter", "delaunay"])
-def test_unstructured_parity(mesh):
+def test_unstructured_parity(mesh, seed):
     if mesh == "jitter":
         c, t = jitter_interior(*kuhn_box(6, 5, 4), amplitude=0.18)
         box = (6.0, 5.0, 4.0)
@@ -66,18 +84,43 @@ def test_unstructured_parity(mesh):
         box = (1.0, 1.0, 1.0)
     n = 4000
     wl = SyntheticWorkload(box=box, num_particles=n, mean_length=0.5 * min(box), seed=3)
-    eng, orc = HostEmulTally(c, t, n), OraclePumiTally(c, t, n)
+    eng, orc = HostEmulTally(c, t, n, seed_grid=seed), OraclePumiTally(c, t, n)
     run_workload(eng, orc, wl, steps=3, label=mesh)
     assert eng.stats()["segments"] == orc.n_segments
 
 
-def test_long_axial_tracks():
+@pytest.mark.parametrize("seed", SEED)
+def test_long_axial_tracks(seed):
     """Config c4 in miniature: forward-peaked tracks crossing many tets."""
     coords, t2v, wl = box_case((4, 4, 40), 1500, mean_length=60.0, mu_min=0.9)
-    eng, orc = HostEmulTally(coords, t2v, wl.n), OraclePumiTally(coords, t2v, wl.n)
+    eng, orc = HostEmulTally(coords, t2v, wl.n, seed_grid=seed), OraclePumiTally(coords, t2v, wl.n)
     run_workload(eng, orc, wl, steps=2, label="c4-mini")
     assert eng.stats()["segments"] / max(eng.stats()["tracks"], 1) > 15
 
 
-def test_edge_cases():
-    edge_case_scenario(lambda c, t, n: HostEmulTally(c, t, n))
+@pytest.mark.parametrize("seed", SEED)
+def test_edge_cases(seed):
+    edge_case_scenario(lambda c, t, n: HostEmulTally(c, t, n, seed_grid=seed))
+
+
+@pytest.mark.parametrize("seed", SEED)
+def test_out_of_mesh_origin_falls_back_to_reference_walk(seed):
+    """A relocation target outside the hull must be clipped along the line from the OLD
+    position (reference semantics), which the seeded walk cannot know: it has to fall back."""
+    coords, t2v = kuhn_box(4, 4, 4)
+    n = 64
+    rng = np.random.default_rng(5)
+    init = rng.uniform(0.2, 3.8, size=(n, 3))
+    eng, orc = HostEmulTally(coords, t2v, n, seed_grid=seed), OraclePumiTally(coords, t2v, n)
+    for e in (eng, orc):
+        e.CopyInitialPosition(init.reshape(-1).copy())
+    origin = rng.uniform(-3.0, 7.0, size=(n, 3))  # many outside the box, far from the old position
+    dest = rng.uniform(0.2, 3.8, size=(n, 3))
+    fly = np.ones(n, dtype=np.int8)
+    w = rng.uniform(0.5, 1.0, size=n)
+    for e in (eng, orc):
+        e.MoveToNextLocation(origin.reshape(-1).copy(), dest.reshape(-1).copy(), fly.copy(), w.copy())
+    assert_flux_close(eng.flux, orc.flux, "outside-origin")
+    np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+    np.testing.assert_allclose(eng.positions, orc.positions, atol=1e-12)
+    assert eng.stats()["lost"] == 0

@@ -310,6 +310,7 @@ def run_gpu(args, rank, local_rank, world):
                    "block": args.block, "l2": "inputs larger than L2 (570 MB of fresh particle data per step)",
                    "parallelism": f"particle stripes x{world}, full-buffer picparts, 1 ncclAllReduce(flux) per batch",
                    "segments_per_track": total_segs / max(total_tracks, 1.0), "lost": int(lost),
+                   "relocation_crossings_per_step": (st1["relocations"] - st0["relocations"]) / max(args.steps, 1),
                    "flux_sum": flux_sum},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": recorded_traffic(),
@@ -331,7 +332,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--particles", type=int, default=0, help="override particles per GPU (debug only)")
-    ap.add_argument("--variant", type=int, default=env_int("PUMITALLY_VARIANT", 3))
+    ap.add_argument("--variant", type=int, default=env_int("PUMITALLY_VARIANT", 4))
     ap.add_argument("--block", type=int, default=env_int("PUMITALLY_BLOCK", 128))
     ap.add_argument("--cpu-sample", type=int, default=500_000)
     ap.add_argument("--cpu-steps", type=int, default=3)

@@ -230,9 +230,12 @@ bool HostMesh::finalize(std::string *err) {
         for (int q = 0; q < 4; ++q) p[q] = -p[q];
       else if (side == 0.0)
         degenerate = true;
-      uint32_t nb = uint32_t(t2t[4 * e + f]);
+      // payload = this tet XOR neighbour (hull: neighbour = -1): the same 32 bits on both
+      // sides of the face, so the two records hold bit-identical planes up to the sign bit
+      // and the kernel can use the doubles as they are, payload included
+      uint32_t pay = uint32_t(e) ^ uint32_t(t2t[4 * e + f]);
       for (int q = 0; q < 4; ++q)
-        r.d[4 * f + q] = bdouble(dbits(p[q]) | uint64_t((nb >> (8 * q)) & 0xffu));
+        r.d[4 * f + q] = bdouble(dbits(p[q]) | uint64_t((pay >> (8 * q)) & 0xffu));
     }
   }
   if (degenerate) { *err = "mesh contains a degenerate (zero-volume) tet"; return false; }

@@ -20,11 +20,12 @@ namespace ptb {
 // Both tets that share a face carry the *same* plane up to an exact sign flip
 // (it is built once from the three face vertices in ascending global id), so
 // the ray parameter of a crossing is bit-identical seen from either side and
-// the walk is watertight.  The low 8 bits of each of the 16 mantissas do not
-// hold geometry: the four low bytes of face f's four doubles spell the int32
-// id of the neighbour across face f (-1 = hull).  The kernel masks them off
-// (2^-44 relative truncation, applied before the sign flip so both sides still
-// agree bit for bit).
+// the walk is watertight.  The low 8 bits of each of the 16 mantissas carry a
+// payload instead of geometry: the four low bytes of face f's four doubles
+// spell  (this tet id) XOR (id of the neighbour across face f, -1 = hull).
+// The XOR is the same number in both records, so the planes stay bit-identical
+// on both sides *with* the payload in place (a 2^-44 relative perturbation) and
+// the kernel needs no masking; it recovers the neighbour as payload XOR own id.
 struct alignas(128) TetRecord {
   double d[16];
 };

@@ -43,31 +43,32 @@ PTB_HD uint32_t dlo(double x) {
   uint64_t u; memcpy(&u, &x, 8); return (uint32_t)u;
 #endif
 }
-PTB_HD double dmask(double x) {
-#if defined(__CUDA_ARCH__)
-  return __hiloint2double(__double2hiint(x), __double2loint(x) & (int)0xffffff00);
-#else
-  uint64_t u; memcpy(&u, &x, 8); u &= ~uint64_t(0xff); memcpy(&x, &u, 8); return x;
-#endif
-}
-
 // Decoded face planes of one tet.
 struct TetPlanes {
   double nx[4], ny[4], nz[4], c[4];
   int32_t nbr[4];
 };
 
-// r = the 16 raw doubles of a TetRecord.
-PTB_HD void decode_record(const double (&r)[16], TetPlanes &t) {
+// byte 0 of four words -> one word (b0 | b1<<8 | b2<<16 | b3<<24)
+PTB_HD uint32_t pack_low_bytes(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(__byte_perm(w0, w1, 0x0040), __byte_perm(w2, w3, 0x0040), 0x5410);
+#else
+  return (w0 & 0xffu) | ((w1 & 0xffu) << 8) | ((w2 & 0xffu) << 16) | ((w3 & 0xffu) << 24);
+#endif
+}
+
+// r = the 16 raw doubles of the record of tet `self`.  The doubles are used as
+// stored (the payload bytes are part of the plane on both sides of the face).
+PTB_HD void decode_record(const double (&r)[16], int32_t self, TetPlanes &t) {
 PTB_UNROLL
   for (int f = 0; f < 4; ++f) {
-    uint32_t b0 = dlo(r[4 * f + 0]) & 0xffu, b1 = dlo(r[4 * f + 1]) & 0xffu;
-    uint32_t b2 = dlo(r[4 * f + 2]) & 0xffu, b3 = dlo(r[4 * f + 3]) & 0xffu;
-    t.nbr[f] = (int32_t)(b0 | (b1 << 8) | (b2 << 16) | (b3 << 24));
-    t.nx[f] = dmask(r[4 * f + 0]);
-    t.ny[f] = dmask(r[4 * f + 1]);
-    t.nz[f] = dmask(r[4 * f + 2]);
-    t.c[f] = dmask(r[4 * f + 3]);
+    t.nbr[f] = (int32_t)(pack_low_bytes(dlo(r[4 * f]), dlo(r[4 * f + 1]), dlo(r[4 * f + 2]), dlo(r[4 * f + 3])) ^
+                         (uint32_t)self);
+    t.nx[f] = r[4 * f + 0];
+    t.ny[f] = r[4 * f + 1];
+    t.nz[f] = r[4 * f + 2];
+    t.c[f] = r[4 * f + 3];
   }
 }
 

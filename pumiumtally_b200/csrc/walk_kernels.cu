@@ -39,7 +39,7 @@ __device__ __forceinline__ void flush_counters(const WalkParams &P, const Counte
 
 __device__ __forceinline__ void load_face_256(const double *p, double &a, double &b, double &c,
                                               double &d) {
-  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 }
 
 __global__ void __launch_bounds__(256) walk_ldg_kernel(const WalkParams P) {
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) walk_ldg_kernel(const WalkParams P) {
     for (int f = 0; f < 4; ++f)
       load_face_256(rec + 4 * f, raw[4 * f], raw[4 * f + 1], raw[4 * f + 2], raw[4 * f + 3]);
     TetPlanes t;
-    decode_record(raw, t);
+    decode_record(raw, r.e, t);
     double texit;
     int32_t next;
     exit_face(t, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, texit, next);
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(BLOCK) walk_bulk_kernel(const WalkParams P) {
                      : "=d"(raw[2 * j]), "=d"(raw[2 * j + 1])
                      : "r"(row + 16 * j));
       TetPlanes t;
-      decode_record(raw, t);
+      decode_record(raw, r.e, t);
       double texit;
       int32_t next;
       exit_face(t, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, texit, next);
@@ -172,9 +172,8 @@ __global__ void __launch_bounds__(256) walk_quad_kernel(const WalkParams P) {
   while (r.stage != kStageDone) {
     double a, b, cc, d;
     load_face_256(P.tets[r.e].d + 4 * f, a, b, cc, d);
-    const uint32_t nbu = (dlo(a) & 0xffu) | ((dlo(b) & 0xffu) << 8) | ((dlo(cc) & 0xffu) << 16) |
-                         ((dlo(d) & 0xffu) << 24);
-    const double nx = dmask(a), ny = dmask(b), nz = dmask(cc), pc = dmask(d);
+    const uint32_t nbu = pack_low_bytes(dlo(a), dlo(b), dlo(cc), dlo(d)) ^ (uint32_t)r.e;
+    const double nx = a, ny = b, nz = cc, pc = d;
     const double den = nx * r.ux + ny * r.uy + nz * r.uz;
     const double num = pc - (nx * r.ox + ny * r.oy + nz * r.oz);
     const bool out = den > 0.0;
@@ -313,10 +312,10 @@ template <int FETCH>
 __device__ __forceinline__ void load_face(const double *p, uint64_t pol, double &a, double &b,
                                           double &c, double &d) {
   if constexpr (FETCH == kFetchPolicy)
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
         : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
   else if constexpr (FETCH == kFetchPolicy128)
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::128B.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::128B.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
         : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
   else
     load_face_256(p, a, b, c, d);
@@ -453,7 +452,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
           load_face<FETCH>(rec + 4 * f, keep, raw[4 * f], raw[4 * f + 1], raw[4 * f + 2], raw[4 * f + 3]);
       }
       TetPlanes t;
-      decode_record(raw, t);
+      decode_record(raw, r.e, t);
       double texit;
       int32_t next;
       exit_face(t, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, texit, next);

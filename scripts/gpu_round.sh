@@ -33,9 +33,9 @@ PY
   cat "$OUT/bench_reference.json";;
 ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file "$OUT/launches.csv" \
-      python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e > "$OUT/ncu_launches.log" 2>&1; echo "ncu launches rc=$?" | tee -a "$OUT/summary.txt"
+      python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e ${NCU_ARGS:-} > "$OUT/ncu_launches.log" 2>&1; echo "ncu launches rc=$?" | tee -a "$OUT/summary.txt"
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:walk_ -s 2 -c 2 -o "$OUT/walk_full" -f \
-      python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e > "$OUT/ncu_full.log" 2>&1; echo "ncu full rc=$?" | tee -a "$OUT/summary.txt";;
+      python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e ${NCU_ARGS:-} > "$OUT/ncu_full.log" 2>&1; echo "ncu full rc=$?" | tee -a "$OUT/summary.txt";;
 esac
 done
 cat "$OUT/summary.txt"

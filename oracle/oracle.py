@@ -53,6 +53,7 @@ def lib():
             getattr(L, name).argtypes = [C.c_void_p]
         L.um_oracle_reset_flux.argtypes = [C.c_void_p]
         L.um_oracle_num_threads.restype = C.c_int
+        L.um_oracle_set_num_threads.argtypes = [C.c_int]
         L.um_bruteforce_tally.argtypes = [dp, ip, C.c_int, dp, dp, dp, C.c_int, dp, dp, ip]
         _lib = L
     return _lib
@@ -150,6 +151,10 @@ class OraclePumiTally:
 
 def num_threads() -> int:
     return int(lib().um_oracle_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    lib().um_oracle_set_num_threads(int(n))
 
 
 def bruteforce_tally(coords, tet2vert, a, b, w):

@@ -424,6 +424,13 @@ void um_oracle_reset_flux(um_oracle *o) {
   memset(o->flux, 0, sizeof(double) * (size_t)o->ntets);
   o->n_segments = o->n_crossings = o->n_tracks = 0;
 }
+void um_oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int um_oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

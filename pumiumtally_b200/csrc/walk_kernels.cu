@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(256) walk_quad_kernel(const WalkParams P) {
 // chunks of 32 particles are claimed from a global counter so long walks never
 // hold back the rest of the range.
 
-constexpr int kChunk = 32;
+constexpr int kChunk = 16;  // particles per staged chunk (all slice sizes stay multiples of 16 bytes)
+constexpr uint32_t kB8 = 8u * kChunk, kB24 = 24u * kChunk, kB4 = 4u * kChunk, kB1 = 1u * kChunk;
 
 struct __align__(16) ParticleStage {
   double origin[3 * kChunk];
@@ -213,7 +214,7 @@ struct __align__(16) ParticleStage {
   int32_t elem[kChunk];
   int8_t fly[kChunk];
 };
-static_assert(sizeof(ParticleStage) == 2720, "stage layout");
+static_assert(sizeof(ParticleStage) == 85 * kChunk && sizeof(ParticleStage) % 16 == 0, "stage layout");
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -225,19 +226,19 @@ __device__ __forceinline__ void stage_load(const WalkParams &P, int chunk, Parti
   const int count = (int)min((long long)kChunk, (long long)P.end - base);
   if (count == kChunk && P.bulk_ok) {
     if (lane == 0) {
-      const uint32_t bytes = 3u * 256u + 128u + (P.origin ? 768u : 0u) + (P.dest ? 768u + 256u : 0u) +
-                             (P.flying ? 32u : 0u);
+      const uint32_t bytes = 3u * kB8 + kB4 + (P.origin ? kB24 : 0u) + (P.dest ? kB24 + kB8 : 0u) +
+                             (P.flying ? kB1 : 0u);
       mbar_expect_tx(bar, bytes);
-      bulk_g2s(smem_u32(st->px), P.px + base, 256u, bar);
-      bulk_g2s(smem_u32(st->py), P.py + base, 256u, bar);
-      bulk_g2s(smem_u32(st->pz), P.pz + base, 256u, bar);
-      bulk_g2s(smem_u32(st->elem), P.elem + base, 128u, bar);
-      if (P.origin) bulk_g2s(smem_u32(st->origin), P.origin + 3 * base, 768u, bar);
+      bulk_g2s(smem_u32(st->px), P.px + base, kB8, bar);
+      bulk_g2s(smem_u32(st->py), P.py + base, kB8, bar);
+      bulk_g2s(smem_u32(st->pz), P.pz + base, kB8, bar);
+      bulk_g2s(smem_u32(st->elem), P.elem + base, kB4, bar);
+      if (P.origin) bulk_g2s(smem_u32(st->origin), P.origin + 3 * base, kB24, bar);
       if (P.dest) {
-        bulk_g2s(smem_u32(st->dest), P.dest + 3 * base, 768u, bar);
-        bulk_g2s(smem_u32(st->w), P.weights + base, 256u, bar);
+        bulk_g2s(smem_u32(st->dest), P.dest + 3 * base, kB24, bar);
+        bulk_g2s(smem_u32(st->w), P.weights + base, kB8, bar);
       }
-      if (P.flying) bulk_g2s(smem_u32(st->fly), P.flying + base, 32u, bar);
+      if (P.flying) bulk_g2s(smem_u32(st->fly), P.flying + base, kB1, bar);
     }
   } else {
     // ragged last chunk, or caller pointers that are not 16-byte aligned
@@ -288,7 +289,10 @@ __device__ __forceinline__ void begin_from_stage(const WalkParams &P, const Part
 //      (staging copies, state stores) is evict_first -- keeps the tet table L2-resident
 //   2  as 1, plus the L2::128B prefetch size (first sector miss pulls the whole line)
 //   3  one cp.async.bulk of 128 B per lane into a shared-memory row (policies as 1)
-enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3 };
+//   4  cooperative: in four rounds the four lanes of a quad load the four 32-byte sectors of ONE
+//      lane's record with a single instruction (one 4-sector request per line instead of four
+//      1-sector requests), records are transposed through per-warp shared-memory rows
+enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3, kFetchCoop = 4 };
 
 __device__ __forceinline__ uint64_t l2_policy_keep() {
   uint64_t p;
@@ -328,36 +332,40 @@ __device__ __forceinline__ void stage_load_hint(const WalkParams &P, int chunk, 
   const int count = (int)min((long long)kChunk, (long long)P.end - base);
   if (count == kChunk && P.bulk_ok) {
     if (lane == 0) {
-      const uint32_t bytes = 3u * 256u + 128u + (P.origin ? 768u : 0u) + (P.dest ? 768u + 256u : 0u) +
-                             (P.flying ? 32u : 0u);
+      const uint32_t bytes = 3u * kB8 + kB4 + (P.origin ? kB24 : 0u) + (P.dest ? kB24 + kB8 : 0u) +
+                             (P.flying ? kB1 : 0u);
       mbar_expect_tx(bar, bytes);
-      bulk_g2s_hint(smem_u32(st->px), P.px + base, 256u, bar, pol);
-      bulk_g2s_hint(smem_u32(st->py), P.py + base, 256u, bar, pol);
-      bulk_g2s_hint(smem_u32(st->pz), P.pz + base, 256u, bar, pol);
-      bulk_g2s_hint(smem_u32(st->elem), P.elem + base, 128u, bar, pol);
-      if (P.origin) bulk_g2s_hint(smem_u32(st->origin), P.origin + 3 * base, 768u, bar, pol);
+      bulk_g2s_hint(smem_u32(st->px), P.px + base, kB8, bar, pol);
+      bulk_g2s_hint(smem_u32(st->py), P.py + base, kB8, bar, pol);
+      bulk_g2s_hint(smem_u32(st->pz), P.pz + base, kB8, bar, pol);
+      bulk_g2s_hint(smem_u32(st->elem), P.elem + base, kB4, bar, pol);
+      if (P.origin) bulk_g2s_hint(smem_u32(st->origin), P.origin + 3 * base, kB24, bar, pol);
       if (P.dest) {
-        bulk_g2s_hint(smem_u32(st->dest), P.dest + 3 * base, 768u, bar, pol);
-        bulk_g2s_hint(smem_u32(st->w), P.weights + base, 256u, bar, pol);
+        bulk_g2s_hint(smem_u32(st->dest), P.dest + 3 * base, kB24, bar, pol);
+        bulk_g2s_hint(smem_u32(st->w), P.weights + base, kB8, bar, pol);
       }
-      if (P.flying) bulk_g2s_hint(smem_u32(st->fly), P.flying + base, 32u, bar, pol);
+      if (P.flying) bulk_g2s_hint(smem_u32(st->fly), P.flying + base, kB1, bar, pol);
     }
   } else {
     stage_load(P, chunk, st, bar, lane);  // ragged / unaligned: plain path
   }
 }
 
-template <int BLOCK, int FETCH, int MINB>
+// REFILL_T: idle lanes are topped up only when at least this many have finished -- the
+// refill code then runs with REFILL_T+ active lanes instead of the ~3 that finish per
+// iteration, at the price of a few idle lanes in the walk step.
+template <int BLOCK, int FETCH, int MINB, int REFILL_T>
 __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkParams P) {
   constexpr int WARPS = BLOCK / 32;
   constexpr bool kBulkTets = FETCH == kFetchBulk;
+  constexpr bool kRows = FETCH == kFetchBulk || FETCH == kFetchCoop;
   __shared__ ParticleStage stages[WARPS][2];
   __shared__ __align__(8) unsigned long long bars[WARPS][3];
-  __shared__ __align__(128) unsigned char rows[kBulkTets ? WARPS : 1][kBulkTets ? 32 * kRowBytes : 16];
+  __shared__ __align__(128) unsigned char rows[kRows ? WARPS : 1][kRows ? 32 * kRowBytes : 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t bar0 = smem_u32(&bars[warp][0]);
   const uint32_t bar_row = bar0 + 16;
-  const uint32_t row = smem_u32(&rows[kBulkTets ? warp : 0][kBulkTets ? lane * kRowBytes : 0]);
+  const uint32_t row = smem_u32(&rows[kRows ? warp : 0][kRows ? lane * kRowBytes : 0]);
   if (lane == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
@@ -400,7 +408,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
   int my_i = 0;
   for (;;) {
     unsigned idle = __ballot_sync(0xffffffffu, r.stage == kStageDone);
-    while (idle != 0u && cur_count > 0) {
+    while (cur_count > 0 && (int)__popc(idle) >= REFILL_T) {
       const int slot = cursor + __popc(idle & ((1u << lane) - 1u));
       if (r.stage == kStageDone && slot < cur_count) {
         my_i = P.begin + chunk_cur * kChunk + slot;
@@ -438,8 +446,31 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
       mbar_wait(bar_row, (parity >> 2) & 1u);
       parity ^= 4u;
     }
+    if constexpr (FETCH == kFetchCoop) {
+      const unsigned act = ~idle;
+      const uint32_t rows0 = row - (uint32_t)lane * kRowBytes;
+      const int sec = lane & 3;
+      double q[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int src = 8 * j + (lane >> 2);
+        const int es = __shfl_sync(0xffffffffu, r.e, src);
+        if ((act >> src) & 1u)
+          load_face<kFetchPolicy>(P.tets[es].d + 4 * sec, keep, q[j][0], q[j][1], q[j][2], q[j][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int src = 8 * j + (lane >> 2);
+        if ((act >> src) & 1u) {
+          const uint32_t dst = rows0 + (uint32_t)src * kRowBytes + 32u * sec;
+          asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(dst), "d"(q[j][0]), "d"(q[j][1]) : "memory");
+          asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(dst + 16u), "d"(q[j][2]), "d"(q[j][3]) : "memory");
+        }
+      }
+      __syncwarp();
+    }
     if (r.stage != kStageDone) {
-      if constexpr (kBulkTets) {
+      if constexpr (kRows) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];"
@@ -462,7 +493,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
   flush_counters(P, c);
 }
 
-template <int BLOCK, int FETCH, int MINB>
+template <int BLOCK, int FETCH, int MINB, int REFILL_T = 1>
 cudaError_t launch_persist(const WalkParams &p, long long n, cudaStream_t stream) {
   static int sms = 0, occ = 0;
   if (!sms) {
@@ -470,9 +501,9 @@ cudaError_t launch_persist(const WalkParams &p, long long n, cudaStream_t stream
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // leave as much of the unified L1/smem array to shared memory as the kernel can use
-    cudaFuncSetAttribute(walk_persist_kernel<BLOCK, FETCH, MINB>,
+    cudaFuncSetAttribute(walk_persist_kernel<BLOCK, FETCH, MINB, REFILL_T>,
                          cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_persist_kernel<BLOCK, FETCH, MINB>, BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_persist_kernel<BLOCK, FETCH, MINB, REFILL_T>, BLOCK, 0);
     if (occ < 1) occ = 1;
   }
   const long long nchunks = (n + kChunk - 1) / kChunk;
@@ -480,7 +511,7 @@ cudaError_t launch_persist(const WalkParams &p, long long n, cudaStream_t stream
   const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * occ);
   cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
-  walk_persist_kernel<BLOCK, FETCH, MINB><<<grid, BLOCK, 0, stream>>>(p);
+  walk_persist_kernel<BLOCK, FETCH, MINB, REFILL_T><<<grid, BLOCK, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -563,6 +594,20 @@ cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_
       return launch_persist<128, kFetchBulk, 5>(p, n, stream);
     case kVariantPersistPolicy128Occ8:
       return launch_persist<128, kFetchPolicy128, 8>(p, n, stream);
+    case kVariantPersistCoop:
+      return launch_persist<128, kFetchCoop, 7>(p, n, stream);
+    case kVariantPersistCoopRefill8:
+      return launch_persist<128, kFetchCoop, 7, 8>(p, n, stream);
+    case kVariantPersistBulkOcc7:
+      return launch_persist<128, kFetchBulk, 7>(p, n, stream);
+    case kVariantPersistCoopOcc6:
+      return launch_persist<128, kFetchCoop, 6>(p, n, stream);
+    case kVariantPersistRefill8:
+      return launch_persist<128, kFetchPolicy, 7, 8>(p, n, stream);
+    case kVariantPersistRefill12:
+      return launch_persist<128, kFetchPolicy, 7, 12>(p, n, stream);
+    case kVariantPersistRefill16:
+      return launch_persist<128, kFetchPolicy, 7, 16>(p, n, stream);
     default:
       return cudaErrorInvalidValue;
   }

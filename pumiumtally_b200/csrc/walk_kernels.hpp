@@ -17,7 +17,14 @@ enum WalkVariant : int {
   kVariantPersistPolicy128 = 5,      // 4 + L2::128B prefetch size on tet loads
   kVariantPersistBulk = 6,           // 4 with tet records fetched by cp.async.bulk into smem rows
   kVariantPersistPolicy128Occ8 = 7,  // 5 compiled for 8 resident blocks (64 registers)
-  kNumVariants = 8
+  kVariantPersistRefill8 = 8,        // 4, refilling only when >= 8 lanes are idle
+  kVariantPersistRefill12 = 9,
+  kVariantPersistRefill16 = 10,
+  kVariantPersistCoop = 11,          // 4 with cooperative coalesced tet fetch (quad loads + smem transpose)
+  kVariantPersistCoopRefill8 = 12,
+  kVariantPersistBulkOcc7 = 13,      // 6 compiled for 7 resident blocks
+  kVariantPersistCoopOcc6 = 14,      // 11 compiled for 6 resident blocks (no spills)
+  kNumVariants = 15
 };
 
 cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_t stream);

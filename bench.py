@@ -315,6 +315,9 @@ def run_gpu(args, rank, local_rank, world):
                "sample": f"first {ns} particles of the first {cpu_steps} batches ({orc.n_segments} segments, "
                          f"{t_cpu:.1f} s) on the full mesh; reference-algorithm restatement, OpenMP"}
 
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = measured_peak()

@@ -20,6 +20,7 @@ LIB = os.path.join(LIBDIR, "libpumitally.so")
 
 SOURCES = [
     "walk_kernels.cu",
+    "bin_kernels.cu",
     "engine.cu",
     "tet_mesh.cpp",
     "osh_reader.cpp",

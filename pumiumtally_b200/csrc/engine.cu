@@ -71,6 +71,9 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
   dev_alloc(&d_flying_, N, "flying staging");
   dev_alloc(&d_stats_, 1, "stats");
   dev_alloc(&d_tickets_, kTicketRing, "tickets");
+  dev_alloc(&d_pcell_, N, "particle cells");
+  dev_alloc(&d_order_, N, "processing order");
+  dev_alloc(&d_work_count_, kTicketRing, "work counts");
 
   cuda_or_throw(cudaMemcpy(d_tets_, mesh_.records.data(), E * sizeof(TetRecord), cudaMemcpyHostToDevice), "upload tets");
   cuda_or_throw(cudaMemcpy(d_volume_, mesh_.volume.data(), E * sizeof(double), cudaMemcpyHostToDevice), "upload volume");
@@ -100,6 +103,8 @@ Engine::~Engine() {
   cudaFree(d_stats_);
   cudaFree(d_tickets_);
   cudaFree(d_grid_);
+  cudaFree(d_pcell_); cudaFree(d_order_); cudaFree(d_cell_count_); cudaFree(d_cell_sums_);
+  cudaFree(d_work_count_);
   if (compute_) cudaStreamDestroy(compute_);
   if (copy_) cudaStreamDestroy(copy_);
 }
@@ -138,6 +143,8 @@ void Engine::build_seed_grid() {
   cuda_or_throw(cudaMemset(d_stats_, 0, sizeof(DeviceStats)), "memset");
   cudaFree(xyz); cudaFree(tx); cudaFree(ty); cudaFree(tz); cudaFree(te);
   grid_.cell_tet = d_grid_;
+  dev_alloc(&d_cell_count_, size_t(ncell), "cell histogram");
+  dev_alloc(&d_cell_sums_, size_t(ncell) / 1024 + 2, "cell block sums");
 }
 
 void Engine::collect_timers(bool wait) {
@@ -189,6 +196,16 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
       timers_free_.pop_back();
     }
     PTB_CUDA_OK(cudaEventRecord(t.a, stream));
+  }
+  if (variant_ == kVariantPersistGather || variant_ == kVariantPersistGatherL1) {
+    // counting sort of the range's flying particles by seed-grid cell of their origin
+    unsigned int *wc = d_work_count_ + (ticket_next_ % kTicketRing);
+    const double *key = d_origin ? d_origin : d_dest;
+    PTB_CUDA_OK(launch_bin_particles(grid_, key, d_flying, begin, end, d_pcell_, d_cell_count_,
+                                     d_cell_sums_, d_order_ + begin, wc, stream));
+    p.order = d_order_ + begin;
+    p.work_count = wc;
+    p.flying = nullptr;  // order[] holds flying particles only
   }
   PTB_CUDA_OK(launch_walk(p, variant_, block_, stream));
   if (timed) {
@@ -412,6 +429,11 @@ int Engine::comm_init(int rank, int nranks, const uint8_t id[128]) {
   if (nccl_comm_init_rank(&nccl_comm_, nranks, id, rank)) return 1;
   rank_ = rank;
   nranks_ = nranks;
+  // NCCL sets up its NVLink connections lazily inside the first collective: pay that here,
+  // on the scratch array, not in the first batch-end exchange
+  PTB_CUDA_OK(cudaMemsetAsync(d_scratch_, 0, size_t(mesh_.ntets) * sizeof(double), compute_));
+  if (nccl_allreduce_sum_f64(nccl_comm_, d_scratch_, size_t(mesh_.ntets), compute_)) return 1;
+  PTB_CUDA_OK(cudaStreamSynchronize(compute_));
   return 0;
 }
 

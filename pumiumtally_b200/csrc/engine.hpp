@@ -92,6 +92,9 @@ class Engine {
   unsigned ticket_next_ = 0;
   SeedGrid grid_{};              // relocation seed grid (grid_.cell_tet lives in d_grid_)
   int32_t *d_grid_ = nullptr;
+  // spatial binning of the flying particles (gather-mode kernels)
+  int32_t *d_pcell_ = nullptr, *d_order_ = nullptr;
+  unsigned int *d_cell_count_ = nullptr, *d_cell_sums_ = nullptr, *d_work_count_ = nullptr;
 
   cudaStream_t compute_ = nullptr, copy_ = nullptr;
   struct TimerPair { cudaEvent_t a, b; };

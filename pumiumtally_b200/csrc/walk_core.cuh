@@ -152,6 +152,8 @@ struct WalkParams {
   int32_t max_iters;       // crossing limit per walk ("May need more loops in search")
   int32_t bulk_ok;         // all particle arrays 16-byte aligned: cp.async.bulk staging allowed
   unsigned int *work_counter;  // chunk ticket of the persistent kernel (zeroed per launch)
+  const int32_t *order;        // gather mode: ids of the flying particles in processing order
+  const unsigned int *work_count;  // gather mode: number of entries in order[] (device scalar)
   DeviceStats *stats;
   SeedGrid grid;
 };

@@ -213,8 +213,9 @@ struct __align__(16) ParticleStage {
   double px[kChunk], py[kChunk], pz[kChunk], w[kChunk];
   int32_t elem[kChunk];
   int8_t fly[kChunk];
+  int32_t id[kChunk];  // gather mode: particle id of each slot
 };
-static_assert(sizeof(ParticleStage) == 85 * kChunk && sizeof(ParticleStage) % 16 == 0, "stage layout");
+static_assert(sizeof(ParticleStage) == 89 * kChunk && sizeof(ParticleStage) % 16 == 0, "stage layout");
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -292,7 +293,9 @@ __device__ __forceinline__ void begin_from_stage(const WalkParams &P, const Part
 //   4  cooperative: in four rounds the four lanes of a quad load the four 32-byte sectors of ONE
 //      lane's record with a single instruction (one 4-sector request per line instead of four
 //      1-sector requests), records are transposed through per-warp shared-memory rows
-enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3, kFetchCoop = 4 };
+//   5  as 1 but the tet loads allocate in L1 (worth it once particles are processed in
+//      spatial order and neighbouring lanes/warps revisit the same records)
+enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3, kFetchCoop = 4, kFetchPolicyL1 = 5 };
 
 __device__ __forceinline__ uint64_t l2_policy_keep() {
   uint64_t p;
@@ -317,6 +320,9 @@ __device__ __forceinline__ void load_face(const double *p, uint64_t pol, double 
                                           double &c, double &d) {
   if constexpr (FETCH == kFetchPolicy)
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+        : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
+  else if constexpr (FETCH == kFetchPolicyL1)
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
         : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
   else if constexpr (FETCH == kFetchPolicy128)
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::128B.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
@@ -351,10 +357,48 @@ __device__ __forceinline__ void stage_load_hint(const WalkParams &P, int chunk, 
   }
 }
 
+// ---- gather mode: the chunk's particles are not contiguous (order[] comes from the binning
+// pass); every lane pulls its particle's fields with 8/4-byte cp.async copies that complete on
+// the stage's mbarrier (cp.async.mbarrier.arrive.noinc: one arrival per lane, barrier count 32)
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void stage_gather(const WalkParams &P, int chunk, int total,
+                                             ParticleStage *st, uint32_t bar, int lane) {
+  const int base = chunk * kChunk;
+  const int count = min(kChunk, total - base);
+  if (lane < count) {
+    const int i = __ldg(P.order + base + lane);
+    st->id[lane] = i;
+    cp_async_8(smem_u32(&st->px[lane]), P.px + i);
+    cp_async_8(smem_u32(&st->py[lane]), P.py + i);
+    cp_async_8(smem_u32(&st->pz[lane]), P.pz + i);
+    cp_async_4(smem_u32(&st->elem[lane]), P.elem + i);
+    if (P.origin) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cp_async_8(smem_u32(&st->origin[3 * lane + k]), P.origin + 3 * (size_t)i + k);
+    }
+    if (P.dest) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cp_async_8(smem_u32(&st->dest[3 * lane + k]), P.dest + 3 * (size_t)i + k);
+      cp_async_8(smem_u32(&st->w[lane]), P.weights + i);
+    }
+  }
+  cp_async_arrive_noinc(bar);
+}
+
+constexpr int kClaimRun = 4;  // gather mode: a warp takes this many consecutive chunks per ticket
+
 // REFILL_T: idle lanes are topped up only when at least this many have finished -- the
 // refill code then runs with REFILL_T+ active lanes instead of the ~3 that finish per
 // iteration, at the price of a few idle lanes in the walk step.
-template <int BLOCK, int FETCH, int MINB, int REFILL_T>
+template <int BLOCK, int FETCH, int MINB, int REFILL_T, bool GATHER>
 __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkParams P) {
   constexpr int WARPS = BLOCK / 32;
   constexpr bool kBulkTets = FETCH == kFetchBulk;
@@ -367,8 +411,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
   const uint32_t bar_row = bar0 + 16;
   const uint32_t row = smem_u32(&rows[kRows ? warp : 0][kRows ? lane * kRowBytes : 0]);
   if (lane == 0) {
-    mbar_init(bar0, 1);
-    mbar_init(bar0 + 8, 1);
+    mbar_init(bar0, GATHER ? 32 : 1);
+    mbar_init(bar0 + 8, GATHER ? 32 : 1);
     mbar_init(bar_row, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -376,17 +420,29 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
   __syncwarp();
   const uint64_t keep = FETCH != kFetchPlain ? l2_policy_keep() : 0;
   const uint64_t strm = FETCH != kFetchPlain ? l2_policy_stream() : 0;
+  const int total = GATHER ? (int)__ldg(P.work_count) : P.end - P.begin;
+  const int nchunks = (total + kChunk - 1) / kChunk;
   auto load_stage = [&](int chunk, ParticleStage *st, uint32_t bar) {
-    if constexpr (FETCH == kFetchPlain) stage_load(P, chunk, st, bar, lane);
+    if constexpr (GATHER) stage_gather(P, chunk, total, st, bar, lane);
+    else if constexpr (FETCH == kFetchPlain) stage_load(P, chunk, st, bar, lane);
     else stage_load_hint(P, chunk, st, bar, lane, strm);
   };
-
-  const int total = P.end - P.begin;
-  const int nchunks = (total + kChunk - 1) / kChunk;
+  int run_next = 0, run_end = 0;  // gather mode: remaining chunks of the current ticket
   auto claim = [&]() -> int {
     int c = 0;
-    if (lane == 0) c = (int)atomicAdd(P.work_counter, 1u);
-    c = __shfl_sync(0xffffffffu, c, 0);
+    if constexpr (GATHER) {
+      if (run_next < run_end) {
+        c = run_next++;
+      } else {
+        if (lane == 0) c = (int)atomicAdd(P.work_counter, (unsigned)kClaimRun);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        run_next = c + 1;
+        run_end = c + kClaimRun;
+      }
+    } else {
+      if (lane == 0) c = (int)atomicAdd(P.work_counter, 1u);
+      c = __shfl_sync(0xffffffffu, c, 0);
+    }
     return c < nchunks ? c : -1;
   };
 
@@ -411,7 +467,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
     while (cur_count > 0 && (int)__popc(idle) >= REFILL_T) {
       const int slot = cursor + __popc(idle & ((1u << lane) - 1u));
       if (r.stage == kStageDone && slot < cur_count) {
-        my_i = P.begin + chunk_cur * kChunk + slot;
+        my_i = GATHER ? stages[warp][cur].id[slot] : P.begin + chunk_cur * kChunk + slot;
         begin_from_stage(P, &stages[warp][cur], slot, r, c);
       }
       __syncwarp();
@@ -493,7 +549,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
   flush_counters(P, c);
 }
 
-template <int BLOCK, int FETCH, int MINB, int REFILL_T = 1>
+template <int BLOCK, int FETCH, int MINB, int REFILL_T = 1, bool GATHER = false, int CARVE = -1>
 cudaError_t launch_persist(const WalkParams &p, long long n, cudaStream_t stream) {
   static int sms = 0, occ = 0;
   if (!sms) {
@@ -501,9 +557,10 @@ cudaError_t launch_persist(const WalkParams &p, long long n, cudaStream_t stream
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // leave as much of the unified L1/smem array to shared memory as the kernel can use
-    cudaFuncSetAttribute(walk_persist_kernel<BLOCK, FETCH, MINB, REFILL_T>,
-                         cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_persist_kernel<BLOCK, FETCH, MINB, REFILL_T>, BLOCK, 0);
+    cudaFuncSetAttribute(walk_persist_kernel<BLOCK, FETCH, MINB, REFILL_T, GATHER>,
+                         cudaFuncAttributePreferredSharedMemoryCarveout,
+                         CARVE < 0 ? (int)cudaSharedmemCarveoutMaxShared : CARVE);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_persist_kernel<BLOCK, FETCH, MINB, REFILL_T, GATHER>, BLOCK, 0);
     if (occ < 1) occ = 1;
   }
   const long long nchunks = (n + kChunk - 1) / kChunk;
@@ -511,7 +568,7 @@ cudaError_t launch_persist(const WalkParams &p, long long n, cudaStream_t stream
   const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * occ);
   cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
-  walk_persist_kernel<BLOCK, FETCH, MINB, REFILL_T><<<grid, BLOCK, 0, stream>>>(p);
+  walk_persist_kernel<BLOCK, FETCH, MINB, REFILL_T, GATHER><<<grid, BLOCK, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -594,6 +651,10 @@ cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_
       return launch_persist<128, kFetchBulk, 5>(p, n, stream);
     case kVariantPersistPolicy128Occ8:
       return launch_persist<128, kFetchPolicy128, 8>(p, n, stream);
+    case kVariantPersistGather:
+      return launch_persist<128, kFetchPolicy, 7, 1, true>(p, n, stream);
+    case kVariantPersistGatherL1:
+      return launch_persist<128, kFetchPolicyL1, 7, 1, true, 40>(p, n, stream);
     case kVariantPersistCoop:
       return launch_persist<128, kFetchCoop, 7>(p, n, stream);
     case kVariantPersistCoopRefill8:

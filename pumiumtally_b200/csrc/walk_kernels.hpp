@@ -24,10 +24,16 @@ enum WalkVariant : int {
   kVariantPersistCoopRefill8 = 12,
   kVariantPersistBulkOcc7 = 13,      // 6 compiled for 7 resident blocks
   kVariantPersistCoopOcc6 = 14,      // 11 compiled for 6 resident blocks (no spills)
-  kNumVariants = 15
+  kVariantPersistGather = 15,        // 4 on spatially binned particles (order[] from launch_bin_particles)
+  kVariantPersistGatherL1 = 16,      // 15 with L1-allocating tet loads and a larger L1 carve-out
+  kNumVariants = 17
 };
 
 cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_t stream);
+cudaError_t launch_bin_particles(const SeedGrid &g, const double *origin, const int8_t *flying,
+                                 int32_t begin, int32_t end, int32_t *pcell, unsigned int *count,
+                                 unsigned int *sums, int32_t *order, unsigned int *work_count,
+                                 cudaStream_t stream);
 cudaError_t launch_seed_points(const SeedGrid &g, double *xyz, cudaStream_t stream);
 cudaError_t launch_seed_finalize(const double *xyz, const double *px, const double *py,
                                  const double *pz, const int32_t *elem, int32_t *cell_tet,

@@ -17,8 +17,8 @@ from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
 from test_oracle_golden import golden_scenario
 
 pytestmark = pytest.mark.gpu
-VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14]
-BIG_VARIANTS = [0, 4, 6, 8, 11]
+VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14, 15, 16]
+BIG_VARIANTS = [0, 4, 6, 15, 16]
 
 
 def gpu_engine(variant, block=128, chunk=None, seed_grid=True):

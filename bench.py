@@ -208,8 +208,16 @@ def run_gpu(args, rank, local_rank, world):
     wl = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], mu_min=cfg["mu_min"],
                            backend="torch", device=dev, id_offset=rank * n)
     init = wl.initial_positions().contiguous()
-    batches = [tuple(x.contiguous() for x in wl.next_step()) for _ in range(nsteps)]
+    bytes_per_step = n * 57
+    pregen = nsteps * bytes_per_step <= args.pregen_gb * (1 << 30)
+    # default (c2): all batches are generated up front and the K timed steps run back to back.
+    # Configs whose batches do not fit (100M particles) generate each batch just before its step,
+    # outside the timed region, and the per-step device times are summed.
+    batches = [tuple(x.contiguous() for x in wl.next_step()) for _ in range(nsteps)] if pregen else None
     stream = torch.cuda.current_stream().cuda_stream
+
+    def batch(k):
+        return batches[k] if pregen else tuple(x.contiguous() for x in wl.next_step())
 
     def barrier():
         if dist is not None:
@@ -224,7 +232,7 @@ def run_gpu(args, rank, local_rank, world):
         eng.comm_init(rank, world, broadcast_unique_id(dist, PumiTally.nccl_unique_id, device=dev))
     eng.copy_initial_position_device(init.data_ptr(), stream)
     for k in range(args.warmup):
-        o, d, f, w = batches[k]
+        o, d, f, w = batch(k)
         eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
     barrier()
     st0 = eng.stats()
@@ -233,17 +241,33 @@ def run_gpu(args, rank, local_rank, world):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record()
-    for k in range(args.warmup, nsteps):
-        o, d, f, w = batches[k]
-        eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
-    if world > 1:
-        torch.cuda.current_stream().synchronize()
-        eng.allreduce_tally()  # batch-end exchange of the ghost tallies over NVLink
-    ev1.record()
-    barrier()
+    if pregen:
+        ev0.record()
+        for k in range(args.warmup, nsteps):
+            o, d, f, w = batches[k]
+            eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
+        if world > 1:
+            torch.cuda.current_stream().synchronize()
+            eng.allreduce_tally()  # batch-end exchange of the ghost tallies over NVLink
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+    else:
+        ms = 0.0
+        for k in range(args.warmup, nsteps):
+            o, d, f, w = batch(k)
+            barrier()
+            ev0.record()
+            eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
+            if world > 1 and k == nsteps - 1:
+                torch.cuda.current_stream().synchronize()
+                eng.allreduce_tally()
+            ev1.record()
+            torch.cuda.synchronize()
+            ms += ev0.elapsed_time(ev1)
+            del o, d, f, w
+        barrier()
     clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
     st1 = eng.stats()
     segs = st1["segments"] - st0["segments"]
     tracks = st1["tracks"] - st0["tracks"]
@@ -263,25 +287,42 @@ def run_gpu(args, rank, local_rank, world):
     # ---------------- end-to-end arm through the host-pointer C ABI: `e2e` ------
     e2e = None
     if not args.no_e2e:
-        host = []
-        for (o, d, f, w) in batches:
-            host.append(tuple(torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x) for x in (o, d, f, w)))
+        if not pregen:  # replay the same counter-based stream from the start
+            wl = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], mu_min=cfg["mu_min"],
+                                   backend="torch", device=dev, id_offset=rank * n)
+            init = wl.initial_positions().contiguous()
+
+        def pinned(t):
+            return tuple(torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x) for x in t)
+
+        host = [pinned(b) for b in batches] if pregen else None
+        one = None if pregen else pinned(batch(0))
         init_h = init.cpu()
         eng2 = new_engine()
         eng2.CopyInitialPosition(init_h.numpy().reshape(-1))
+
+        def host_batch(k):
+            if pregen:
+                return host[k]
+            if k > 0:
+                for dst, src in zip(one, batch(k)):
+                    dst.copy_(src)
+                torch.cuda.synchronize()
+            return one
+
         for k in range(args.warmup):
-            o, d, f, w = host[k]
+            o, d, f, w = host_batch(k)
             eng2.move_host_ptr(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr())
             eng2.stats()
         barrier()
         s0 = eng2.stats()["segments"]
-        t0 = time.perf_counter()
+        dt = 0.0
         for k in range(args.warmup, nsteps):
-            o, d, f, w = host[k]
+            o, d, f, w = host_batch(k)
+            t0 = time.perf_counter()
             eng2.move_host_ptr(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr())
-            s1 = eng2.stats()["segments"]  # device->host read of the step's result
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+            s1 = eng2.stats()["segments"]  # device->host read of the step's result (synchronises)
+            dt += time.perf_counter() - t0
         e_t = torch.tensor([dt], dtype=torch.float64, device=dev)
         e_s = torch.tensor([float(s1 - s0)], dtype=torch.float64, device=dev)
         if dist is not None:
@@ -291,7 +332,7 @@ def run_gpu(args, rank, local_rank, world):
                "h2d_bytes_per_step": n * (24 + 24 + 8 + 1), "d2h_bytes_per_step": 56,
                "ms_per_step": 1e3 * float(e_t[0]) / args.steps,
                "note": "MoveToNextLocation on pinned host buffers + per-step stats read-back"}
-        del eng2, host
+        del eng2, host, one
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------
     cpu = None
@@ -302,12 +343,13 @@ def run_gpu(args, rank, local_rank, world):
         ns = min(args.cpu_sample, n)
         coords, t2v = kuhn_box(*cells)
         orc = OraclePumiTally(coords, t2v, ns, per_particle=True)
-        orc.CopyInitialPosition(init[:ns].cpu().numpy().reshape(-1))
+        # counter-based generator: the numpy stream of ids [0, ns) is the GPU batch's first ns particles
+        wl_cpu = SyntheticWorkload(box=box, num_particles=ns, mean_length=cfg["mean_length"], mu_min=cfg["mu_min"])
+        orc.CopyInitialPosition(wl_cpu.initial_positions().reshape(-1))
         cpu_steps = min(args.cpu_steps, nsteps)
         s0, t_cpu = 0, 0.0
         for k in range(cpu_steps):
-            o, d, f, w = (x[:ns].cpu().numpy() for x in batches[k])
-            f = f.copy()
+            o, d, f, w = wl_cpu.next_step()
             t0 = time.perf_counter()
             orc.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
             t_cpu += time.perf_counter() - t0
@@ -328,7 +370,10 @@ def run_gpu(args, rank, local_rank, world):
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_description(args.config, cfg, n), "variant": args.variant,
-                   "block": args.block, "l2": "inputs larger than L2 (570 MB of fresh particle data per step)",
+                   "block": args.block,
+                   "l2": f"inputs larger than L2 ({bytes_per_step / 1e6:.0f} MB of fresh particle data per step)",
+                   "timing": "K steps back to back between two CUDA events" if pregen else
+                             "per-step CUDA-event times summed (batches generated between steps, untimed)",
                    "parallelism": f"particle stripes x{world}, full-buffer picparts, 1 ncclAllReduce(flux) per batch",
                    "segments_per_track": total_segs / max(total_tracks, 1.0), "lost": int(lost),
                    "relocation_crossings_per_step": (st1["relocations"] - st0["relocations"]) / max(args.steps, 1),
@@ -358,6 +403,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=500_000)
     ap.add_argument("--ref-sample", type=int, default=2_000_000, help="particles per step of the --impl reference arm")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--pregen-gb", type=float, default=24.0, help="pre-generate all batches if they fit in this many GiB")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -124,6 +124,10 @@ int pumitally_nccl_unique_id(uint8_t out_id[128]);
 int pumitally_comm_init(pumitally_engine *e, int32_t rank, int32_t nranks, const uint8_t id[128]);
 int pumitally_allreduce_tally(pumitally_engine *e);
 
+/* test hook: processing order produced by the last binning pass (ids of flying particles
+ * grouped by seed-grid cell); returns the number of entries, copies at most n of them */
+int64_t pumitally_debug_order(pumitally_engine *e, int32_t *out, int64_t n);
+
 const char *pumitally_version(void);
 
 #ifdef __cplusplus

@@ -187,6 +187,11 @@ int pumitally_allreduce_tally(pumitally_engine *e) {
   return guarded(e, [&](ptb::Engine &g) { return g.allreduce_tally(); });
 }
 
+int64_t pumitally_debug_order(pumitally_engine *e, int32_t *out, int64_t n) {
+  if (!e || !e->impl) return -1;
+  return e->impl->debug_order(out, n);
+}
+
 const char *pumitally_version(void) { return "pumitally-b200 0.1 (sm_100a)"; }
 
 }  // extern "C"

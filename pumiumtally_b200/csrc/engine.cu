@@ -59,10 +59,7 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
   dev_alloc(&d_flux_, E, "flux");
   dev_alloc(&d_volume_, E, "volume");
   dev_alloc(&d_scratch_, E, "scratch");
-  dev_alloc(&d_px_, N, "px");
-  dev_alloc(&d_py_, N, "py");
-  dev_alloc(&d_pz_, N, "pz");
-  dev_alloc(&d_elem_, N, "elem");
+  dev_alloc(&d_state_, N, "particle state");
   // staging buffers (PumiTallyImpl.cpp:36-41; origin and dest get their own so one
   // upload per array suffices instead of re-using one position buffer twice)
   dev_alloc(&d_origin_, 3 * N, "origin staging");
@@ -80,7 +77,7 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
   cuda_or_throw(cudaMemset(d_flux_, 0, E * sizeof(double)), "memset");
   cuda_or_throw(cudaMemset(d_stats_, 0, sizeof(DeviceStats)), "memset");
   // InitializeParticlesInElement0 (PumiTallyImpl.cpp:492-528)
-  cuda_or_throw(launch_init_particles(d_px_, d_py_, d_pz_, d_elem_, n_, mesh_.centroid0[0],
+  cuda_or_throw(launch_init_particles(d_state_, n_, mesh_.centroid0[0],
                                       mesh_.centroid0[1], mesh_.centroid0[2], compute_), "init particles");
   cuda_or_throw(cudaStreamSynchronize(compute_), "init sync");
   build_seed_grid();
@@ -98,7 +95,7 @@ Engine::~Engine() {
   for (auto &t : timers_busy_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto &e : chunk_events_) cudaEventDestroy(e);
   cudaFree(d_tets_); cudaFree(d_flux_); cudaFree(d_volume_); cudaFree(d_scratch_);
-  cudaFree(d_px_); cudaFree(d_py_); cudaFree(d_pz_); cudaFree(d_elem_);
+  cudaFree(d_state_);
   cudaFree(d_origin_); cudaFree(d_dest_); cudaFree(d_weights_); cudaFree(d_flying_);
   cudaFree(d_stats_);
   cudaFree(d_tickets_);
@@ -114,22 +111,18 @@ Engine::~Engine() {
 void Engine::build_seed_grid() {
   grid_ = choose_seed_grid(mesh_);
   const int32_t ncell = grid_.nx * grid_.ny * grid_.nz;
-  double *xyz = nullptr, *tx = nullptr, *ty = nullptr, *tz = nullptr;
-  int32_t *te = nullptr;
+  double *xyz = nullptr;
+  ParticleState *ts = nullptr;
   dev_alloc(&d_grid_, size_t(ncell), "seed grid");
   dev_alloc(&xyz, 3 * size_t(ncell), "seed points");
-  dev_alloc(&tx, size_t(ncell), "seed tmp");
-  dev_alloc(&ty, size_t(ncell), "seed tmp");
-  dev_alloc(&tz, size_t(ncell), "seed tmp");
-  dev_alloc(&te, size_t(ncell), "seed tmp");
+  dev_alloc(&ts, size_t(ncell), "seed tmp");
   cuda_or_throw(launch_seed_points(grid_, xyz, compute_), "seed points");
-  cuda_or_throw(launch_init_particles(tx, ty, tz, te, ncell, mesh_.centroid0[0], mesh_.centroid0[1],
+  cuda_or_throw(launch_init_particles(ts, ncell, mesh_.centroid0[0], mesh_.centroid0[1],
                                       mesh_.centroid0[2], compute_), "seed init");
   WalkParams p{};
   p.tets = d_tets_;
   p.flux = d_flux_;
-  p.px = tx; p.py = ty; p.pz = tz;
-  p.elem = te;
+  p.state = ts;
   p.origin = xyz;
   p.begin = 0;
   p.end = ncell;
@@ -138,10 +131,10 @@ void Engine::build_seed_grid() {
   p.work_counter = d_tickets_;
   p.stats = d_stats_;
   cuda_or_throw(launch_walk(p, kVariantPersist, 128, compute_), "seed walk");
-  cuda_or_throw(launch_seed_finalize(xyz, tx, ty, tz, te, d_grid_, ncell, compute_), "seed finalize");
+  cuda_or_throw(launch_seed_finalize(xyz, ts, d_grid_, ncell, compute_), "seed finalize");
   cuda_or_throw(cudaStreamSynchronize(compute_), "seed sync");
   cuda_or_throw(cudaMemset(d_stats_, 0, sizeof(DeviceStats)), "memset");
-  cudaFree(xyz); cudaFree(tx); cudaFree(ty); cudaFree(tz); cudaFree(te);
+  cudaFree(xyz); cudaFree(ts);
   grid_.cell_tet = d_grid_;
   dev_alloc(&d_cell_count_, size_t(ncell), "cell histogram");
   dev_alloc(&d_cell_sums_, size_t(ncell) / 1024 + 2, "cell block sums");
@@ -170,8 +163,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   WalkParams p;
   p.tets = d_tets_;
   p.flux = d_flux_;
-  p.px = d_px_; p.py = d_py_; p.pz = d_pz_;
-  p.elem = d_elem_;
+  p.state = d_state_;
   p.origin = d_origin;
   p.dest = d_dest;
   p.flying = d_flying;
@@ -197,7 +189,8 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
     }
     PTB_CUDA_OK(cudaEventRecord(t.a, stream));
   }
-  if (variant_ == kVariantPersistGather || variant_ == kVariantPersistGatherL1) {
+  if (variant_ == kVariantPersistGather || variant_ == kVariantPersistGatherL1 ||
+      variant_ == kVariantPersistGatherPlain) {
     // counting sort of the range's flying particles by seed-grid cell of their origin
     unsigned int *wc = d_work_count_ + (ticket_next_ % kTicketRing);
     const double *key = d_origin ? d_origin : d_dest;
@@ -205,6 +198,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
                                      d_cell_sums_, d_order_ + begin, wc, stream));
     p.order = d_order_ + begin;
     p.work_count = wc;
+    last_work_count_ = wc;
     p.flying = nullptr;  // order[] holds flying particles only
   }
   PTB_CUDA_OK(launch_walk(p, variant_, block_, stream));
@@ -344,21 +338,21 @@ int Engine::get_normalized_flux(double *out_flux, double *out_volume, int64_t n)
 int Engine::get_element_ids(int32_t *out, int64_t n) {
   if (n != n_) return 1;
   if (synchronize()) return 1;
-  PTB_CUDA_OK(cudaMemcpy(out, d_elem_, size_t(n) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  std::vector<ParticleState> tmp(static_cast<size_t>(n_));
+  PTB_CUDA_OK(cudaMemcpy(tmp.data(), d_state_, size_t(n_) * sizeof(ParticleState), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n_; ++i) out[i] = tmp[i].elem;
   return 0;
 }
 
 int Engine::get_positions(double *out, int64_t n3) {
   if (n3 != 3 * int64_t(n_)) return 1;
   if (synchronize()) return 1;
-  std::vector<double> tmp(size_t(n_) * 3);
-  PTB_CUDA_OK(cudaMemcpy(tmp.data(), d_px_, size_t(n_) * 8, cudaMemcpyDeviceToHost));
-  PTB_CUDA_OK(cudaMemcpy(tmp.data() + n_, d_py_, size_t(n_) * 8, cudaMemcpyDeviceToHost));
-  PTB_CUDA_OK(cudaMemcpy(tmp.data() + 2 * size_t(n_), d_pz_, size_t(n_) * 8, cudaMemcpyDeviceToHost));
+  std::vector<ParticleState> tmp(static_cast<size_t>(n_));
+  PTB_CUDA_OK(cudaMemcpy(tmp.data(), d_state_, size_t(n_) * sizeof(ParticleState), cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < n_; ++i) {
-    out[3 * i] = tmp[i];
-    out[3 * i + 1] = tmp[size_t(n_) + i];
-    out[3 * i + 2] = tmp[2 * size_t(n_) + i];
+    out[3 * i] = tmp[i].x;
+    out[3 * i + 1] = tmp[i].y;
+    out[3 * i + 2] = tmp[i].z;
   }
   return 0;
 }
@@ -407,6 +401,15 @@ int Engine::set_option(const std::string &name, int64_t v) {
     return 1;
   }
   return 0;
+}
+
+int64_t Engine::debug_order(int32_t *out, int64_t n) {
+  if (!last_work_count_ || synchronize()) return -1;
+  unsigned int cnt = 0;
+  if (cudaMemcpy(&cnt, last_work_count_, sizeof(cnt), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  const int64_t m = std::min<int64_t>(n, cnt);
+  if (m > 0 && cudaMemcpy(out, d_order_, size_t(m) * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return cnt;
 }
 
 // FinalizeTallies (PumiTallyImpl.cpp:411-416)

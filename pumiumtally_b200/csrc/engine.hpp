@@ -54,6 +54,7 @@ class Engine {
   int set_option(const std::string &name, int64_t value);
   void set_output_name(const std::string &s) { output_name_ = s; }
   int write_tally_results();
+  int64_t debug_order(int32_t *out, int64_t n);
 
   // multi-GPU exchange step
   int comm_init(int rank, int nranks, const uint8_t id[128]);
@@ -83,8 +84,7 @@ class Engine {
   // device memory
   TetRecord *d_tets_ = nullptr;
   double *d_flux_ = nullptr, *d_volume_ = nullptr, *d_scratch_ = nullptr;
-  double *d_px_ = nullptr, *d_py_ = nullptr, *d_pz_ = nullptr;
-  int32_t *d_elem_ = nullptr;
+  ParticleState *d_state_ = nullptr;  // persistent position + parent element, 32 B per particle
   double *d_origin_ = nullptr, *d_dest_ = nullptr, *d_weights_ = nullptr;  // staging
   int8_t *d_flying_ = nullptr;
   DeviceStats *d_stats_ = nullptr;
@@ -94,6 +94,7 @@ class Engine {
   int32_t *d_grid_ = nullptr;
   // spatial binning of the flying particles (gather-mode kernels)
   int32_t *d_pcell_ = nullptr, *d_order_ = nullptr;
+  unsigned int *last_work_count_ = nullptr;
   unsigned int *d_cell_count_ = nullptr, *d_cell_sums_ = nullptr, *d_work_count_ = nullptr;
 
   cudaStream_t compute_ = nullptr, copy_ = nullptr;

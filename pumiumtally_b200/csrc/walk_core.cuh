@@ -113,6 +113,43 @@ struct DeviceStats {
 
 struct TetRecord;
 
+// Persistent per-particle state: position + parent element in one 32-byte, 32-byte aligned
+// record = one DRAM/L2 sector.  A particle is read with one 256-bit load and written back with
+// one full-sector 256-bit store (no read-modify-write fill), in whatever order particles are
+// processed.  (Reference: DPS members origin + the tracer's elem_ids, PumiTallyImpl.h:39-41.)
+struct alignas(32) ParticleState {
+  double x, y, z;
+  int32_t elem;
+  int32_t pad;
+};
+static_assert(sizeof(ParticleState) == 32, "ParticleState must be one sector");
+
+PTB_HD ParticleState load_state(const ParticleState *p) {
+#if defined(__CUDA_ARCH__)
+  unsigned long long a, b, c, d;
+  asm volatile("ld.global.L1::no_allocate.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+  ParticleState s;
+  s.x = __longlong_as_double((long long)a);
+  s.y = __longlong_as_double((long long)b);
+  s.z = __longlong_as_double((long long)c);
+  s.elem = (int32_t)(d & 0xffffffffull);
+  s.pad = 0;
+  return s;
+#else
+  return *p;
+#endif
+}
+PTB_HD void store_state(ParticleState *p, double x, double y, double z, int32_t elem) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.L1::no_allocate.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p),
+               "l"((unsigned long long)__double_as_longlong(x)), "l"((unsigned long long)__double_as_longlong(y)),
+               "l"((unsigned long long)__double_as_longlong(z)), "l"((unsigned long long)(uint32_t)elem)
+               : "memory");
+#else
+  p->x = x; p->y = y; p->z = z; p->elem = elem; p->pad = 0;
+#endif
+}
+
 // Uniform background grid over the mesh bounding box: cell -> the tet that
 // contains the cell centre (-1 if the centre is outside the mesh).  A far
 // relocation (re-sampled particle, initial localisation) starts its tally-off
@@ -142,8 +179,7 @@ PTB_HD void seed_point(const SeedGrid &g, int cx, int cy, int cz, double &x, dou
 struct WalkParams {
   const TetRecord *tets;   // [E] packed records
   double *flux;            // [E] raw tally
-  double *px, *py, *pz;    // [N] persistent particle position (SoA)
-  int32_t *elem;           // [N] persistent parent element
+  ParticleState *state;    // [N] persistent particle position + parent element
   const double *origin;    // [3N] AoS relocation target (phase 1), nullptr = skip phase
   const double *dest;      // [3N] AoS flight target (phase 2), nullptr = skip phase
   const int8_t *flying;    // [N], nullptr = every particle flies (localisation)
@@ -228,8 +264,9 @@ PTB_HD void begin_particle(const WalkParams &P, int i, Ray &r, Counters &c, bool
   r.stage = kStageDone;
   const bool fly = P.flying ? (P.flying[i] == 1) : true;  // only the value 1 flies (Impl.cpp:95)
   if (!fly) return;  // dest := own origin => zero-length walk, nothing changes (Impl.cpp:100-102)
-  const double x = P.px[i], y = P.py[i], z = P.pz[i];
-  r.e = P.elem[i];
+  const ParticleState s0 = load_state(P.state + i);
+  const double x = s0.x, y = s0.y, z = s0.z;
+  r.e = s0.elem;
   if (P.origin) {
     const double tx = PTB_LDG(P.origin + 3 * (size_t)i), ty = PTB_LDG(P.origin + 3 * (size_t)i + 1),
                  tz = PTB_LDG(P.origin + 3 * (size_t)i + 2);
@@ -248,8 +285,9 @@ PTB_HD void end_ray(const WalkParams &P, int i, Ray &r, bool reached, double tne
   if (r.stage == kStageSeed && !reached) {
     // the target is not reachable from the seed inside the mesh (it lies outside the hull):
     // redo phase 1 exactly as the reference does, from the particle's stored position
-    x = P.px[i]; y = P.py[i]; z = P.pz[i];
-    r.e = P.elem[i];
+    const ParticleState s0 = load_state(P.state + i);
+    x = s0.x; y = s0.y; z = s0.z;
+    r.e = s0.elem;
     set_ray(r, x, y, z, r.tx, r.ty, r.tz);
     r.stage = kStageReloc;
     return;
@@ -263,8 +301,7 @@ PTB_HD void end_ray(const WalkParams &P, int i, Ray &r, bool reached, double tne
     start_tally(P, i, r, x, y, z, c, writer);  // phase 2 starts where phase 1 ended
   } else {
     if (writer) {
-      P.px[i] = x; P.py[i] = y; P.pz[i] = z;
-      P.elem[i] = r.e;
+      store_state(P.state + i, x, y, z, r.e);
     }
     r.stage = kStageDone;
   }

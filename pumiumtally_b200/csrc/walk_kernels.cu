@@ -13,6 +13,7 @@
 #include "walk_kernels.hpp"
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdint>
 
 #include "walk_core.cuh"
@@ -205,17 +206,17 @@ __global__ void __launch_bounds__(256) walk_quad_kernel(const WalkParams P) {
 // hold back the rest of the range.
 
 constexpr int kChunk = 16;  // particles per staged chunk (all slice sizes stay multiples of 16 bytes)
-constexpr uint32_t kB8 = 8u * kChunk, kB24 = 24u * kChunk, kB4 = 4u * kChunk, kB1 = 1u * kChunk;
+constexpr uint32_t kB8 = 8u * kChunk, kB24 = 24u * kChunk, kB32 = 32u * kChunk, kB1 = 1u * kChunk;
 
-struct __align__(16) ParticleStage {
+struct __align__(32) ParticleStage {
   double origin[3 * kChunk];
   double dest[3 * kChunk];
-  double px[kChunk], py[kChunk], pz[kChunk], w[kChunk];
-  int32_t elem[kChunk];
+  ParticleState state[kChunk];
+  double w[kChunk];
   int8_t fly[kChunk];
   int32_t id[kChunk];  // gather mode: particle id of each slot
 };
-static_assert(sizeof(ParticleStage) == 89 * kChunk && sizeof(ParticleStage) % 16 == 0, "stage layout");
+static_assert(sizeof(ParticleStage) % 32 == 0 && offsetof(ParticleStage, state) % 32 == 0 && offsetof(ParticleStage, w) % 16 == 0 && offsetof(ParticleStage, fly) % 16 == 0, "stage layout");
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -227,13 +228,10 @@ __device__ __forceinline__ void stage_load(const WalkParams &P, int chunk, Parti
   const int count = (int)min((long long)kChunk, (long long)P.end - base);
   if (count == kChunk && P.bulk_ok) {
     if (lane == 0) {
-      const uint32_t bytes = 3u * kB8 + kB4 + (P.origin ? kB24 : 0u) + (P.dest ? kB24 + kB8 : 0u) +
+      const uint32_t bytes = kB32 + (P.origin ? kB24 : 0u) + (P.dest ? kB24 + kB8 : 0u) +
                              (P.flying ? kB1 : 0u);
       mbar_expect_tx(bar, bytes);
-      bulk_g2s(smem_u32(st->px), P.px + base, kB8, bar);
-      bulk_g2s(smem_u32(st->py), P.py + base, kB8, bar);
-      bulk_g2s(smem_u32(st->pz), P.pz + base, kB8, bar);
-      bulk_g2s(smem_u32(st->elem), P.elem + base, kB4, bar);
+      bulk_g2s(smem_u32(st->state), P.state + base, kB32, bar);
       if (P.origin) bulk_g2s(smem_u32(st->origin), P.origin + 3 * base, kB24, bar);
       if (P.dest) {
         bulk_g2s(smem_u32(st->dest), P.dest + 3 * base, kB24, bar);
@@ -245,8 +243,7 @@ __device__ __forceinline__ void stage_load(const WalkParams &P, int chunk, Parti
     // ragged last chunk, or caller pointers that are not 16-byte aligned
     if (lane < count) {
       const long long i = base + lane;
-      st->px[lane] = P.px[i]; st->py[lane] = P.py[i]; st->pz[lane] = P.pz[i];
-      st->elem[lane] = P.elem[i];
+      st->state[lane] = load_state(P.state + i);
       if (P.origin)
         for (int k = 0; k < 3; ++k) st->origin[3 * lane + k] = P.origin[3 * i + k];
       if (P.dest) {
@@ -266,8 +263,8 @@ __device__ __forceinline__ void begin_from_stage(const WalkParams &P, const Part
   r.stage = kStageDone;
   const bool fly = P.flying ? (st->fly[s] == 1) : true;
   if (!fly) return;
-  const double x = st->px[s], y = st->py[s], z = st->pz[s];
-  r.e = st->elem[s];
+  const double x = st->state[s].x, y = st->state[s].y, z = st->state[s].z;
+  r.e = st->state[s].elem;
   if (P.origin) {
     const double tx = st->origin[3 * s], ty = st->origin[3 * s + 1], tz = st->origin[3 * s + 2];
     if (tx != x || ty != y || tz != z) {
@@ -338,13 +335,10 @@ __device__ __forceinline__ void stage_load_hint(const WalkParams &P, int chunk, 
   const int count = (int)min((long long)kChunk, (long long)P.end - base);
   if (count == kChunk && P.bulk_ok) {
     if (lane == 0) {
-      const uint32_t bytes = 3u * kB8 + kB4 + (P.origin ? kB24 : 0u) + (P.dest ? kB24 + kB8 : 0u) +
+      const uint32_t bytes = kB32 + (P.origin ? kB24 : 0u) + (P.dest ? kB24 + kB8 : 0u) +
                              (P.flying ? kB1 : 0u);
       mbar_expect_tx(bar, bytes);
-      bulk_g2s_hint(smem_u32(st->px), P.px + base, kB8, bar, pol);
-      bulk_g2s_hint(smem_u32(st->py), P.py + base, kB8, bar, pol);
-      bulk_g2s_hint(smem_u32(st->pz), P.pz + base, kB8, bar, pol);
-      bulk_g2s_hint(smem_u32(st->elem), P.elem + base, kB4, bar, pol);
+      bulk_g2s_hint(smem_u32(st->state), P.state + base, kB32, bar, pol);
       if (P.origin) bulk_g2s_hint(smem_u32(st->origin), P.origin + 3 * base, kB24, bar, pol);
       if (P.dest) {
         bulk_g2s_hint(smem_u32(st->dest), P.dest + 3 * base, kB24, bar, pol);
@@ -363,8 +357,8 @@ __device__ __forceinline__ void stage_load_hint(const WalkParams &P, int chunk, 
 __device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_4(uint32_t dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
@@ -376,10 +370,8 @@ __device__ __forceinline__ void stage_gather(const WalkParams &P, int chunk, int
   if (lane < count) {
     const int i = __ldg(P.order + base + lane);
     st->id[lane] = i;
-    cp_async_8(smem_u32(&st->px[lane]), P.px + i);
-    cp_async_8(smem_u32(&st->py[lane]), P.py + i);
-    cp_async_8(smem_u32(&st->pz[lane]), P.pz + i);
-    cp_async_4(smem_u32(&st->elem[lane]), P.elem + i);
+    cp_async_16(smem_u32(&st->state[lane]), P.state + i);
+    cp_async_16(smem_u32(&st->state[lane]) + 16u, reinterpret_cast<const char *>(P.state + i) + 16);
     if (P.origin) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) cp_async_8(smem_u32(&st->origin[3 * lane + k]), P.origin + 3 * (size_t)i + k);
@@ -576,13 +568,9 @@ cudaError_t launch_persist(const WalkParams &p, long long n, cudaStream_t stream
 
 // K14-K16 of SURVEY.md 2b (PumiTallyImpl.cpp:492-528): every particle starts
 // at the centroid of element 0.
-__global__ void init_particles_kernel(double *px, double *py, double *pz, int32_t *elem, int32_t n,
-                                      double cx, double cy, double cz) {
+__global__ void init_particles_kernel(ParticleState *state, int32_t n, double cx, double cy, double cz) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    px[i] = cx; py[i] = cy; pz[i] = cz;
-    elem[i] = 0;
-  }
+  if (i < n) store_state(state + i, cx, cy, cz, 0);
 }
 
 // Seed grid construction: the seed points are written as "particles to
@@ -598,14 +586,13 @@ __global__ void seed_points_kernel(SeedGrid g, double *xyz, int32_t ncell) {
   }
 }
 
-__global__ void seed_finalize_kernel(const double *xyz, const double *px, const double *py,
-                                     const double *pz, const int32_t *elem, int32_t *cell_tet,
+__global__ void seed_finalize_kernel(const double *xyz, const ParticleState *state, int32_t *cell_tet,
                                      int32_t ncell) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < ncell) {
-    const bool reached = px[i] == xyz[3 * (size_t)i] && py[i] == xyz[3 * (size_t)i + 1] &&
-                         pz[i] == xyz[3 * (size_t)i + 2];
-    cell_tet[i] = reached ? elem[i] : -1;
+    const ParticleState s = load_state(state + i);
+    const bool reached = s.x == xyz[3 * (size_t)i] && s.y == xyz[3 * (size_t)i + 1] && s.z == xyz[3 * (size_t)i + 2];
+    cell_tet[i] = reached ? s.elem : -1;
   }
 }
 
@@ -655,6 +642,10 @@ cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_
       return launch_persist<128, kFetchPolicy, 7, 1, true>(p, n, stream);
     case kVariantPersistGatherL1:
       return launch_persist<128, kFetchPolicyL1, 7, 1, true, 40>(p, n, stream);
+    case kVariantPersistGatherPlain:
+      return launch_persist<128, kFetchPlain, 7, 1, true, 40>(p, n, stream);
+    case kVariantPersistPlainL1:
+      return launch_persist<128, kFetchPlain, 7, 1, false, 40>(p, n, stream);
     case kVariantPersistCoop:
       return launch_persist<128, kFetchCoop, 7>(p, n, stream);
     case kVariantPersistCoopRefill8:
@@ -675,10 +666,10 @@ cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_
   return cudaGetLastError();
 }
 
-cudaError_t launch_init_particles(double *px, double *py, double *pz, int32_t *elem, int32_t n,
-                                  double cx, double cy, double cz, cudaStream_t stream) {
+cudaError_t launch_init_particles(ParticleState *state, int32_t n, double cx, double cy, double cz,
+                                  cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  init_particles_kernel<<<(n + 255) / 256, 256, 0, stream>>>(px, py, pz, elem, n, cx, cy, cz);
+  init_particles_kernel<<<(n + 255) / 256, 256, 0, stream>>>(state, n, cx, cy, cz);
   return cudaGetLastError();
 }
 
@@ -688,10 +679,9 @@ cudaError_t launch_seed_points(const SeedGrid &g, double *xyz, cudaStream_t stre
   return cudaGetLastError();
 }
 
-cudaError_t launch_seed_finalize(const double *xyz, const double *px, const double *py,
-                                 const double *pz, const int32_t *elem, int32_t *cell_tet,
+cudaError_t launch_seed_finalize(const double *xyz, const ParticleState *state, int32_t *cell_tet,
                                  int32_t ncell, cudaStream_t stream) {
-  seed_finalize_kernel<<<(ncell + 255) / 256, 256, 0, stream>>>(xyz, px, py, pz, elem, cell_tet, ncell);
+  seed_finalize_kernel<<<(ncell + 255) / 256, 256, 0, stream>>>(xyz, state, cell_tet, ncell);
   return cudaGetLastError();
 }
 

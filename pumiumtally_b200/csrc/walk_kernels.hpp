@@ -26,7 +26,9 @@ enum WalkVariant : int {
   kVariantPersistCoopOcc6 = 14,      // 11 compiled for 6 resident blocks (no spills)
   kVariantPersistGather = 15,        // 4 on spatially binned particles (order[] from launch_bin_particles)
   kVariantPersistGatherL1 = 16,      // 15 with L1-allocating tet loads and a larger L1 carve-out
-  kNumVariants = 17
+  kVariantPersistGatherPlain = 17,   // 15 with plain (L1-allocating, no policy) tet loads
+  kVariantPersistPlainL1 = 18,       // 3 with a 40% shared-memory carve-out (large L1)
+  kNumVariants = 19
 };
 
 cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_t stream);
@@ -35,11 +37,10 @@ cudaError_t launch_bin_particles(const SeedGrid &g, const double *origin, const 
                                  unsigned int *sums, int32_t *order, unsigned int *work_count,
                                  cudaStream_t stream);
 cudaError_t launch_seed_points(const SeedGrid &g, double *xyz, cudaStream_t stream);
-cudaError_t launch_seed_finalize(const double *xyz, const double *px, const double *py,
-                                 const double *pz, const int32_t *elem, int32_t *cell_tet,
+cudaError_t launch_seed_finalize(const double *xyz, const ParticleState *state, int32_t *cell_tet,
                                  int32_t ncell, cudaStream_t stream);
-cudaError_t launch_init_particles(double *px, double *py, double *pz, int32_t *elem, int32_t n,
-                                  double cx, double cy, double cz, cudaStream_t stream);
+cudaError_t launch_init_particles(ParticleState *state, int32_t n, double cx, double cy, double cz,
+                                  cudaStream_t stream);
 cudaError_t launch_normalize(const double *flux, const double *volume, double *out, int64_t n,
                              cudaStream_t stream);
 

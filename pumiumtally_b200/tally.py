@@ -59,6 +59,7 @@ C_API = {
     "pumitally_nccl_unique_id": (C.c_int, [_u8p]),
     "pumitally_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _u8p]),
     "pumitally_allreduce_tally": (C.c_int, [C.c_void_p]),
+    "pumitally_debug_order": (C.c_int64, [C.c_void_p, _ip, C.c_int64]),
     "pumitally_version": (C.c_char_p, []),
 }
 
@@ -229,6 +230,11 @@ class PumiTally:
         if self._L.pumitally_get_stats(self._h, C.byref(s)):
             raise RuntimeError("get_stats failed")
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def debug_order(self):
+        out = np.empty(self.num_particles, dtype=np.int32)
+        cnt = int(self._L.pumitally_debug_order(self._h, out.ctypes.data_as(_ip), out.size))
+        return out[:max(cnt, 0)]
 
     def reset_tally(self):
         self._L.pumitally_reset_tally(self._h)

@@ -20,8 +20,8 @@ namespace {
 struct Emul {
   HostMesh mesh;
   std::vector<TetRecord> recs;
-  std::vector<double> flux, px, py, pz;
-  std::vector<int32_t> elem;
+  std::vector<double> flux;
+  std::vector<ParticleState> state;
   DeviceStats stats{};
   int n = 0;
   SeedGrid grid{};
@@ -31,30 +31,28 @@ struct Emul {
   void build_grid() {
     grid = choose_seed_grid(mesh);
     const int nc = grid.nx * grid.ny * grid.nz;
-    std::vector<double> xyz(3 * size_t(nc)), tx(nc, mesh.centroid0[0]), ty(nc, mesh.centroid0[1]),
-        tz(nc, mesh.centroid0[2]);
-    std::vector<int32_t> te(nc, 0);
+    std::vector<double> xyz(3 * size_t(nc));
+    std::vector<ParticleState> ts(nc, ParticleState{mesh.centroid0[0], mesh.centroid0[1], mesh.centroid0[2], 0, 0});
     for (int i = 0; i < nc; ++i)
       seed_point(grid, i % grid.nx, (i / grid.nx) % grid.ny, i / (grid.nx * grid.ny), xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
     DeviceStats scratch{};
-    walk(tx.data(), ty.data(), tz.data(), te.data(), nc, xyz.data(), nullptr, nullptr, nullptr, &scratch, nullptr);
+    walk(ts.data(), nc, xyz.data(), nullptr, nullptr, nullptr, &scratch, nullptr);
     cell_tet.resize(nc);
     for (int i = 0; i < nc; ++i)
-      cell_tet[i] = (tx[i] == xyz[3 * i] && ty[i] == xyz[3 * i + 1] && tz[i] == xyz[3 * i + 2]) ? te[i] : -1;
+      cell_tet[i] = (ts[i].x == xyz[3 * i] && ts[i].y == xyz[3 * i + 1] && ts[i].z == xyz[3 * i + 2]) ? ts[i].elem : -1;
     grid.cell_tet = cell_tet.data();
   }
   void run(const double *origin, const double *dest, const int8_t *flying, const double *weights) {
-    walk(px.data(), py.data(), pz.data(), elem.data(), n, origin, dest, flying, weights, &stats,
+    walk(state.data(), n, origin, dest, flying, weights, &stats,
          grid.cell_tet ? &grid : nullptr);
   }
-  void walk(double *qx, double *qy, double *qz, int32_t *qe, int count, const double *origin,
+  void walk(ParticleState *qs, int count, const double *origin,
             const double *dest, const int8_t *flying, const double *weights, DeviceStats *st,
             const SeedGrid *g) {
     WalkParams P{};
     P.tets = recs.data();
     P.flux = flux.data();
-    P.px = qx; P.py = qy; P.pz = qz;
-    P.elem = qe;
+    P.state = qs;
     P.origin = origin; P.dest = dest; P.flying = flying; P.weights = weights;
     P.begin = 0; P.end = count;
     P.max_iters = int32_t(mesh.ntets + 16);
@@ -91,10 +89,7 @@ void *ptb_emul_create(const double *coords, int64_t nverts, const int32_t *t2v, 
   e->recs = e->mesh.records;
   e->n = n;
   e->flux.assign(size_t(ntets), 0.0);
-  e->px.assign(size_t(n), e->mesh.centroid0[0]);
-  e->py.assign(size_t(n), e->mesh.centroid0[1]);
-  e->pz.assign(size_t(n), e->mesh.centroid0[2]);
-  e->elem.assign(size_t(n), 0);
+  e->state.assign(size_t(n), ParticleState{e->mesh.centroid0[0], e->mesh.centroid0[1], e->mesh.centroid0[2], 0, 0});
   return e;
 }
 void *ptb_emul_create_spec(const char *spec, int n) {
@@ -104,10 +99,7 @@ void *ptb_emul_create_spec(const char *spec, int n) {
   e->recs = e->mesh.records;
   e->n = n;
   e->flux.assign(size_t(e->mesh.ntets), 0.0);
-  e->px.assign(size_t(n), e->mesh.centroid0[0]);
-  e->py.assign(size_t(n), e->mesh.centroid0[1]);
-  e->pz.assign(size_t(n), e->mesh.centroid0[2]);
-  e->elem.assign(size_t(n), 0);
+  e->state.assign(size_t(n), ParticleState{e->mesh.centroid0[0], e->mesh.centroid0[1], e->mesh.centroid0[2], 0, 0});
   return e;
 }
 int ptb_emul_build_grid(void *h) {
@@ -141,9 +133,10 @@ void ptb_emul_move(void *h, const double *origin, const double *dest, int8_t *fl
 void ptb_emul_get(void *h, double *flux, int32_t *elem, double *pos, unsigned long long *stats, int32_t *adj) {
   auto *e = static_cast<Emul *>(h);
   if (flux) std::memcpy(flux, e->flux.data(), e->flux.size() * 8);
-  if (elem) std::memcpy(elem, e->elem.data(), e->elem.size() * 4);
+  if (elem)
+    for (int i = 0; i < e->n; ++i) elem[i] = e->state[i].elem;
   if (pos)
-    for (int i = 0; i < e->n; ++i) { pos[3 * i] = e->px[i]; pos[3 * i + 1] = e->py[i]; pos[3 * i + 2] = e->pz[i]; }
+    for (int i = 0; i < e->n; ++i) { pos[3 * i] = e->state[i].x; pos[3 * i + 1] = e->state[i].y; pos[3 * i + 2] = e->state[i].z; }
   if (stats) { stats[0] = e->stats.segments; stats[1] = e->stats.tracks; stats[2] = e->stats.relocations; stats[3] = e->stats.lost; }
   if (adj) std::memcpy(adj, e->mesh.t2t.data(), e->mesh.t2t.size() * 4);
 }

@@ -68,6 +68,29 @@ def test_out_of_mesh_origin_falls_back_to_reference_walk(seed_grid):
     assert eng.stats()["lost"] == 0
 
 
+def test_binning_groups_flying_particles_by_cell():
+    """The per-move counting sort: order[] holds exactly the flying particles, grouped by the
+    seed-grid cell of their origin in ascending cell order."""
+    cells = (12, 10, 8)
+    coords, t2v, wl = box_case(cells, 200_000)
+    e = gpu_engine(16)(coords, t2v, wl.n)
+    e.CopyInitialPosition(wl.initial_positions().reshape(-1))
+    o, d, f, w = wl.next_step()
+    fly = f == 1
+    e.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
+    order = e.debug_order()
+    assert len(order) == int(fly.sum())
+    assert np.array_equal(np.sort(order), np.flatnonzero(fly))
+    # recompute the cell of every origin with the grid geometry of csrc/seed_grid.hpp
+    ncell_target = max(len(t2v) / 4.0, 1.0)
+    h = (np.prod(cells) / ncell_target) ** (1.0 / 3.0)
+    dims = np.minimum(np.maximum(np.ceil(np.array(cells) / h), 1), 1024).astype(int)
+    h = max(h, *(np.array(cells) / dims))
+    c = np.minimum((o[order] / h).astype(int), dims - 1)
+    key = (c[:, 2] * dims[1] + c[:, 1]) * dims[0] + c[:, 0]
+    assert (np.diff(key) >= 0).all(), f"{int((np.diff(key) < 0).sum())} order inversions"
+
+
 def test_seed_grid_cuts_relocation_work_not_results():
     coords, t2v, wl = box_case((12, 12, 12), 100_000)
     res = []

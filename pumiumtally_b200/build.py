@@ -24,6 +24,7 @@ SOURCES = [
     "engine.cu",
     "tet_mesh.cpp",
     "osh_reader.cpp",
+    "gmsh_reader.cpp",
     "vtk_writer.cpp",
     "nccl_dl.cpp",
     "c_api.cpp",

@@ -42,7 +42,7 @@ struct HostMesh {
   double centroid0[3] = {0, 0, 0};  // centroid of element 0 (PumiTallyImpl.cpp:500-509)
   double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};
 
-  // "box:nx,ny,nz[,lx,ly,lz]" | raw mesh file | Omega_h .osh directory.
+  // "box:nx,ny,nz[,lx,ly,lz]" | raw mesh file | Gmsh .msh (ASCII 2.2 / 4.1) | Omega_h .osh directory.
   bool load(const std::string &spec, std::string *err);
   bool from_arrays(const double *coords, int64_t nverts, const int32_t *tet2vert, int64_t ntets,
                    std::string *err);
@@ -55,6 +55,8 @@ void build_kuhn_box(int nx, int ny, int nz, double lx, double ly, double lz,
                     std::vector<double> *coords, std::vector<int32_t> *t2v);
 bool read_raw_mesh(const std::string &path, std::vector<double> *coords,
                    std::vector<int32_t> *t2v, std::string *err);
+bool read_gmsh_mesh(const std::string &path, std::vector<double> *coords,
+                    std::vector<int32_t> *t2v, std::string *err);
 bool read_osh_mesh(const std::string &dir, std::vector<double> *coords,
                    std::vector<int32_t> *t2v, std::string *err);
 

@@ -112,3 +112,35 @@ def save_raw_mesh(path: str, coords, tet2vert) -> None:
         f.write(np.array([coords.shape[0], tet2vert.shape[0]], dtype="<i8").tobytes())
         f.write(coords.tobytes())
         f.write(tet2vert.tobytes())
+
+
+def save_gmsh(path: str, coords, tet2vert, version: str = "2.2", node_id_offset: int = 1) -> None:
+    """Write an ASCII Gmsh file (format 2.2 or 4.1) holding the nodes and the tets as element
+    type 4, plus one boundary triangle and one point element that readers must skip."""
+    coords = np.asarray(coords, dtype=np.float64)
+    t2v = np.asarray(tet2vert, dtype=np.int64) + node_id_offset
+    nv, nt = len(coords), len(t2v)
+    with open(path, "w") as f:
+        if version.startswith("2"):
+            f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % nv)
+            for i, (x, y, z) in enumerate(coords):
+                f.write("%d %.17g %.17g %.17g\n" % (i + node_id_offset, x, y, z))
+            f.write("$EndNodes\n$Elements\n%d\n" % (nt + 2))
+            f.write("1 15 2 0 1 %d\n" % t2v[0, 0])
+            f.write("2 2 2 0 1 %d %d %d\n" % tuple(t2v[0, :3]))
+            for e, t in enumerate(t2v):
+                f.write("%d 4 2 0 1 %d %d %d %d\n" % (e + 3, *t))
+            f.write("$EndElements\n")
+        else:
+            f.write("$MeshFormat\n4.1 0 8\n$EndMeshFormat\n")
+            f.write("$Nodes\n1 %d %d %d\n3 1 0 %d\n" % (nv, node_id_offset, nv + node_id_offset - 1, nv))
+            for i in range(nv):
+                f.write("%d\n" % (i + node_id_offset))
+            for x, y, z in coords:
+                f.write("%.17g %.17g %.17g\n" % (x, y, z))
+            f.write("$EndNodes\n$Elements\n2 %d 1 %d\n" % (nt + 1, nt + 1))
+            f.write("2 1 2 1\n1 %d %d %d\n" % tuple(t2v[0, :3]))
+            f.write("3 1 4 %d\n" % nt)
+            for e, t in enumerate(t2v):
+                f.write("%d %d %d %d %d\n" % (e + 2, *t))
+            f.write("$EndElements\n")

@@ -71,7 +71,8 @@ def emul_lib():
         so = os.path.join(HERE, "host_emul", "libptb_emul.so")
         srcs = [os.path.join(HERE, "host_emul", "emul_walk.cpp"),
                 os.path.join(ROOT, "pumiumtally_b200", "csrc", "tet_mesh.cpp"),
-                os.path.join(ROOT, "pumiumtally_b200", "csrc", "osh_reader.cpp")]
+                os.path.join(ROOT, "pumiumtally_b200", "csrc", "osh_reader.cpp"),
+                os.path.join(ROOT, "pumiumtally_b200", "csrc", "gmsh_reader.cpp")]
         deps = srcs + [os.path.join(ROOT, "pumiumtally_b200", "csrc", h) for h in ("walk_core.cuh", "tet_mesh.hpp", "seed_grid.hpp")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp",

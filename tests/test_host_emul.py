@@ -31,6 +31,22 @@ def test_box_spec_matches_numpy_generator():
     np.testing.assert_allclose(v, tet_volumes(cn, tn), rtol=1e-13)
 
 
+@pytest.mark.parametrize("version", ["2.2", "4.1"])
+def test_gmsh_ingest(tmp_path, version):
+    """Gmsh .msh (ASCII 2.2 / 4.1) -> same mesh as the arrays it was written from; non-tet
+    elements and 1-based node ids are handled."""
+    from pumiumtally_b200.mesh import save_gmsh
+
+    c, t = jitter_interior(*kuhn_box(3, 2, 2), amplitude=0.1)
+    path = str(tmp_path / "mesh.msh")
+    save_gmsh(path, c, t, version=version)
+    e = HostEmulTally(spec=path, num_particles=1)
+    cm, tm, vm = e.mesh_arrays()
+    np.testing.assert_array_equal(tm, t)
+    np.testing.assert_array_equal(cm, c)
+    np.testing.assert_allclose(vm, tet_volumes(c, t), rtol=1e-13)
+
+
 @pytest.mark.parametrize("mesh", ["kuhn", "jitter", "delaunay"])
 def test_adjacency_matches_oracle(mesh):
     if mesh == "kuhn":

@@ -142,7 +142,7 @@ bool HostMesh::from_arrays(const double *c, int64_t nv, const int32_t *t, int64_
 }
 
 bool HostMesh::finalize(std::string *err) {
-  if (ntets >= int64_t(0x7fffffff) / 4) { *err = "too many tets for int32 face slots"; return false; }
+  if (ntets >= int64_t(0x3fffffff)) { *err = "too many tets: element ids are 30-bit"; return false; }
   for (size_t i = 0; i < t2v.size(); ++i)
     if (t2v[i] < 0 || t2v[i] >= nverts) { *err = "tet2vert index out of range"; return false; }
 
@@ -235,7 +235,15 @@ bool HostMesh::finalize(std::string *err) {
       // payload = this tet XOR neighbour (hull: neighbour = -1): the same 32 bits on both
       // sides of the face, so the two records hold bit-identical planes up to the sign bit
       // and the kernel can use the doubles as they are, payload included
-      uint32_t pay = uint32_t(e) ^ uint32_t(t2t[4 * e + f]);
+      // bits 0..29: this tet XOR neighbour (hull = all ones); bits 30..31: f XOR the neighbour's
+      // local index of this face.  Both are symmetric, so both records carry the same 32 bits.
+      const int32_t nb = t2t[4 * e + f];
+      int back = f;
+      if (nb >= 0)
+        for (int q = 0; q < 4; ++q)
+          if (t2t[4 * size_t(nb) + q] == int32_t(e)) back = q;
+      const uint32_t idmask = 0x3fffffffu;
+      uint32_t pay = ((uint32_t(e) ^ (nb < 0 ? idmask : uint32_t(nb))) & idmask) | (uint32_t(f ^ back) << 30);
       for (int q = 0; q < 4; ++q)
         r.d[4 * f + q] = bdouble(dbits(p[q]) | uint64_t((pay >> (8 * q)) & 0xffu));
     }

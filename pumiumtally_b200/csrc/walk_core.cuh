@@ -43,11 +43,8 @@ PTB_HD uint32_t dlo(double x) {
   uint64_t u; memcpy(&u, &x, 8); return (uint32_t)u;
 #endif
 }
-// Decoded face planes of one tet.
-struct TetPlanes {
-  double nx[4], ny[4], nz[4], c[4];
-  int32_t nbr[4];
-};
+// Tet ids are 30-bit; the all-ones id marks the hull.
+constexpr uint32_t kIdMask = 0x3fffffffu;
 
 // byte 0 of four words -> one word (b0 | b1<<8 | b2<<16 | b3<<24)
 PTB_HD uint32_t pack_low_bytes(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
@@ -58,45 +55,55 @@ PTB_HD uint32_t pack_low_bytes(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w
 #endif
 }
 
-// r = the 16 raw doubles of the record of tet `self`.  The doubles are used as
-// stored (the payload bytes are part of the plane on both sides of the face).
-PTB_HD void decode_record(const double (&r)[16], int32_t self, TetPlanes &t) {
-PTB_UNROLL
-  for (int f = 0; f < 4; ++f) {
-    t.nbr[f] = (int32_t)(pack_low_bytes(dlo(r[4 * f]), dlo(r[4 * f + 1]), dlo(r[4 * f + 2]), dlo(r[4 * f + 3])) ^
-                         (uint32_t)self);
-    t.nx[f] = r[4 * f + 0];
-    t.ny[f] = r[4 * f + 1];
-    t.nz[f] = r[4 * f + 2];
-    t.c[f] = r[4 * f + 3];
-  }
+// Payload of one face of tet `self` (the four doubles a,b,c,d of local face f): the id of the
+// neighbour across it (-1 = hull) and `back`, the neighbour's local index of the shared face.
+// Stored symmetrically -- bits 0..29 = self XOR neighbour, bits 30..31 = f XOR back -- so the
+// payload, and with it the plane, is bit-identical in the two records that share the face.
+PTB_HD void face_payload(double a, double b, double c, double d, int32_t self, int f, int32_t &nbr,
+                         int32_t &back) {
+  const uint32_t pay = pack_low_bytes(dlo(a), dlo(b), dlo(c), dlo(d));
+  const uint32_t x = (pay ^ (uint32_t)self) & kIdMask;
+  nbr = (int32_t)((x + 1u) & kIdMask) - 1;  // kIdMask -> -1 (hull), everything else unchanged
+  back = (int32_t)((pay >> 30) ^ (uint32_t)f);
 }
 
-// Ray x(t) = o + t*u, t in [0,1].  Returns the smallest exit parameter over
-// the faces the ray leaves through (n.u > 0) and that face's neighbour; texit
-// = +inf when no face qualifies (zero-length ray).  Numerator and denominator
-// depend only on the plane and the ray, never on the tet, so both tets sharing
-// a face compute the identical quotient.
-//
-// The minimum is selected by cross-multiplication (num_a*den_b < num_b*den_a,
-// both den > 0) so a crossing costs one fp64 division instead of four; ties
-// within rounding pick either face, which only reorders a zero-length piece.
-PTB_HD void exit_face(const TetPlanes &t, double ox, double oy, double oz, double ux, double uy,
-                      double uz, double &texit, int32_t &next) {
+// Running minimum of the exit parameter over the faces scanned so far.  Ray x(t) = o + t*u,
+// t in [0,1]; a face is a candidate when the ray leaves through it (n.u > 0).  Numerator and
+// denominator depend only on the plane and the ray, never on the tet, so both tets sharing a
+// face compute the identical quotient.  The minimum is selected by cross-multiplication
+// (num_a*den_b < num_b*den_a, both den > 0): one fp64 division per crossing instead of one per
+// face; ties within rounding pick either face, which only reorders a zero-length piece.
+struct ExitScan {
   double bnum = 1.0, bden = 0.0;  // t = +inf
-  int32_t nb = -2;
+  int32_t nbr = -2, back = -1;
+};
+
+PTB_HD void scan_face(ExitScan &s, double nx, double ny, double nz, double c, int32_t nbr,
+                      int32_t back, double ox, double oy, double oz, double ux, double uy,
+                      double uz) {
+  const double den = nx * ux + ny * uy + nz * uz;
+  const double num = c - (nx * ox + ny * oy + nz * oz);
+  const bool take = (den > 0.0) && (num * s.bden < s.bnum * den);
+  s.bnum = take ? num : s.bnum;
+  s.bden = take ? den : s.bden;
+  s.nbr = take ? nbr : s.nbr;
+  s.back = take ? back : s.back;
+}
+
+// bnum >= bden  <=>  t >= 1: the destination lies in this tet, no division needed
+PTB_HD double exit_parameter(const ExitScan &s) {
+  return (s.bnum < s.bden) ? s.bnum / s.bden : __builtin_huge_val();
+}
+
+// All four faces of a record held as 16 raw doubles (variants that fetch the whole line).
+PTB_HD void scan_record(const double (&r)[16], int32_t self, double ox, double oy, double oz,
+                        double ux, double uy, double uz, ExitScan &s) {
 PTB_UNROLL
   for (int f = 0; f < 4; ++f) {
-    const double den = t.nx[f] * ux + t.ny[f] * uy + t.nz[f] * uz;
-    const double num = t.c[f] - (t.nx[f] * ox + t.ny[f] * oy + t.nz[f] * oz);
-    const bool take = (den > 0.0) && (num * bden < bnum * den);
-    bnum = take ? num : bnum;
-    bden = take ? den : bden;
-    nb = take ? t.nbr[f] : nb;
+    int32_t nb, bk;
+    face_payload(r[4 * f], r[4 * f + 1], r[4 * f + 2], r[4 * f + 3], self, f, nb, bk);
+    scan_face(s, r[4 * f], r[4 * f + 1], r[4 * f + 2], r[4 * f + 3], nb, bk, ox, oy, oz, ux, uy, uz);
   }
-  // bnum >= bden  <=>  t >= 1: destination lies in this tet, no division needed
-  texit = (bnum < bden) ? bnum / bden : __builtin_huge_val();
-  next = nb;
 }
 
 
@@ -206,6 +213,8 @@ struct Ray {
   double tcur;        // parameter of the last crossing (the reference's prev_xpoint)
   double wl;          // weight * |u|  (tally phase)
   int32_t e;          // current tet
+  int32_t entry;      // local face of `e` the ray came in through (-1 at the start of a ray):
+                      // it can never be the exit, so its sector need not be fetched
   int32_t stage;
   int32_t iters;
 };
@@ -220,6 +229,7 @@ PTB_HD void set_ray(Ray &r, double x, double y, double z, double tx, double ty, 
   r.tx = tx; r.ty = ty; r.tz = tz;
   r.tcur = 0.0;
   r.iters = 0;
+  r.entry = -1;
 }
 
 PTB_HD void start_tally(const WalkParams &P, int i, Ray &r, double x, double y, double z,
@@ -308,8 +318,8 @@ PTB_HD void end_ray(const WalkParams &P, int i, Ray &r, bool reached, double tne
 }
 
 // Functor body for one crossing, given the tracer's answer (texit, next).
-PTB_HD void advance(const WalkParams &P, int i, Ray &r, double texit, int32_t next, Counters &c,
-                    bool writer) {
+PTB_HD void advance(const WalkParams &P, int i, Ray &r, double texit, int32_t next, int32_t back,
+                    Counters &c, bool writer) {
   const bool reached = !(texit < 1.0);  // last_exit == -1: destination inside this tet
   const double tnew = reached ? 1.0 : fmax(texit, r.tcur);
   if (r.stage == kStageTally) {  // EvaluateFlux (Impl.cpp:362-379)
@@ -328,6 +338,7 @@ PTB_HD void advance(const WalkParams &P, int i, Ray &r, double texit, int32_t ne
     end_ray(P, i, r, reached, tnew, c, writer);
   } else {
     r.e = next;  // UpdateCurrentElement (Impl.cpp:247-253)
+    r.entry = back;
     r.tcur = tnew;
   }
 }

@@ -55,12 +55,9 @@ __global__ void __launch_bounds__(256) walk_ldg_kernel(const WalkParams P) {
 #pragma unroll
     for (int f = 0; f < 4; ++f)
       load_face_256(rec + 4 * f, raw[4 * f], raw[4 * f + 1], raw[4 * f + 2], raw[4 * f + 3]);
-    TetPlanes t;
-    decode_record(raw, r.e, t);
-    double texit;
-    int32_t next;
-    exit_face(t, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, texit, next);
-    advance(P, i, r, texit, next, c, true);
+    ExitScan sc;
+    scan_record(raw, r.e, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, sc);
+    advance(P, i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
   }
   flush_counters(P, c);
 }
@@ -142,12 +139,9 @@ __global__ void __launch_bounds__(BLOCK) walk_bulk_kernel(const WalkParams P) {
         asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];"
                      : "=d"(raw[2 * j]), "=d"(raw[2 * j + 1])
                      : "r"(row + 16 * j));
-      TetPlanes t;
-      decode_record(raw, r.e, t);
-      double texit;
-      int32_t next;
-      exit_face(t, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, texit, next);
-      advance(P, i, r, texit, next, c, true);
+      ExitScan sc;
+      scan_record(raw, r.e, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, sc);
+      advance(P, i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
     }
   }
   flush_counters(P, c);
@@ -173,23 +167,28 @@ __global__ void __launch_bounds__(256) walk_quad_kernel(const WalkParams P) {
   while (r.stage != kStageDone) {
     double a, b, cc, d;
     load_face_256(P.tets[r.e].d + 4 * f, a, b, cc, d);
-    const uint32_t nbu = pack_low_bytes(dlo(a), dlo(b), dlo(cc), dlo(d)) ^ (uint32_t)r.e;
+    int32_t nbf, bkf;
+    face_payload(a, b, cc, d, r.e, f, nbf, bkf);
     const double nx = a, ny = b, nz = cc, pc = d;
     const double den = nx * r.ux + ny * r.uy + nz * r.uz;
     const double num = pc - (nx * r.ox + ny * r.oy + nz * r.oz);
     const bool out = den > 0.0;
     double tb = out ? num / den : __builtin_huge_val();
-    int32_t nb = out ? (int32_t)nbu : -2;
+    int32_t nb = out ? nbf : -2;
+    int32_t bk = out ? bkf : -1;
 #pragma unroll
     for (int m = 1; m <= 2; m <<= 1) {
       const double to = __shfl_xor_sync(qmask, tb, m);
       const int32_t no = __shfl_xor_sync(qmask, nb, m);
-      // ties go to the lower face index, as in the sequential scan of exit_face()
+      const int32_t bo = __shfl_xor_sync(qmask, bk, m);
+      // ties go to the lower face index, as in the sequential scan
       const bool take = (to < tb) || (to == tb && (lane & m));
       tb = take ? to : tb;
       nb = take ? no : nb;
+      bk = take ? bo : bk;
     }
-    advance(P, i, r, tb, nb, c, writer);
+    if (!(tb < 1.0)) tb = __builtin_huge_val();
+    advance(P, i, r, tb, nb, bk, c, writer);
   }
   flush_counters(P, c);
 }
@@ -486,7 +485,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
       idle = __ballot_sync(0xffffffffu, r.stage == kStageDone);
     }
     if (idle == 0xffffffffu) break;  // no lane active and nothing left to hand out
-    double raw[16];
     if constexpr (kBulkTets) {
       const unsigned act = ~idle;
       if (lane == __ffs(act) - 1) mbar_expect_tx(bar_row, 128u * __popc(act));
@@ -518,24 +516,42 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
       __syncwarp();
     }
     if (r.stage != kStageDone) {
+      ExitScan sc;
       if constexpr (kRows) {
+        double raw[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];"
                        : "=d"(raw[2 * j]), "=d"(raw[2 * j + 1])
                        : "r"(row + 16 * j));
+        scan_record(raw, r.e, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, sc);
       } else {
+        // entry-face elision: after a crossing the face the ray came in through is known
+        // (r.entry) and can never be the exit, so only the other three 32-byte sectors of the
+        // record are fetched; the first tet of a ray needs all four.
         const double *rec = P.tets[r.e].d;
+        const int en = r.entry;
+        double q[3][4], q3[4];
 #pragma unroll
-        for (int f = 0; f < 4; ++f)
-          load_face<FETCH>(rec + 4 * f, keep, raw[4 * f], raw[4 * f + 1], raw[4 * f + 2], raw[4 * f + 3]);
+        for (int k = 0; k < 3; ++k) {
+          const int fk = k + ((en >= 0 && k >= en) ? 1 : 0);
+          load_face<FETCH>(rec + 4 * fk, keep, q[k][0], q[k][1], q[k][2], q[k][3]);
+        }
+        if (en < 0) load_face<FETCH>(rec + 12, keep, q3[0], q3[1], q3[2], q3[3]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int fk = k + ((en >= 0 && k >= en) ? 1 : 0);
+          int32_t nb, bk;
+          face_payload(q[k][0], q[k][1], q[k][2], q[k][3], r.e, fk, nb, bk);
+          scan_face(sc, q[k][0], q[k][1], q[k][2], q[k][3], nb, bk, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
+        }
+        if (en < 0) {
+          int32_t nb, bk;
+          face_payload(q3[0], q3[1], q3[2], q3[3], r.e, 3, nb, bk);
+          scan_face(sc, q3[0], q3[1], q3[2], q3[3], nb, bk, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
+        }
       }
-      TetPlanes t;
-      decode_record(raw, r.e, t);
-      double texit;
-      int32_t next;
-      exit_face(t, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, texit, next);
-      advance(P, my_i, r, texit, next, c, true);
+      advance(P, my_i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
     }
   }
   flush_counters(P, c);

@@ -65,14 +65,18 @@ struct Emul {
       Ray r;
       begin_particle(P, i, r, c, true);
       while (r.stage != kStageDone) {
-        double raw[16];
-        std::memcpy(raw, recs[r.e].d, 128);
-        TetPlanes t;
-        decode_record(raw, r.e, t);
-        double texit;
-        int32_t next;
-        exit_face(t, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, texit, next);
-        advance(P, i, r, texit, next, c, true);
+        // mirror of the persistent kernel's fetch: the entry face's sector is never read
+        const double *rec = recs[r.e].d;
+        const int en = r.entry;
+        ExitScan sc;
+        for (int k = 0; k < (en < 0 ? 4 : 3); ++k) {
+          const int fk = k + ((en >= 0 && k >= en) ? 1 : 0);
+          int32_t nb, bk;
+          face_payload(rec[4 * fk], rec[4 * fk + 1], rec[4 * fk + 2], rec[4 * fk + 3], r.e, fk, nb, bk);
+          scan_face(sc, rec[4 * fk], rec[4 * fk + 1], rec[4 * fk + 2], rec[4 * fk + 3], nb, bk, r.ox, r.oy,
+                    r.oz, r.ux, r.uy, r.uz);
+        }
+        advance(P, i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
       }
       stats.segments += c.segs; stats.tracks += c.tracks;
       stats.relocations += c.relocs; stats.lost += c.lost;

@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--particles", type=int, default=0, help="override particles per GPU (debug only)")
-    ap.add_argument("--variant", type=int, default=env_int("PUMITALLY_VARIANT", 4))
+    ap.add_argument("--variant", type=int, default=env_int("PUMITALLY_VARIANT", 8))
     ap.add_argument("--block", type=int, default=env_int("PUMITALLY_BLOCK", 128))
     ap.add_argument("--cpu-sample", type=int, default=500_000)
     ap.add_argument("--ref-sample", type=int, default=2_000_000, help="particles per step of the --impl reference arm")

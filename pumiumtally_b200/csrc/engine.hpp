@@ -76,7 +76,7 @@ class Engine {
   std::string output_name_ = "fluxresult.vtk";
 
   // options
-  int variant_ = kVariantPersistPolicy;
+  int variant_ = kVariantPersistRefill8;
   int block_ = 128;
   int32_t chunk_ = 1 << 20;  // particles per H2D/compute pipeline stage
   bool use_seed_grid_ = true;

@@ -193,7 +193,10 @@ def run_gpu(args, rank, local_rank, world):
 
     cfg = CONFIGS[args.config]
     cells = cfg["cells"]
-    n = args.particles or cfg["particles"]
+    # per-GPU particle count: the config's total divided by the GPU count it is quoted on
+    n = args.particles or cfg["particles"] // (cfg.get("gpus", 1) if world > 1 else 1)
+    if world == 1 and cfg.get("gpus", 1) > 1 and not args.particles:
+        n = cfg["particles"] // cfg["gpus"] if args.per_gpu_share else cfg["particles"]
     box = tuple(float(c) for c in cells)
     spec = f"box:{cells[0]},{cells[1]},{cells[2]}"
     nsteps = args.warmup + args.steps
@@ -379,7 +382,8 @@ def run_gpu(args, rank, local_rank, world):
                    "relocation_crossings_per_step": (st1["relocations"] - st0["relocations"]) / max(args.steps, 1),
                    "flux_sum": flux_sum},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": recorded_traffic(),
+                     "frac": (achieved / peak) if achieved else None,
+                     "traffic": recorded_traffic() if (args.config == "c2" and not args.particles) else None,
                      "kernel": "walk kernel (variant %d), %d launches, %.3f ms each" % (args.variant, args.steps, kernel_ms / max(args.steps, 1)),
                      "algorithmic_bytes_per_launch": alg_bytes / max(args.steps, 1), "peak_source": peak_src},
         "cpu_baseline": cpu,
@@ -404,6 +408,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=2_000_000, help="particles per step of the --impl reference arm")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--pregen-gb", type=float, default=24.0, help="pre-generate all batches if they fit in this many GiB")
+    ap.add_argument("--per-gpu-share", action="store_true",
+                    help="on one GPU, run only the per-GPU share of a multi-GPU config")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

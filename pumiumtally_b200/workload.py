@@ -189,11 +189,13 @@ class SyntheticWorkload:
         return origin, dest, o.to_int8(fly), weights
 
 
-# BASELINE.json configs -> (box cells nx,ny,nz, particles, mean track length, mu_min)
+# BASELINE.json configs -> box cells (nx,ny,nz), total particles, mean track length, mu_min, and the
+# GPU count the config is quoted on (bench.py gives every GPU particles // gpus of them).
 CONFIGS = {
-    "c1": dict(cells=(6, 6, 5), particles=10_000, mean_length=3.0, mu_min=-1.0),
-    "c2": dict(cells=(55, 55, 55), particles=10_000_000, mean_length=3.0, mu_min=-1.0),
-    "c3": dict(cells=(20, 20, 20), particles=100_000_000, mean_length=3.0, mu_min=-1.0),
-    "c4": dict(cells=(32, 32, 163), particles=1_000_000, mean_length=200.0, mu_min=0.9),
-    "c5": dict(cells=(118, 118, 118), particles=100_000_000, mean_length=3.0, mu_min=-1.0),
+    "c1": dict(cells=(6, 6, 5), particles=10_000, mean_length=3.0, mu_min=-1.0, gpus=1),
+    "c2": dict(cells=(55, 55, 55), particles=10_000_000, mean_length=3.0, mu_min=-1.0, gpus=1),
+    "c3": dict(cells=(20, 20, 20), particles=100_000_000, mean_length=3.0, mu_min=-1.0, gpus=1),
+    # long axial tracks: a 5.7-degree cone and tracks that run to the hull (~3 tets per cell layer)
+    "c4": dict(cells=(32, 32, 163), particles=1_000_000, mean_length=1000.0, mu_min=0.995, gpus=4),
+    "c5": dict(cells=(118, 118, 118), particles=100_000_000, mean_length=3.0, mu_min=-1.0, gpus=8),
 }

@@ -54,7 +54,7 @@ def test_workload_properties():
 
 
 def test_forward_peaked_directions():
-    wl = SyntheticWorkload(box=(32.0, 32.0, 163.0), num_particles=4000, mean_length=200.0, mu_min=0.9)
+    wl = SyntheticWorkload(box=(32.0, 32.0, 163.0), num_particles=4000, mean_length=1000.0, mu_min=0.9)
     wl.initial_positions()
     o, d, f, w = wl.next_step()
     u = (d - o)[f == 1]

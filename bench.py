@@ -203,7 +203,7 @@ def run_gpu(args, rank, local_rank, world):
 
     def new_engine():
         e = PumiTally.from_spec(spec, n, device=local_rank)
-        e.set_option("variant", args.variant)
+        e.set_option("variant", args.variant)  # -1 = the engine's own choice for this mesh
         e.set_option("block", args.block)
         return e
 
@@ -285,6 +285,7 @@ def run_gpu(args, rank, local_rank, world):
     total_segs, total_tracks = float(s_all[0]), float(s_all[1])
     value = total_segs / (ms_max * 1e-3)
     flux_sum = float(eng.flux.sum())
+    variant_used = eng.get_option("variant")
     del eng
 
     # ---------------- end-to-end arm through the host-pointer C ABI: `e2e` ------
@@ -372,7 +373,7 @@ def run_gpu(args, rank, local_rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_description(args.config, cfg, n), "variant": args.variant,
+        "config": {"workload": workload_description(args.config, cfg, n), "variant": variant_used,
                    "block": args.block,
                    "l2": f"inputs larger than L2 ({bytes_per_step / 1e6:.0f} MB of fresh particle data per step)",
                    "timing": "K steps back to back between two CUDA events" if pregen else
@@ -384,7 +385,9 @@ def run_gpu(args, rank, local_rank, world):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None,
                      "traffic": recorded_traffic() if (args.config == "c2" and not args.particles) else None,
-                     "kernel": "walk kernel (variant %d), %d launches, %.3f ms each" % (args.variant, args.steps, kernel_ms / max(args.steps, 1)),
+                     "kernel": "walk kernel (variant %d%s), %d launches, %.3f ms each" % (
+                         variant_used, " incl. binning pass" if variant_used in (15, 16, 17) else "", args.steps,
+                         kernel_ms / max(args.steps, 1)),
                      "algorithmic_bytes_per_launch": alg_bytes / max(args.steps, 1), "peak_source": peak_src},
         "cpu_baseline": cpu,
         "e2e": e2e,
@@ -402,7 +405,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--particles", type=int, default=0, help="override particles per GPU (debug only)")
-    ap.add_argument("--variant", type=int, default=env_int("PUMITALLY_VARIANT", 8))
+    ap.add_argument("--variant", type=int, default=env_int("PUMITALLY_VARIANT", -1))
     ap.add_argument("--block", type=int, default=env_int("PUMITALLY_BLOCK", 128))
     ap.add_argument("--cpu-sample", type=int, default=500_000)
     ap.add_argument("--ref-sample", type=int, default=2_000_000, help="particles per step of the --impl reference arm")

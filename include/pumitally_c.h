@@ -96,8 +96,10 @@ int pumitally_get_stats(pumitally_engine *e, pumitally_stats *out);
 
 /* Per-call output file name for WriteTallyResults (default "fluxresult.vtk"). */
 int pumitally_set_output_name(pumitally_engine *e, const char *filename);
-/* Tuning knobs: name in {"variant","block","sort_every","chunk","aggregate"}. */
+/* Tuning knobs: name in {"variant","block","chunk","seed_grid"}.  variant = -1 lets the engine
+ * choose the walk kernel from the mesh size (the default). */
 int pumitally_set_option(pumitally_engine *e, const char *name, int64_t value);
+int64_t pumitally_get_option(const pumitally_engine *e, const char *name);
 
 /* ---- additive: device-pointer entry points -------------------------------
  * Same semantics as the host versions, but the arrays already live in device

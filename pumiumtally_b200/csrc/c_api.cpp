@@ -158,6 +158,10 @@ int pumitally_set_option(pumitally_engine *e, const char *name, int64_t value) {
   return guarded(e, [&](ptb::Engine &g) { return g.set_option(name ? name : "", value); });
 }
 
+int64_t pumitally_get_option(const pumitally_engine *e, const char *name) {
+  return (e && e->impl && name) ? e->impl->get_option(name) : -1;
+}
+
 int pumitally_copy_initial_position_device(pumitally_engine *e, const double *d_xyz, int32_t size,
                                            void *stream) {
   return guarded(e, [&](ptb::Engine &g) {

@@ -81,6 +81,7 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
                                       mesh_.centroid0[1], mesh_.centroid0[2], compute_), "init particles");
   cuda_or_throw(cudaStreamSynchronize(compute_), "init sync");
   build_seed_grid();
+  variant_ = choose_variant();
   // the packed records are only needed on the device from here on
   std::vector<TetRecord>().swap(mesh_.records);
   printf("[INFO] pumitally-b200: %lld elements, %d particles on CUDA device %d\n",
@@ -385,8 +386,29 @@ int Engine::get_stats(EngineStats *out) {
   return 0;
 }
 
+// The tet table of config c2 (128 MB) still half-fits the L2, and streaming the particles in
+// storage order through the TMA stages is fastest.  Once the table is several times the L2
+// (config c5: 1.26 GB) nearly every record fetch is a random 32-byte DRAM access; processing the
+// particles in spatial order (binning pass + gather staging) then pays for itself twice over
+// (profiles/r01/README.md, section q).
+int Engine::choose_variant() const {
+  int l2 = 0;
+  cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device_);
+  const double table = double(mesh_.ntets) * sizeof(TetRecord);
+  return (l2 > 0 && table > 2.0 * double(l2)) ? kVariantPersistGatherL1 : kVariantPersistRefill8;
+}
+
+int64_t Engine::get_option(const std::string &name) const {
+  if (name == "variant") return variant_;
+  if (name == "block") return block_;
+  if (name == "chunk") return chunk_;
+  if (name == "seed_grid") return use_seed_grid_ ? 1 : 0;
+  return -1;
+}
+
 int Engine::set_option(const std::string &name, int64_t v) {
   if (name == "variant") {
+    if (v == -1) { variant_ = choose_variant(); return 0; }  // automatic
     if (v < 0 || v >= kNumVariants) return 1;
     variant_ = int(v);
   } else if (name == "block") {

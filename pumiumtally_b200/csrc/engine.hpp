@@ -52,6 +52,7 @@ class Engine {
   int synchronize();
   double *flux_device_ptr() { return d_flux_; }
   int set_option(const std::string &name, int64_t value);
+  int64_t get_option(const std::string &name) const;
   void set_output_name(const std::string &s) { output_name_ = s; }
   int write_tally_results();
   int64_t debug_order(int32_t *out, int64_t n);
@@ -76,7 +77,8 @@ class Engine {
   std::string output_name_ = "fluxresult.vtk";
 
   // options
-  int variant_ = kVariantPersistRefill8;
+  int variant_ = kVariantPersistRefill8;  // chosen in the constructor from mesh size vs L2 (choose_variant)
+  int choose_variant() const;
   int block_ = 128;
   int32_t chunk_ = 1 << 20;  // particles per H2D/compute pipeline stage
   bool use_seed_grid_ = true;

@@ -51,6 +51,7 @@ C_API = {
     "pumitally_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "pumitally_set_output_name": (C.c_int, [C.c_void_p, C.c_char_p]),
     "pumitally_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "pumitally_get_option": (C.c_int64, [C.c_void_p, C.c_char_p]),
     "pumitally_copy_initial_position_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pumitally_move_to_next_location_device": (
         C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
@@ -242,6 +243,9 @@ class PumiTally:
     def set_option(self, name: str, value: int):
         if self._L.pumitally_set_option(self._h, name.encode(), int(value)):
             raise ValueError(f"bad option {name}={value}")
+
+    def get_option(self, name: str) -> int:
+        return int(self._L.pumitally_get_option(self._h, name.encode()))
 
     # ---- multi-GPU -------------------------------------------------------------
     @staticmethod

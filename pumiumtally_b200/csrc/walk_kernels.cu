@@ -353,32 +353,36 @@ __device__ __forceinline__ void stage_load_hint(const WalkParams &P, int chunk, 
 // ---- gather mode: the chunk's particles are not contiguous (order[] comes from the binning
 // pass); every lane pulls its particle's fields with 8/4-byte cp.async copies that complete on
 // the stage's mbarrier (cp.async.mbarrier.arrive.noinc: one arrival per lane, barrier count 32)
-__device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+// (the gathered particle data is used once: evict_first keeps it from displacing tet records in L2)
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void *src, uint64_t pol) {
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "l"(pol)
+               : "memory");
 }
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void *src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol)
+               : "memory");
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void stage_gather(const WalkParams &P, int chunk, int total,
-                                             ParticleStage *st, uint32_t bar, int lane) {
-  const int base = chunk * kChunk;
-  const int count = min(kChunk, total - base);
+// `id` = this lane's particle for the chunk (lanes >= count hold garbage and copy nothing)
+__device__ __forceinline__ void stage_gather(const WalkParams &P, int id, int count, ParticleStage *st,
+                                             uint32_t bar, int lane, uint64_t pol) {
   if (lane < count) {
-    const int i = __ldg(P.order + base + lane);
+    const int i = id;
     st->id[lane] = i;
-    cp_async_16(smem_u32(&st->state[lane]), P.state + i);
-    cp_async_16(smem_u32(&st->state[lane]) + 16u, reinterpret_cast<const char *>(P.state + i) + 16);
+    cp_async_16(smem_u32(&st->state[lane]), P.state + i, pol);
+    cp_async_16(smem_u32(&st->state[lane]) + 16u, reinterpret_cast<const char *>(P.state + i) + 16, pol);
     if (P.origin) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) cp_async_8(smem_u32(&st->origin[3 * lane + k]), P.origin + 3 * (size_t)i + k);
+      for (int k = 0; k < 3; ++k)
+        cp_async_8(smem_u32(&st->origin[3 * lane + k]), P.origin + 3 * (size_t)i + k, pol);
     }
     if (P.dest) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) cp_async_8(smem_u32(&st->dest[3 * lane + k]), P.dest + 3 * (size_t)i + k);
-      cp_async_8(smem_u32(&st->w[lane]), P.weights + i);
+      for (int k = 0; k < 3; ++k)
+        cp_async_8(smem_u32(&st->dest[3 * lane + k]), P.dest + 3 * (size_t)i + k, pol);
+      cp_async_8(smem_u32(&st->w[lane]), P.weights + i, pol);
     }
   }
   cp_async_arrive_noinc(bar);
@@ -410,26 +414,46 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
   }
   __syncwarp();
   const uint64_t keep = FETCH != kFetchPlain ? l2_policy_keep() : 0;
-  const uint64_t strm = FETCH != kFetchPlain ? l2_policy_stream() : 0;
+  const uint64_t strm = (FETCH != kFetchPlain || GATHER) ? l2_policy_stream() : 0;
   const int total = GATHER ? (int)__ldg(P.work_count) : P.end - P.begin;
   const int nchunks = (total + kChunk - 1) / kChunk;
-  auto load_stage = [&](int chunk, ParticleStage *st, uint32_t bar) {
-    if constexpr (GATHER) stage_gather(P, chunk, total, st, bar, lane);
-    else if constexpr (FETCH == kFetchPlain) stage_load(P, chunk, st, bar, lane);
-    else stage_load_hint(P, chunk, st, bar, lane, strm);
+  // Gather mode: a ticket is a run of kClaimRun chunks = 64 particles whose ids sit in two
+  // registers per lane.  The *next* ticket is claimed, and its ids requested, one run ahead, so
+  // neither the atomic nor the id loads are ever waited for.
+  static_assert(kClaimRun * kChunk == 64, "two id registers per lane cover one ticket");
+  int run_base = 0, run_next = 0, run_end = 0, ids0 = 0, ids1 = 0;
+  int pend_base = -1, pend0 = 0, pend1 = 0;
+  auto fetch_ticket = [&]() {
+    int c = 0;
+    if (lane == 0) c = (int)atomicAdd(P.work_counter, (unsigned)kClaimRun);
+    pend_base = __shfl_sync(0xffffffffu, c, 0);
+    const long long p0 = (long long)pend_base * kChunk + lane, p1 = p0 + 32;
+    pend0 = p0 < total ? __ldg(P.order + p0) : 0;
+    pend1 = p1 < total ? __ldg(P.order + p1) : 0;
   };
-  int run_next = 0, run_end = 0;  // gather mode: remaining chunks of the current ticket
+  auto load_stage = [&](int chunk, ParticleStage *st, uint32_t bar) {
+    if constexpr (GATHER) {
+      const int k = chunk - run_base;  // chunk's position in the current ticket (warp-uniform)
+      const int id = __shfl_sync(0xffffffffu, (k >> 1) ? ids1 : ids0, ((k & 1) << 4) | (lane & 15));
+      stage_gather(P, id, min(kChunk, total - chunk * kChunk), st, bar, lane, strm);
+    } else if constexpr (FETCH == kFetchPlain) {
+      stage_load(P, chunk, st, bar, lane);
+    } else {
+      stage_load_hint(P, chunk, st, bar, lane, strm);
+    }
+  };
   auto claim = [&]() -> int {
     int c = 0;
     if constexpr (GATHER) {
-      if (run_next < run_end) {
-        c = run_next++;
-      } else {
-        if (lane == 0) c = (int)atomicAdd(P.work_counter, (unsigned)kClaimRun);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        run_next = c + 1;
-        run_end = c + kClaimRun;
+      if (run_next >= run_end) {
+        if (pend_base < 0) fetch_ticket();
+        run_base = run_next = pend_base;
+        run_end = pend_base + kClaimRun;
+        ids0 = pend0;
+        ids1 = pend1;
+        fetch_ticket();
       }
+      c = run_next++;
     } else {
       if (lane == 0) c = (int)atomicAdd(P.work_counter, 1u);
       c = __shfl_sync(0xffffffffu, c, 0);
@@ -655,9 +679,9 @@ cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_
     case kVariantPersistPolicy128Occ8:
       return launch_persist<128, kFetchPolicy128, 8>(p, n, stream);
     case kVariantPersistGather:
-      return launch_persist<128, kFetchPolicy, 7, 1, true>(p, n, stream);
+      return launch_persist<128, kFetchPolicy, 7, 8, true>(p, n, stream);
     case kVariantPersistGatherL1:
-      return launch_persist<128, kFetchPolicyL1, 7, 1, true, 40>(p, n, stream);
+      return launch_persist<128, kFetchPolicyL1, 6, 8, true, 40>(p, n, stream);
     case kVariantPersistGatherPlain:
       return launch_persist<128, kFetchPlain, 7, 1, true, 40>(p, n, stream);
     case kVariantPersistPlainL1:

@@ -8,8 +8,8 @@
 // registers; the only global traffic per crossing is one 128-byte tet record
 // and one fp64 reduction into flux[elem].
 //
-// Three record-fetch strategies are compiled (WalkVariant); all share the same
-// per-ray state machine below so they produce identical results.
+// Several kernel variants are compiled (WalkVariant in walk_kernels.hpp); all share the per-ray
+// state machine of walk_core.cuh and produce identical results.
 #include "walk_kernels.hpp"
 
 #include <algorithm>
@@ -286,9 +286,8 @@ __device__ __forceinline__ void begin_from_stage(const WalkParams &P, const Part
 //      (staging copies, state stores) is evict_first -- keeps the tet table L2-resident
 //   2  as 1, plus the L2::128B prefetch size (first sector miss pulls the whole line)
 //   3  one cp.async.bulk of 128 B per lane into a shared-memory row (policies as 1)
-//   4  cooperative: in four rounds the four lanes of a quad load the four 32-byte sectors of ONE
-//      lane's record with a single instruction (one 4-sector request per line instead of four
-//      1-sector requests), records are transposed through per-warp shared-memory rows
+//   (4 was a cooperative quad-load + shared-memory transpose; measured 4.9 ms vs 3.0 ms on c2,
+//      profiles/r01/README.md section c/d, and removed)
 //   5  as 1 but the tet loads allocate in L1 (worth it once particles are processed in
 //      spatial order and neighbouring lanes/warps revisit the same records)
 enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3, kFetchCoop = 4, kFetchPolicyL1 = 5 };
@@ -397,7 +396,7 @@ template <int BLOCK, int FETCH, int MINB, int REFILL_T, bool GATHER>
 __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkParams P) {
   constexpr int WARPS = BLOCK / 32;
   constexpr bool kBulkTets = FETCH == kFetchBulk;
-  constexpr bool kRows = FETCH == kFetchBulk || FETCH == kFetchCoop;
+  constexpr bool kRows = FETCH == kFetchBulk;
   __shared__ ParticleStage stages[WARPS][2];
   __shared__ __align__(8) unsigned long long bars[WARPS][3];
   __shared__ __align__(128) unsigned char rows[kRows ? WARPS : 1][kRows ? 32 * kRowBytes : 16];
@@ -515,29 +514,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
       if (r.stage != kStageDone) bulk_g2s_hint(row, P.tets + r.e, 128u, bar_row, keep);
       mbar_wait(bar_row, (parity >> 2) & 1u);
       parity ^= 4u;
-    }
-    if constexpr (FETCH == kFetchCoop) {
-      const unsigned act = ~idle;
-      const uint32_t rows0 = row - (uint32_t)lane * kRowBytes;
-      const int sec = lane & 3;
-      double q[4][4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int src = 8 * j + (lane >> 2);
-        const int es = __shfl_sync(0xffffffffu, r.e, src);
-        if ((act >> src) & 1u)
-          load_face<kFetchPolicy>(P.tets[es].d + 4 * sec, keep, q[j][0], q[j][1], q[j][2], q[j][3]);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int src = 8 * j + (lane >> 2);
-        if ((act >> src) & 1u) {
-          const uint32_t dst = rows0 + (uint32_t)src * kRowBytes + 32u * sec;
-          asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(dst), "d"(q[j][0]), "d"(q[j][1]) : "memory");
-          asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(dst + 16u), "d"(q[j][2]), "d"(q[j][3]) : "memory");
-        }
-      }
-      __syncwarp();
     }
     if (r.stage != kStageDone) {
       ExitScan sc;
@@ -684,22 +660,10 @@ cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_
       return launch_persist<128, kFetchPolicyL1, 6, 8, true, 40>(p, n, stream);
     case kVariantPersistGatherPlain:
       return launch_persist<128, kFetchPlain, 7, 1, true, 40>(p, n, stream);
-    case kVariantPersistPlainL1:
-      return launch_persist<128, kFetchPlain, 7, 1, false, 40>(p, n, stream);
-    case kVariantPersistCoop:
-      return launch_persist<128, kFetchCoop, 7>(p, n, stream);
-    case kVariantPersistCoopRefill8:
-      return launch_persist<128, kFetchCoop, 7, 8>(p, n, stream);
     case kVariantPersistBulkOcc7:
       return launch_persist<128, kFetchBulk, 7>(p, n, stream);
-    case kVariantPersistCoopOcc6:
-      return launch_persist<128, kFetchCoop, 6>(p, n, stream);
     case kVariantPersistRefill8:
       return launch_persist<128, kFetchPolicy, 7, 8>(p, n, stream);
-    case kVariantPersistRefill12:
-      return launch_persist<128, kFetchPolicy, 7, 12>(p, n, stream);
-    case kVariantPersistRefill16:
-      return launch_persist<128, kFetchPolicy, 7, 16>(p, n, stream);
     default:
       return cudaErrorInvalidValue;
   }

@@ -8,28 +8,25 @@
 
 namespace ptb {
 
+// Values are stable (profiles/ refer to them); the gaps are experiments that were measured,
+// lost and removed (9/10 other refill thresholds, 11/12/14 cooperative transposed fetch, 18).
 enum WalkVariant : int {
-  kVariantLdg = 0,   // thread per particle, 4 x 256-bit loads of the tet record
-  kVariantBulk = 1,  // thread per particle, record staged in smem by cp.async.bulk + mbarrier
-  kVariantQuad = 2,  // 4 lanes per particle (lane per face), coalesced 32 B loads
-  kVariantPersist = 3,  // persistent warps, TMA-staged particle chunks, per-lane refill
+  kVariantLdg = 0,    // thread per particle, 4 x 256-bit loads of the tet record (first correct path)
+  kVariantBulk = 1,   // thread per particle, record staged in smem by cp.async.bulk + mbarrier
+  kVariantQuad = 2,   // 4 lanes per particle (lane per face), coalesced 32 B loads
+  kVariantPersist = 3,               // persistent warps, TMA-staged particle chunks, per-lane refill
   kVariantPersistPolicy = 4,         // 3 + L2 evict_last on tets / evict_first on the particle stream
   kVariantPersistPolicy128 = 5,      // 4 + L2::128B prefetch size on tet loads
   kVariantPersistBulk = 6,           // 4 with tet records fetched by cp.async.bulk into smem rows
   kVariantPersistPolicy128Occ8 = 7,  // 5 compiled for 8 resident blocks (64 registers)
-  kVariantPersistRefill8 = 8,        // 4, refilling only when >= 8 lanes are idle
-  kVariantPersistRefill12 = 9,
-  kVariantPersistRefill16 = 10,
-  kVariantPersistCoop = 11,          // 4 with cooperative coalesced tet fetch (quad loads + smem transpose)
-  kVariantPersistCoopRefill8 = 12,
+  kVariantPersistRefill8 = 8,        // 4, refilling only when >= 8 lanes are idle (default, mesh <~ 2x L2)
   kVariantPersistBulkOcc7 = 13,      // 6 compiled for 7 resident blocks
-  kVariantPersistCoopOcc6 = 14,      // 11 compiled for 6 resident blocks (no spills)
-  kVariantPersistGather = 15,        // 4 on spatially binned particles (order[] from launch_bin_particles)
-  kVariantPersistGatherL1 = 16,      // 15 with L1-allocating tet loads and a larger L1 carve-out
-  kVariantPersistGatherPlain = 17,   // 15 with plain (L1-allocating, no policy) tet loads
-  kVariantPersistPlainL1 = 18,       // 3 with a 40% shared-memory carve-out (large L1)
-  kNumVariants = 19
+  kVariantPersistGather = 15,        // 8 on spatially binned particles (order[] from launch_bin_particles)
+  kVariantPersistGatherL1 = 16,      // 15 with L1-allocating tet loads (default, mesh >> L2)
+  kVariantPersistGatherPlain = 17,   // 15 with plain tet loads (no L2 policy)
+  kNumVariants = 18
 };
+
 
 cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_t stream);
 cudaError_t launch_bin_particles(const SeedGrid &g, const double *origin, const int8_t *flying,

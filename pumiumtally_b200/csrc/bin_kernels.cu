@@ -1,5 +1,5 @@
-// Per-move spatial binning of the flying particles (counting sort by seed-grid
-// cell of the particle's origin).  Output: order[] = ids of the flying
+// Per-move spatial binning of the flying particles (counting sort by the Morton rank of the
+// seed-grid cell of the particle's origin).  Output: order[] = ids of the flying
 // particles of the range grouped by cell, and the number of them.  The walk
 // kernel then processes particles in that order, so the lanes of a warp, the
 // warps of a block and the blocks in flight at any moment work on neighbouring
@@ -23,7 +23,8 @@ __device__ __forceinline__ int32_t cell_of(const SeedGrid &g, double x, double y
   const int cx = fx > 0.0 ? min((int)fx, g.nx - 1) : 0;
   const int cy = fy > 0.0 ? min((int)fy, g.ny - 1) : 0;
   const int cz = fz > 0.0 ? min((int)fz, g.nz - 1) : 0;
-  return (cz * g.ny + cy) * g.nx + cx;
+  const int32_t c = (cz * g.ny + cy) * g.nx + cx;
+  return g.cell_rank ? __ldg(g.cell_rank + c) : c;  // Morton rank of the cell = the bin
 }
 
 // pass 1: cell of every flying particle of [begin,end) + histogram

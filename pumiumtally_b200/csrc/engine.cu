@@ -101,6 +101,7 @@ Engine::~Engine() {
   cudaFree(d_stats_);
   cudaFree(d_tickets_);
   cudaFree(d_grid_);
+  cudaFree(d_cell_rank_);
   cudaFree(d_pcell_); cudaFree(d_order_); cudaFree(d_cell_count_); cudaFree(d_cell_sums_);
   cudaFree(d_work_count_);
   if (compute_) cudaStreamDestroy(compute_);
@@ -137,6 +138,12 @@ void Engine::build_seed_grid() {
   cuda_or_throw(cudaMemset(d_stats_, 0, sizeof(DeviceStats)), "memset");
   cudaFree(xyz); cudaFree(ts);
   grid_.cell_tet = d_grid_;
+  {
+    const std::vector<int32_t> rank = morton_cell_ranks(grid_);
+    dev_alloc(&d_cell_rank_, size_t(ncell), "cell ranks");
+    cuda_or_throw(cudaMemcpy(d_cell_rank_, rank.data(), size_t(ncell) * sizeof(int32_t), cudaMemcpyHostToDevice), "upload cell ranks");
+    grid_.cell_rank = d_cell_rank_;
+  }
   dev_alloc(&d_cell_count_, size_t(ncell), "cell histogram");
   dev_alloc(&d_cell_sums_, size_t(ncell) / 1024 + 2, "cell block sums");
 }

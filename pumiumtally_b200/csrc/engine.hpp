@@ -94,6 +94,7 @@ class Engine {
   unsigned ticket_next_ = 0;
   SeedGrid grid_{};              // relocation seed grid (grid_.cell_tet lives in d_grid_)
   int32_t *d_grid_ = nullptr;
+  int32_t *d_cell_rank_ = nullptr;
   // spatial binning of the flying particles (gather-mode kernels)
   int32_t *d_pcell_ = nullptr, *d_order_ = nullptr;
   unsigned int *last_work_count_ = nullptr;

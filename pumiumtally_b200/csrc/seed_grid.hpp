@@ -2,6 +2,9 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
+#include <utility>
+#include <vector>
 
 #include "tet_mesh.hpp"
 #include "walk_core.cuh"
@@ -27,6 +30,33 @@ inline SeedGrid choose_seed_grid(const HostMesh &m, double tets_per_cell = 4.0) 
   g.far2 = 4.0 * h * h;  // seed when the target is more than two cells away
   g.cell_tet = nullptr;
   return g;
+}
+
+// Rank of every grid cell along the Morton (Z-order) curve through the cells that exist: the
+// binning pass sorts particles by this rank, so a run of consecutive particles covers a compact
+// 3-D block of the mesh instead of a one-cell-thick slab (smaller L2 working set per window).
+inline std::vector<int32_t> morton_cell_ranks(const SeedGrid &g) {
+  auto spread = [](uint64_t v) {  // 21 bits -> every third bit
+    v &= 0x1fffff;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+  };
+  const int64_t n = int64_t(g.nx) * g.ny * g.nz;
+  std::vector<std::pair<uint64_t, int32_t>> key(static_cast<size_t>(n));
+  for (int cz = 0; cz < g.nz; ++cz)
+    for (int cy = 0; cy < g.ny; ++cy)
+      for (int cx = 0; cx < g.nx; ++cx) {
+        const int32_t c = (cz * g.ny + cy) * g.nx + cx;
+        key[c] = {spread(cx) | spread(cy) << 1 | spread(cz) << 2, c};
+      }
+  std::sort(key.begin(), key.end());
+  std::vector<int32_t> rank(static_cast<size_t>(n));
+  for (int64_t r = 0; r < n; ++r) rank[key[r].second] = int32_t(r);
+  return rank;
 }
 
 }  // namespace ptb

@@ -167,6 +167,7 @@ PTB_HD void store_state(ParticleState *p, double x, double y, double z, int32_t 
 // which also reproduces the clip point of an out-of-mesh target.
 struct SeedGrid {
   const int32_t *cell_tet;  // [nx*ny*nz]; nullptr = grid disabled
+  const int32_t *cell_rank; // [nx*ny*nz] position of the cell along a Morton curve (binning key)
   double x0, y0, z0;        // low corner of the bounding box
   double h, inv_h;          // cell edge and its reciprocal
   double far2;              // seed only when |target - position|^2 exceeds this

@@ -87,8 +87,16 @@ def test_binning_groups_flying_particles_by_cell():
     dims = np.minimum(np.maximum(np.ceil(np.array(cells) / h), 1), 1024).astype(int)
     h = max(h, *(np.array(cells) / dims))
     c = np.minimum((o[order] / h).astype(int), dims - 1)
-    key = (c[:, 2] * dims[1] + c[:, 1]) * dims[0] + c[:, 0]
-    assert (np.diff(key) >= 0).all(), f"{int((np.diff(key) < 0).sum())} order inversions"
+
+    def spread(v):  # Morton bit interleave, as csrc/seed_grid.hpp::morton_cell_ranks
+        v = v.astype(np.uint64) & np.uint64(0x1fffff)
+        for sh, m in ((32, 0x1f00000000ffff), (16, 0x1f0000ff0000ff), (8, 0x100f00f00f00f00f),
+                      (4, 0x10c30c30c30c30c3), (2, 0x1249249249249249)):
+            v = (v | (v << np.uint64(sh))) & np.uint64(m)
+        return v
+
+    key = spread(c[:, 0]) | (spread(c[:, 1]) << np.uint64(1)) | (spread(c[:, 2]) << np.uint64(2))
+    assert (np.diff(key.astype(np.int64)) >= 0).all(), f"{int((np.diff(key.astype(np.int64)) < 0).sum())} order inversions"
 
 
 def test_seed_grid_cuts_relocation_work_not_results():

@@ -205,6 +205,9 @@ def run_gpu(args, rank, local_rank, world):
         e = PumiTally.from_spec(spec, n, device=local_rank)
         e.set_option("variant", args.variant)  # -1 = the engine's own choice for this mesh
         e.set_option("block", args.block)
+        for kv in args.opt:
+            k, v = kv.split("=")
+            e.set_option(k, int(v))
         return e
 
     # identical batches for both arms, generated on the device once
@@ -413,6 +416,7 @@ def main():
     ap.add_argument("--pregen-gb", type=float, default=24.0, help="pre-generate all batches if they fit in this many GiB")
     ap.add_argument("--per-gpu-share", action="store_true",
                     help="on one GPU, run only the per-GPU share of a multi-GPU config")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -202,7 +202,10 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
     // counting sort of the range's flying particles by seed-grid cell of their origin
     unsigned int *wc = d_work_count_ + (ticket_next_ % kTicketRing);
     const double *key = d_origin ? d_origin : d_dest;
-    PTB_CUDA_OK(launch_bin_particles(grid_, key, d_flying, begin, end, d_pcell_, d_cell_count_,
+    SeedGrid bin_grid = grid_;
+    if (!morton_) bin_grid.cell_rank = nullptr;
+    p.claim_run = claim_run_;
+    PTB_CUDA_OK(launch_bin_particles(bin_grid, key, d_flying, begin, end, d_pcell_, d_cell_count_,
                                      d_cell_sums_, d_order_ + begin, wc, stream));
     p.order = d_order_ + begin;
     p.work_count = wc;
@@ -426,6 +429,11 @@ int Engine::set_option(const std::string &name, int64_t v) {
     chunk_ = int32_t(std::min<int64_t>(v, INT_MAX)) & ~1023;  // keeps every range 16-byte aligned
   } else if (name == "seed_grid") {
     use_seed_grid_ = v != 0;
+  } else if (name == "morton") {
+    morton_ = v != 0;
+  } else if (name == "claim_run") {
+    if (v != 1 && v != 2 && v != 4) return 1;
+    claim_run_ = int(v);
   } else {
     return 1;
   }

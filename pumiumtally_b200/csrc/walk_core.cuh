@@ -198,6 +198,7 @@ struct WalkParams {
   unsigned int *work_counter;  // chunk ticket of the persistent kernel (zeroed per launch)
   const int32_t *order;        // gather mode: ids of the flying particles in processing order
   const unsigned int *work_count;  // gather mode: number of entries in order[] (device scalar)
+  int32_t claim_run;           // gather mode: chunks per ticket (1, 2 or 4)
   DeviceStats *stats;
   SeedGrid grid;
 };

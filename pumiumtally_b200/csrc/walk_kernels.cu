@@ -387,7 +387,7 @@ __device__ __forceinline__ void stage_gather(const WalkParams &P, int id, int co
   cp_async_arrive_noinc(bar);
 }
 
-constexpr int kClaimRun = 4;  // gather mode: a warp takes this many consecutive chunks per ticket
+constexpr int kClaimRun = 4;  // gather mode: a warp takes up to this many consecutive chunks per ticket
 
 // REFILL_T: idle lanes are topped up only when at least this many have finished -- the
 // refill code then runs with REFILL_T+ active lanes instead of the ~3 that finish per
@@ -419,16 +419,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
   // Gather mode: a ticket is a run of kClaimRun chunks = 64 particles whose ids sit in two
   // registers per lane.  The *next* ticket is claimed, and its ids requested, one run ahead, so
   // neither the atomic nor the id loads are ever waited for.
-  static_assert(kClaimRun * kChunk == 64, "two id registers per lane cover one ticket");
+  static_assert(kClaimRun * kChunk == 64, "two id registers per lane cover the largest ticket");
+  const int claim_run = GATHER ? min(max(P.claim_run, 1), kClaimRun) : 1;
   int run_base = 0, run_next = 0, run_end = 0, ids0 = 0, ids1 = 0;
   int pend_base = -1, pend0 = 0, pend1 = 0;
   auto fetch_ticket = [&]() {
     int c = 0;
-    if (lane == 0) c = (int)atomicAdd(P.work_counter, (unsigned)kClaimRun);
+    if (lane == 0) c = (int)atomicAdd(P.work_counter, (unsigned)claim_run);
     pend_base = __shfl_sync(0xffffffffu, c, 0);
     const long long p0 = (long long)pend_base * kChunk + lane, p1 = p0 + 32;
-    pend0 = p0 < total ? __ldg(P.order + p0) : 0;
-    pend1 = p1 < total ? __ldg(P.order + p1) : 0;
+    const long long pe = min((long long)total, ((long long)pend_base + claim_run) * kChunk);
+    pend0 = p0 < pe ? __ldg(P.order + p0) : 0;
+    pend1 = p1 < pe ? __ldg(P.order + p1) : 0;
   };
   auto load_stage = [&](int chunk, ParticleStage *st, uint32_t bar) {
     if constexpr (GATHER) {
@@ -447,7 +449,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
       if (run_next >= run_end) {
         if (pend_base < 0) fetch_ticket();
         run_base = run_next = pend_base;
-        run_end = pend_base + kClaimRun;
+        run_end = pend_base + claim_run;
         ids0 = pend0;
         ids1 = pend1;
         fetch_ticket();

@@ -74,6 +74,7 @@ def test_binning_groups_flying_particles_by_cell():
     cells = (12, 10, 8)
     coords, t2v, wl = box_case(cells, 200_000)
     e = gpu_engine(16)(coords, t2v, wl.n)
+    e.set_option("morton", 1)
     e.CopyInitialPosition(wl.initial_positions().reshape(-1))
     o, d, f, w = wl.next_step()
     fly = f == 1

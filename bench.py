@@ -394,7 +394,9 @@ def run_gpu(args, rank, local_rank, world):
                      "algorithmic_bytes_per_launch": alg_bytes / max(args.steps, 1), "peak_source": peak_src},
         "cpu_baseline": cpu,
         "e2e": e2e,
-        "gpu_launches": args.steps,
+        # kernels of this repo inside the timed region: one fused walk kernel per move, plus the five
+        # binning kernels (count, 3-kernel scan, scatter) when the binned variant is in use
+        "gpu_launches": args.steps * (6 if variant_used in (15, 16, 17) else 1),
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -96,8 +96,10 @@ int pumitally_get_stats(pumitally_engine *e, pumitally_stats *out);
 
 /* Per-call output file name for WriteTallyResults (default "fluxresult.vtk"). */
 int pumitally_set_output_name(pumitally_engine *e, const char *filename);
-/* Tuning knobs: name in {"variant","block","chunk","seed_grid"}.  variant = -1 lets the engine
- * choose the walk kernel from the mesh size (the default). */
+/* Options: "variant" (-1 = the engine picks the walk kernel from the mesh size, the default),
+ * "block", "chunk", "seed_grid", "morton", "claim_run", and "register_host" (1 = page-lock the
+ * caller's pageable buffers with cudaHostRegister the first time they are seen; also enabled by
+ * the environment variable PUMITALLY_REGISTER_HOST=1). */
 int pumitally_set_option(pumitally_engine *e, const char *name, int64_t value);
 int64_t pumitally_get_option(const pumitally_engine *e, const char *name);
 

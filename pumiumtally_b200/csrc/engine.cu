@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -82,6 +83,7 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
   cuda_or_throw(cudaStreamSynchronize(compute_), "init sync");
   build_seed_grid();
   variant_ = choose_variant();
+  if (const char *env = std::getenv("PUMITALLY_REGISTER_HOST")) register_host_ = std::atoi(env) != 0;
   // the packed records are only needed on the device from here on
   std::vector<TetRecord>().swap(mesh_.records);
   printf("[INFO] pumitally-b200: %lld elements, %d particles on CUDA device %d\n",
@@ -92,6 +94,7 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
   if (nccl_comm_) nccl_comm_destroy(nccl_comm_);
+  for (auto &r : registered_) cudaHostUnregister(const_cast<void *>(r.first));
   for (auto &t : timers_free_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto &t : timers_busy_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto &e : chunk_events_) cudaEventDestroy(e);
@@ -220,6 +223,21 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   return 0;
 }
 
+// OpenMC hands over ordinary (pageable) std::vector storage and reuses the same buffers for every
+// call.  Pageable cudaMemcpyAsync is staged by the driver at a fraction of the PCIe rate, so with
+// option register_host=1 (or PUMITALLY_REGISTER_HOST=1) each new caller buffer is page-locked once
+// with cudaHostRegister and stays registered until the engine is destroyed.  Off by default: the
+// caller must then keep those buffers alive (or at least not free them) for the engine's lifetime.
+void Engine::maybe_register(const void *p, size_t bytes) {
+  if (!register_host_ || !p || bytes == 0 || host_is_pinned(p)) return;
+  for (auto &r : registered_)
+    if (r.first == p && r.second >= bytes) return;
+  if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess)
+    registered_.emplace_back(p, bytes);
+  else
+    cudaGetLastError();  // overlapping/foreign registration: fall back to the pageable path
+}
+
 bool Engine::host_is_pinned(const void *p) const {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -274,6 +292,10 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
   }
   PTB_CUDA_OK(cudaSetDevice(device_));
   collect_timers(false);
+  maybe_register(origin, size_t(size) * sizeof(double));
+  maybe_register(dest, size_t(size) * sizeof(double));
+  maybe_register(weights, size_t(n_) * sizeof(double));
+  maybe_register(flying, size_t(n_));
   const int nchunks = n_ ? (n_ + chunk_ - 1) / chunk_ : 0;
   while (int(chunk_events_.size()) < nchunks + 2) {
     cudaEvent_t e;
@@ -429,6 +451,8 @@ int Engine::set_option(const std::string &name, int64_t v) {
     chunk_ = int32_t(std::min<int64_t>(v, INT_MAX)) & ~1023;  // keeps every range 16-byte aligned
   } else if (name == "seed_grid") {
     use_seed_grid_ = v != 0;
+  } else if (name == "register_host") {
+    register_host_ = v != 0;
   } else if (name == "morton") {
     morton_ = v != 0;
   } else if (name == "claim_run") {

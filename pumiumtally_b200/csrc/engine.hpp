@@ -6,6 +6,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -66,6 +67,7 @@ class Engine {
                    const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream,
                    bool timed);
   bool host_is_pinned(const void *p) const;
+  void maybe_register(const void *p, size_t bytes);
   void collect_timers(bool wait);
   void build_seed_grid();
 
@@ -106,6 +108,9 @@ class Engine {
   struct TimerPair { cudaEvent_t a, b; };
   std::vector<TimerPair> timers_free_, timers_busy_;
   std::vector<cudaEvent_t> chunk_events_;
+  // caller buffers pinned with cudaHostRegister (option "register_host"): base -> bytes
+  std::vector<std::pair<const void *, size_t>> registered_;
+  bool register_host_ = false;
   double kernel_ms_ = 0.0, h2d_bytes_ = 0.0;
 
   // NCCL (resolved with dlopen at comm_init time)

@@ -168,6 +168,29 @@ def test_chunked_upload_pipeline_equals_single_range():
     run_workload(a, orc, wl, steps=3, label="chunked")
 
 
+def test_pageable_buffers_with_host_registration():
+    """register_host=1: the caller's pageable numpy buffers are page-locked once and reused."""
+    coords, t2v, wl = box_case((6, 6, 5), 60_000)
+    eng = gpu_engine(8)(coords, t2v, wl.n)
+    eng.set_option("register_host", 1)
+    orc = OraclePumiTally(coords, t2v, wl.n)
+    init = wl.initial_positions()
+    eng.CopyInitialPosition(init.reshape(-1).copy())
+    orc.CopyInitialPosition(init.reshape(-1).copy())
+    # the same four buffers are reused for every move, as OpenMC does
+    O, D, W = np.empty(3 * wl.n), np.empty(3 * wl.n), np.empty(wl.n)
+    F = np.empty(wl.n, dtype=np.int8)
+    for _ in range(3):
+        o, d, f, w = wl.next_step()
+        O[:], D[:], W[:], F[:] = o.reshape(-1), d.reshape(-1), w, f
+        f2 = f.copy()
+        eng.MoveToNextLocation(O, D, F, W)
+        orc.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f2, w)
+        assert not F.any()
+    assert_flux_close(eng.flux, orc.flux, "registered host buffers")
+    np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+
+
 def test_error_behaviour():
     coords, t2v = kuhn_box(1, 1, 1)
     e = PumiTally.from_arrays(coords, t2v, 5)

@@ -114,7 +114,8 @@ int pumitally_copy_initial_position_device(pumitally_engine *e, const double *d_
 int pumitally_move_to_next_location_device(pumitally_engine *e, const double *d_origin,
                                            const double *d_destinations, const int8_t *d_flying,
                                            const double *d_weights, int32_t size, void *stream);
-/* device address of the raw flux array (double[num_elements]) */
+/* device address of the raw flux array (double[num_elements]); NOTE: in the engine's internal
+ * (spatially sorted) element order -- use pumitally_get_flux for the caller's numbering */
 double *pumitally_flux_device_ptr(pumitally_engine *e);
 int pumitally_synchronize(pumitally_engine *e);
 

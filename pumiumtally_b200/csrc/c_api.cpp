@@ -126,7 +126,8 @@ int pumitally_get_positions(pumitally_engine *e, double *out, int64_t n3) {
 }
 int pumitally_get_adjacency(const pumitally_engine *e, int32_t *out, int64_t n4) {
   if (!e || !e->impl || n4 != 4 * e->impl->num_elements()) return 1;
-  std::memcpy(out, e->impl->mesh().t2t.data(), size_t(n4) * sizeof(int32_t));
+  const std::vector<int32_t> adj = e->impl->mesh().adjacency_original();
+  std::memcpy(out, adj.data(), size_t(n4) * sizeof(int32_t));
   return 0;
 }
 int pumitally_reset_tally(pumitally_engine *e) {

@@ -78,8 +78,8 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
   cuda_or_throw(cudaMemset(d_flux_, 0, E * sizeof(double)), "memset");
   cuda_or_throw(cudaMemset(d_stats_, 0, sizeof(DeviceStats)), "memset");
   // InitializeParticlesInElement0 (PumiTallyImpl.cpp:492-528)
-  cuda_or_throw(launch_init_particles(d_state_, n_, mesh_.centroid0[0],
-                                      mesh_.centroid0[1], mesh_.centroid0[2], compute_), "init particles");
+  cuda_or_throw(launch_init_particles(d_state_, n_, mesh_.centroid0[0], mesh_.centroid0[1],
+                                      mesh_.centroid0[2], mesh_.start_elem, compute_), "init particles");
   cuda_or_throw(cudaStreamSynchronize(compute_), "init sync");
   build_seed_grid();
   variant_ = choose_variant();
@@ -123,7 +123,7 @@ void Engine::build_seed_grid() {
   dev_alloc(&ts, size_t(ncell), "seed tmp");
   cuda_or_throw(launch_seed_points(grid_, xyz, compute_), "seed points");
   cuda_or_throw(launch_init_particles(ts, ncell, mesh_.centroid0[0], mesh_.centroid0[1],
-                                      mesh_.centroid0[2], compute_), "seed init");
+                                      mesh_.centroid0[2], mesh_.start_elem, compute_), "seed init");
   WalkParams p{};
   p.tets = d_tets_;
   p.flux = d_flux_;
@@ -351,7 +351,9 @@ int Engine::synchronize() {
 int Engine::get_flux(double *out, int64_t n) {
   if (n != mesh_.ntets) return 1;
   if (synchronize()) return 1;
-  PTB_CUDA_OK(cudaMemcpy(out, d_flux_, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<double> tmp(static_cast<size_t>(n));
+  PTB_CUDA_OK(cudaMemcpy(tmp.data(), d_flux_, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < n; ++i) out[mesh_.orig_of_internal[i]] = tmp[i];  // caller's numbering
   return 0;
 }
 
@@ -362,9 +364,12 @@ int Engine::get_normalized_flux(double *out_flux, double *out_volume, int64_t n)
   if (out_flux) {
     PTB_CUDA_OK(launch_normalize(d_flux_, d_volume_, d_scratch_, n, compute_));
     PTB_CUDA_OK(cudaStreamSynchronize(compute_));
-    PTB_CUDA_OK(cudaMemcpy(out_flux, d_scratch_, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<double> tmp(static_cast<size_t>(n));
+    PTB_CUDA_OK(cudaMemcpy(tmp.data(), d_scratch_, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < n; ++i) out_flux[mesh_.orig_of_internal[i]] = tmp[i];
   }
-  if (out_volume) std::memcpy(out_volume, mesh_.volume.data(), size_t(n) * sizeof(double));
+  if (out_volume)
+    for (int64_t i = 0; i < n; ++i) out_volume[mesh_.orig_of_internal[i]] = mesh_.volume[i];
   return 0;
 }
 
@@ -373,7 +378,7 @@ int Engine::get_element_ids(int32_t *out, int64_t n) {
   if (synchronize()) return 1;
   std::vector<ParticleState> tmp(static_cast<size_t>(n_));
   PTB_CUDA_OK(cudaMemcpy(tmp.data(), d_state_, size_t(n_) * sizeof(ParticleState), cudaMemcpyDeviceToHost));
-  for (int64_t i = 0; i < n_; ++i) out[i] = tmp[i].elem;
+  for (int64_t i = 0; i < n_; ++i) out[i] = mesh_.orig_of_internal[tmp[i].elem];  // caller's numbering
   return 0;
 }
 
@@ -475,10 +480,10 @@ int64_t Engine::debug_order(int32_t *out, int64_t n) {
 
 // FinalizeTallies (PumiTallyImpl.cpp:411-416)
 int Engine::write_tally_results() {
-  std::vector<double> nf(size_t(mesh_.ntets));
-  if (get_normalized_flux(nf.data(), nullptr, mesh_.ntets)) return 1;
+  std::vector<double> nf(static_cast<size_t>(mesh_.ntets)), vol(static_cast<size_t>(mesh_.ntets));
+  if (get_normalized_flux(nf.data(), vol.data(), mesh_.ntets)) return 1;  // caller's element order
   std::string err;
-  if (!write_vtk_dataset(output_name_, mesh_, nf, mesh_.volume, rank_, nranks_, &err)) {
+  if (!write_vtk_dataset(output_name_, mesh_, nf, vol, rank_, nranks_, &err)) {
     fprintf(stderr, "[pumitally] ERROR: %s\n", err.c_str());
     return 1;
   }

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <utility>
 #include <sys/stat.h>
 
 namespace ptb {
@@ -156,6 +157,39 @@ bool HostMesh::finalize(std::string *err) {
     double s = 0;
     for (int i = 0; i < 4; ++i) s += coords[3 * size_t(t2v[i]) + d];
     centroid0[d] = s / 4.0;
+  }
+
+  // ---- internal element order: z-major background-grid cell of the centroid ----------------
+  {
+    const double lx = bbox_hi[0] - bbox_lo[0], ly = bbox_hi[1] - bbox_lo[1], lz = bbox_hi[2] - bbox_lo[2];
+    const double cells = std::min(std::max(double(ntets) / 4.0, 1.0), double(1 << 24));
+    const double h = std::cbrt(std::max(lx * ly * lz, 1e-300) / cells);
+    auto dim = [&](double l) { return int64_t(std::min(std::max(std::ceil(l / h), 1.0), 1024.0)); };
+    const int64_t gx = dim(lx), gy = dim(ly), gz = dim(lz);
+    std::vector<std::pair<int64_t, int32_t>> key(static_cast<size_t>(ntets));
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < ntets; ++e) {
+      double c[3] = {0, 0, 0};
+      for (int i = 0; i < 4; ++i)
+        for (int d = 0; d < 3; ++d) c[d] += 0.25 * coords[3 * size_t(t2v[4 * e + i]) + d];
+      auto cell = [&](double x, double lo, int64_t n) {
+        return std::min<int64_t>(std::max<int64_t>(int64_t((x - lo) / h), 0), n - 1);
+      };
+      const int64_t k = (cell(c[2], bbox_lo[2], gz) * gy + cell(c[1], bbox_lo[1], gy)) * gx + cell(c[0], bbox_lo[0], gx);
+      key[e] = {k, int32_t(e)};
+    }
+    std::sort(key.begin(), key.end());  // ties keep the caller's relative order (second = id)
+    orig_of_internal.resize(ntets);
+    internal_of_orig.resize(ntets);
+    std::vector<int32_t> t2v_new(t2v.size());
+    for (int64_t i = 0; i < ntets; ++i) {
+      const int32_t o = key[i].second;
+      orig_of_internal[i] = o;
+      internal_of_orig[o] = int32_t(i);
+      for (int q = 0; q < 4; ++q) t2v_new[4 * i + q] = t2v[4 * size_t(o) + q];
+    }
+    t2v.swap(t2v_new);
+    start_elem = internal_of_orig[0];
   }
 
   // ---- face adjacency: sort the 4E (sorted vertex triple, slot) keys --------

@@ -39,7 +39,33 @@ struct HostMesh {
   std::vector<int32_t> t2t;      // [4*ntets], neighbour across face opposite vertex f, -1 hull
   std::vector<double> volume;    // [ntets]
   std::vector<TetRecord> records;  // [ntets]
-  double centroid0[3] = {0, 0, 0};  // centroid of element 0 (PumiTallyImpl.cpp:500-509)
+  double centroid0[3] = {0, 0, 0};  // centroid of (the caller's) element 0 (PumiTallyImpl.cpp:500-509)
+
+  // INTERNAL ELEMENT ORDER.  finalize() renumbers the tets by the z-major index of the
+  // background-grid cell that holds their centroid, so that tets that are close in space are
+  // close in memory whatever numbering the mesh file came with (the spatially binned walk streams
+  // through the mesh slab by slab).  t2v, t2t, volume and records are stored in this internal
+  // order; everything that leaves the library (flux, element ids, adjacency, VTK) is translated
+  // back to the caller's numbering with these two maps.
+  std::vector<int32_t> orig_of_internal, internal_of_orig;
+  int32_t start_elem = 0;  // internal id of the caller's element 0 (where particles are parked)
+
+  template <typename T>
+  std::vector<T> to_original(const T *internal, int ncomp = 1) const {
+    std::vector<T> out(size_t(ntets) * ncomp);
+    for (int64_t i = 0; i < ntets; ++i)
+      for (int c = 0; c < ncomp; ++c) out[size_t(orig_of_internal[i]) * ncomp + c] = internal[size_t(i) * ncomp + c];
+    return out;
+  }
+  std::vector<int32_t> adjacency_original() const {
+    std::vector<int32_t> out(size_t(4) * ntets);
+    for (int64_t i = 0; i < ntets; ++i)
+      for (int f = 0; f < 4; ++f) {
+        const int32_t nb = t2t[4 * i + f];
+        out[size_t(4) * orig_of_internal[i] + f] = nb < 0 ? -1 : orig_of_internal[nb];
+      }
+    return out;
+  }
   double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};
 
   // "box:nx,ny,nz[,lx,ly,lz]" | raw mesh file | Gmsh .msh (ASCII 2.2 / 4.1) | Omega_h .osh directory.

@@ -30,7 +30,9 @@ bool write_vtk_dataset(const std::string &path, const HostMesh &m, const std::ve
   std::vector<int32_t> offsets(E);
   for (uint64_t e = 0; e < E; ++e) offsets[e] = int32_t(4 * (e + 1));
   std::vector<uint8_t> types(E, 10);  // VTK_TETRA
-  const Block blocks[6] = {{m.coords.data(), V * 24}, {m.t2v.data(), E * 16},
+  // connectivity in the caller's element order (the cell data arrays already are)
+  const std::vector<int32_t> conn = m.to_original(m.t2v.data(), 4);
+  const Block blocks[6] = {{m.coords.data(), V * 24}, {conn.data(), E * 16},
                            {offsets.data(), E * 4},   {types.data(), E},
                            {flux.data(), E * 8},      {volume.data(), E * 8}};
   uint64_t off[6], acc = 0;

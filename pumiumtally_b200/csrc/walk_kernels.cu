@@ -586,9 +586,10 @@ cudaError_t launch_persist(const WalkParams &p, long long n, cudaStream_t stream
 
 // K14-K16 of SURVEY.md 2b (PumiTallyImpl.cpp:492-528): every particle starts
 // at the centroid of element 0.
-__global__ void init_particles_kernel(ParticleState *state, int32_t n, double cx, double cy, double cz) {
+__global__ void init_particles_kernel(ParticleState *state, int32_t n, double cx, double cy, double cz,
+                                      int32_t elem) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) store_state(state + i, cx, cy, cz, 0);
+  if (i < n) store_state(state + i, cx, cy, cz, elem);
 }
 
 // Seed grid construction: the seed points are written as "particles to
@@ -673,9 +674,9 @@ cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_
 }
 
 cudaError_t launch_init_particles(ParticleState *state, int32_t n, double cx, double cy, double cz,
-                                  cudaStream_t stream) {
+                                  int32_t elem, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  init_particles_kernel<<<(n + 255) / 256, 256, 0, stream>>>(state, n, cx, cy, cz);
+  init_particles_kernel<<<(n + 255) / 256, 256, 0, stream>>>(state, n, cx, cy, cz, elem);
   return cudaGetLastError();
 }
 

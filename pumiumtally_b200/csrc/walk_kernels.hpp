@@ -37,7 +37,7 @@ cudaError_t launch_seed_points(const SeedGrid &g, double *xyz, cudaStream_t stre
 cudaError_t launch_seed_finalize(const double *xyz, const ParticleState *state, int32_t *cell_tet,
                                  int32_t ncell, cudaStream_t stream);
 cudaError_t launch_init_particles(ParticleState *state, int32_t n, double cx, double cy, double cz,
-                                  cudaStream_t stream);
+                                  int32_t elem, cudaStream_t stream);
 cudaError_t launch_normalize(const double *flux, const double *volume, double *out, int64_t n,
                              cudaStream_t stream);
 

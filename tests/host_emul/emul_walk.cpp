@@ -32,7 +32,7 @@ struct Emul {
     grid = choose_seed_grid(mesh);
     const int nc = grid.nx * grid.ny * grid.nz;
     std::vector<double> xyz(3 * size_t(nc));
-    std::vector<ParticleState> ts(nc, ParticleState{mesh.centroid0[0], mesh.centroid0[1], mesh.centroid0[2], 0, 0});
+    std::vector<ParticleState> ts(nc, ParticleState{mesh.centroid0[0], mesh.centroid0[1], mesh.centroid0[2], mesh.start_elem, 0});
     for (int i = 0; i < nc; ++i)
       seed_point(grid, i % grid.nx, (i / grid.nx) % grid.ny, i / (grid.nx * grid.ny), xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
     DeviceStats scratch{};
@@ -93,7 +93,7 @@ void *ptb_emul_create(const double *coords, int64_t nverts, const int32_t *t2v, 
   e->recs = e->mesh.records;
   e->n = n;
   e->flux.assign(size_t(ntets), 0.0);
-  e->state.assign(size_t(n), ParticleState{e->mesh.centroid0[0], e->mesh.centroid0[1], e->mesh.centroid0[2], 0, 0});
+  e->state.assign(size_t(n), ParticleState{e->mesh.centroid0[0], e->mesh.centroid0[1], e->mesh.centroid0[2], e->mesh.start_elem, 0});
   return e;
 }
 void *ptb_emul_create_spec(const char *spec, int n) {
@@ -103,7 +103,7 @@ void *ptb_emul_create_spec(const char *spec, int n) {
   e->recs = e->mesh.records;
   e->n = n;
   e->flux.assign(size_t(e->mesh.ntets), 0.0);
-  e->state.assign(size_t(n), ParticleState{e->mesh.centroid0[0], e->mesh.centroid0[1], e->mesh.centroid0[2], 0, 0});
+  e->state.assign(size_t(n), ParticleState{e->mesh.centroid0[0], e->mesh.centroid0[1], e->mesh.centroid0[2], e->mesh.start_elem, 0});
   return e;
 }
 int ptb_emul_build_grid(void *h) {
@@ -124,8 +124,10 @@ void ptb_emul_sizes(void *h, int64_t *out) {
 void ptb_emul_mesh(void *h, double *coords, int32_t *t2v, double *vol) {
   auto *e = static_cast<Emul *>(h);
   std::memcpy(coords, e->mesh.coords.data(), e->mesh.coords.size() * 8);
-  std::memcpy(t2v, e->mesh.t2v.data(), e->mesh.t2v.size() * 4);
-  std::memcpy(vol, e->mesh.volume.data(), e->mesh.volume.size() * 8);
+  const auto t2v_o = e->mesh.to_original(e->mesh.t2v.data(), 4);
+  const auto vol_o = e->mesh.to_original(e->mesh.volume.data());
+  std::memcpy(t2v, t2v_o.data(), t2v_o.size() * 4);
+  std::memcpy(vol, vol_o.data(), vol_o.size() * 8);
 }
 void ptb_emul_destroy(void *h) { delete static_cast<Emul *>(h); }
 void ptb_emul_localize(void *h, const double *xyz) { static_cast<Emul *>(h)->run(xyz, nullptr, nullptr, nullptr); }
@@ -136,12 +138,18 @@ void ptb_emul_move(void *h, const double *origin, const double *dest, int8_t *fl
 }
 void ptb_emul_get(void *h, double *flux, int32_t *elem, double *pos, unsigned long long *stats, int32_t *adj) {
   auto *e = static_cast<Emul *>(h);
-  if (flux) std::memcpy(flux, e->flux.data(), e->flux.size() * 8);
+  if (flux) {
+    const auto f = e->mesh.to_original(e->flux.data());
+    std::memcpy(flux, f.data(), f.size() * 8);
+  }
   if (elem)
-    for (int i = 0; i < e->n; ++i) elem[i] = e->state[i].elem;
+    for (int i = 0; i < e->n; ++i) elem[i] = e->mesh.orig_of_internal[e->state[i].elem];
   if (pos)
     for (int i = 0; i < e->n; ++i) { pos[3 * i] = e->state[i].x; pos[3 * i + 1] = e->state[i].y; pos[3 * i + 2] = e->state[i].z; }
   if (stats) { stats[0] = e->stats.segments; stats[1] = e->stats.tracks; stats[2] = e->stats.relocations; stats[3] = e->stats.lost; }
-  if (adj) std::memcpy(adj, e->mesh.t2t.data(), e->mesh.t2t.size() * 4);
+  if (adj) {
+    const auto a = e->mesh.adjacency_original();
+    std::memcpy(adj, a.data(), a.size() * 4);
+  }
 }
 }

@@ -161,11 +161,14 @@ def test_contention_many_particles_few_tets():
     run_workload(eng, orc, wl, steps=2, check_each_step=False, label="c3-mini")
 
 
-def test_chunked_upload_pipeline_equals_single_range():
+@pytest.mark.parametrize("variant", [0, 8, 16])
+def test_chunked_upload_pipeline_equals_single_range(variant):
+    """Host-pointer path cut into many upload/compute ranges (the binned variant bins each range)."""
     coords, t2v, wl = box_case((6, 6, 5), 50_000)
-    a = gpu_engine(0, chunk=4096)(coords, t2v, wl.n)
+    a = gpu_engine(variant, chunk=4096)(coords, t2v, wl.n)
     orc = OraclePumiTally(coords, t2v, wl.n)
     run_workload(a, orc, wl, steps=3, label="chunked")
+    assert a.stats()["segments"] == orc.n_segments
 
 
 def test_pageable_buffers_with_host_registration():

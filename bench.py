@@ -412,9 +412,9 @@ def main():
     ap.add_argument("--particles", type=int, default=0, help="override particles per GPU (debug only)")
     ap.add_argument("--variant", type=int, default=env_int("PUMITALLY_VARIANT", -1))
     ap.add_argument("--block", type=int, default=env_int("PUMITALLY_BLOCK", 128))
-    ap.add_argument("--cpu-sample", type=int, default=500_000)
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--ref-sample", type=int, default=2_000_000, help="particles per step of the --impl reference arm")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=5)
     ap.add_argument("--pregen-gb", type=float, default=24.0, help="pre-generate all batches if they fit in this many GiB")
     ap.add_argument("--per-gpu-share", action="store_true",
                     help="on one GPU, run only the per-GPU share of a multi-GPU config")

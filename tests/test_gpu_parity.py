@@ -14,7 +14,7 @@ from oracle.oracle import OraclePumiTally
 from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, save_raw_mesh, tet_volumes
 from pumiumtally_b200.tally import PumiTally
 from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
-from test_oracle_golden import golden_scenario
+from test_oracle_golden import check_c1_fixture, golden_scenario
 
 pytestmark = pytest.mark.gpu
 VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 13, 15, 16, 17]
@@ -38,6 +38,14 @@ def test_reference_known_answers(variant):
     eng = golden_scenario(gpu_engine(variant))
     st = eng.stats()
     assert st["segments"] == 18 and st["tracks"] == 7 and st["lost"] == 0 and st["moves"] == 2
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_committed_c1_fixture(variant):
+    """CUDA path vs the committed oracle fixture tests/golden/c1_oracle.npz (BASELINE configs[0])."""
+    eng, segs, tracks = check_c1_fixture(gpu_engine(variant))
+    st = eng.stats()
+    assert st["segments"] == segs and st["tracks"] == tracks and st["lost"] == 0
 
 
 @pytest.mark.parametrize("variant", VARIANTS)

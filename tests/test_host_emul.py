@@ -10,7 +10,7 @@ from helpers import HostEmulTally, assert_flux_close, box_case, edge_case_scenar
 from oracle.oracle import OraclePumiTally
 from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, tet_volumes
 from pumiumtally_b200.workload import SyntheticWorkload
-from test_oracle_golden import golden_scenario
+from test_oracle_golden import check_c1_fixture, golden_scenario
 
 SEED = [False, True]
 
@@ -20,6 +20,12 @@ def test_reference_known_answers_device_logic(seed):
     eng = golden_scenario(lambda c, t, n: HostEmulTally(c, t, n, seed_grid=seed))
     st = eng.stats()
     assert st["lost"] == 0 and st["tracks"] == 7 and st["segments"] == 18
+
+
+@pytest.mark.parametrize("seed", SEED)
+def test_device_logic_matches_committed_c1_fixture(seed):
+    eng, segs, tracks = check_c1_fixture(lambda c, t, n: HostEmulTally(c, t, n, seed_grid=seed))
+    assert eng.stats()["segments"] == segs and eng.stats()["tracks"] == tracks
 
 
 def test_box_spec_matches_numpy_generator():

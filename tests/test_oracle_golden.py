@@ -9,12 +9,37 @@ from oracle.oracle import OraclePumiTally, bruteforce_tally
 from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, tet_volumes
 from pumiumtally_b200.workload import SyntheticWorkload
 
+import json
+import os
+
 TOL = 1e-8  # the reference test's is_close tolerance (test line 21-23)
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+T1 = json.load(open(os.path.join(GOLDEN_DIR, "t1_known_answers.json")))
 
 # golden numbers; see SURVEY.md section 4 item 3 for why move 2 starts at (1.0,0.4,0.5)
-SEG_ELEM4 = 0.87904907299
-SEG_ELEM3 = 0.08790490730
-SEG_P2_ELEM4 = 0.55226805086
+SEG_ELEM4 = T1["move2"]["segment_p0_elem4"]
+SEG_ELEM3 = T1["move2"]["segment_p0_elem3"]
+SEG_P2_ELEM4 = T1["move2"]["segment_p2_elem4"]
+
+
+def check_c1_fixture(make_engine):
+    """Run config c1 exactly as tests/golden/make_golden.py did and compare with the committed
+    oracle output (flux 1e-6 relative, parent elements exact, segment counts equal)."""
+    from golden.make_golden import c1_case
+    from helpers import assert_flux_close
+
+    g = np.load(os.path.join(GOLDEN_DIR, "c1_oracle.npz"))
+    coords, t2v, n, wl, steps = c1_case(int(g["steps"]))
+    eng = make_engine(coords, t2v, n)
+    eng.CopyInitialPosition(wl.initial_positions().reshape(-1))
+    np.testing.assert_array_equal(eng.elem_ids, g["elem_after_init"])
+    for _ in range(steps):
+        o, d, f, w = wl.next_step()
+        eng.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
+    assert_flux_close(eng.flux, g["flux"], "c1 fixture")
+    np.testing.assert_array_equal(eng.elem_ids, g["elem_final"])
+    np.testing.assert_allclose(eng.positions, g["positions_final"], rtol=0, atol=1e-9)
+    return eng, int(g["n_segments"]), int(g["n_tracks"])
 
 
 def golden_scenario(make_engine):
@@ -24,10 +49,11 @@ def golden_scenario(make_engine):
     eng = make_engine(coords, t2v, n)
     assert len(t2v) == 6  # test line 69
     # centroid of element 0 (test line 83)
-    np.testing.assert_allclose(coords[t2v[0]].mean(0), [0.5, 0.75, 0.25], atol=TOL)
-    init = np.tile([0.1, 0.4, 0.5], n)
+    np.testing.assert_allclose(coords[t2v[0]].mean(0), T1["centroid_element0"], atol=TOL)
+    assert T1["mesh"]["num_elements"] == len(t2v) and T1["num_particles"] == n
+    init = np.tile(T1["init_position"], n)
     eng.CopyInitialPosition(init.copy(), 3 * n)
-    assert (eng.elem_ids == 2).all()  # test lines 152-159
+    assert (eng.elem_ids == T1["element_after_localisation"]).all()  # test lines 152-159
     assert np.abs(eng.flux).max() < TOL  # test lines 161-169
     # move 1: (0.1,0.4,0.5) -> (1.2,0.4,0.5), w = 1, all flying
     dest = np.tile([1.2, 0.4, 0.5], n)
@@ -36,7 +62,7 @@ def golden_scenario(make_engine):
     assert not flying.any()  # test line 210
     assert (eng.elem_ids == 4).all()  # test lines 221-228
     np.testing.assert_allclose(eng.positions, np.tile([1.0, 0.4, 0.5], (n, 1)), atol=TOL)  # lines 243-251
-    np.testing.assert_allclose(eng.flux, [0, 0, 0.3 * n, 0.1 * n, 0.5 * n, 0], atol=TOL)  # lines 267-282
+    np.testing.assert_allclose(eng.flux, T1["move1"]["flux_after"], atol=TOL)  # lines 267-282
     # move 2: particles 0 and 2 fly on from their true current position
     cur = np.tile([1.0, 0.4, 0.5], n)
     nxt = cur.reshape(n, 3).copy()
@@ -45,7 +71,7 @@ def golden_scenario(make_engine):
     flying = np.array([1, 0, 1, 0, 0], dtype=np.int8)
     w = np.array([2.0, 1.0, 0.5, 1.0, 1.0])
     eng.MoveToNextLocation(cur, nxt.reshape(-1), flying, w, 3 * n)
-    np.testing.assert_array_equal(eng.elem_ids, [3, 4, 4, 4, 4])  # lines 354-358
+    np.testing.assert_array_equal(eng.elem_ids, T1["move2"]["elements_after"])  # lines 354-358
     np.testing.assert_allclose(eng.positions, nxt, atol=TOL)  # lines 323-346
     f = eng.flux
     assert abs(f[3] - (0.1 * n + SEG_ELEM3 * 2.0)) < TOL  # lines 372-373
@@ -57,6 +83,12 @@ def golden_scenario(make_engine):
 @pytest.mark.parametrize("per_particle", [False, True])
 def test_reference_known_answers(per_particle):
     golden_scenario(lambda c, t, n: OraclePumiTally(c, t, n, per_particle=per_particle))
+
+
+@pytest.mark.parametrize("per_particle", [False, True])
+def test_oracle_reproduces_committed_c1_fixture(per_particle):
+    eng, segs, tracks = check_c1_fixture(lambda c, t, n: OraclePumiTally(c, t, n, per_particle=per_particle))
+    assert eng.n_segments == segs and eng.n_tracks == tracks
 
 
 def test_relocation_is_not_tallied_and_documented_semantics():

@@ -72,7 +72,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             subprocess.check_call(cmd)
             relink = True
     if relink:
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fopenmp", "-lgomp", "-ldl",
+        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fopenmp", "-lgomp", "-ldl", "-lz",
                "-gencode", "arch=compute_100a,code=sm_100a"]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)

@@ -122,7 +122,8 @@ bool HostMesh::load(const std::string &spec, std::string *err) {
     struct stat st;
     if (stat(spec.c_str(), &st) != 0) { *err = "mesh not found: " + spec; return false; }
     const bool is_msh = spec.size() > 4 && spec.compare(spec.size() - 4, 4, ".msh") == 0;
-    bool ok = S_ISDIR(st.st_mode) ? read_osh_mesh(spec, &coords, &t2v, err)
+    const bool is_osh = spec.size() > 4 && spec.compare(spec.size() - 4, 4, ".osh") == 0;
+    bool ok = (S_ISDIR(st.st_mode) || is_osh) ? read_osh_mesh(spec, &coords, &t2v, err)
               : is_msh            ? read_gmsh_mesh(spec, &coords, &t2v, err)
                                   : read_raw_mesh(spec, &coords, &t2v, err);
     if (!ok) return false;

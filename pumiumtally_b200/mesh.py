@@ -14,6 +14,8 @@ the (0,0,0)-(1,1,1) diagonal with element 0 = {y>=x>=z} (centroid
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 # Hex-local corner numbering (x fastest): 0:(0,0,0) 1:(1,0,0) 2:(1,1,0) 3:(0,1,0)
@@ -144,3 +146,87 @@ def save_gmsh(path: str, coords, tet2vert, version: str = "2.2", node_id_offset:
             for e, t in enumerate(t2v):
                 f.write("%d %d %d %d %d\n" % (e + 2, *t))
             f.write("$EndElements\n")
+
+
+def simplex_downward(tet2vert):
+    """Edges, triangles and the downward adjacencies tet->tri, tri->edge, edge->vert of a tet
+    mesh (entities numbered in order of first appearance of their sorted vertex tuple)."""
+    t = np.asarray(tet2vert, dtype=np.int64)
+    tri_of_tet = np.stack([t[:, [0, 2, 1]], t[:, [0, 1, 3]], t[:, [1, 2, 3]], t[:, [2, 0, 3]]], axis=1)
+    tri_keys = np.sort(tri_of_tet.reshape(-1, 3), axis=1)
+    tris, rf2f = np.unique(tri_keys, axis=0, return_inverse=True)
+    edge_of_tri = np.stack([tris[:, [0, 1]], tris[:, [1, 2]], tris[:, [0, 2]]], axis=1)
+    edge_keys = np.sort(edge_of_tri.reshape(-1, 2), axis=1)
+    edges, fe2e = np.unique(edge_keys, axis=0, return_inverse=True)
+    return (edges.astype(np.int32), fe2e.reshape(-1).astype(np.int32), rf2f.reshape(-1).astype(np.int32))
+
+
+def save_osh(path: str, coords, tet2vert, version: int = 10, compressed: bool = True,
+             tag_layout: str = "direct", extra_tags: bool = True, bare_stream: bool = False) -> None:
+    """Write an Omega_h-style binary mesh directory (``nparts``, ``version``, ``0.osh``) following
+    the stream layout documented in ``csrc/osh_reader.cpp``.  The layout is a restatement from
+    memory of Omega_h's published format (no Omega_h here to check against): this writer exists so
+    the reader's parsing, zlib handling and tet->tri->edge->vert composition are exercised.
+    Alignment codes are written as zeros (the reader does not consume them).
+
+    tag_layout: "direct" (name, ncomps, type, array), "class_ids" (an i32 class-id count and
+    optional id list before the array) or "flags" (two flag bytes, stream versions < 5)."""
+    import struct
+    import zlib
+
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    ev2v, fe2e, rf2f = simplex_downward(tet2vert)
+    nv = len(coords)
+
+    def arr(a):
+        a = np.ascontiguousarray(a)
+        raw = a.tobytes()
+        head = struct.pack("<i", a.size)
+        if compressed:
+            z = zlib.compress(raw, 1)
+            return head + struct.pack("<q", len(z)) + z
+        return head + raw
+
+    def tag(name, ncomps, type_code, a, class_ids=None):
+        b = struct.pack("<i", len(name)) + name.encode() + struct.pack("<bb", ncomps, type_code)
+        if tag_layout == "class_ids":
+            ids = np.asarray(class_ids if class_ids is not None else [], dtype=np.int32)
+            b += struct.pack("<i", ids.size)
+            if ids.size:
+                b += arr(ids)
+        elif tag_layout == "flags":
+            b += struct.pack("<bb", 1, 1)
+        return b + arr(a)
+
+    s = bytes([0xA1, 0x1A])
+    if bare_stream:
+        s += struct.pack("<i", version)
+    s += struct.pack("<b", 1 if compressed else 0)
+    if version >= 7:
+        s += struct.pack("<b", 0)                       # family: simplex
+    s += struct.pack("<biibib", 3, 1, 0, 0, 0, 0)       # dim, comm size/rank, parting, ghost layers, no hints
+    s += struct.pack("<i", nv)
+    s += arr(ev2v.reshape(-1))
+    s += arr(fe2e) + arr(np.zeros(fe2e.size, dtype=np.int8))
+    s += arr(rf2f) + arr(np.zeros(rf2f.size, dtype=np.int8))
+    vtags = []
+    if extra_tags:
+        vtags.append(tag("class_dim", 1, 0, np.full(nv, 3, dtype=np.int8)))
+        vtags.append(tag("global", 1, 3, np.arange(nv, dtype=np.int64), class_ids=[1, 2, 3]))
+    vtags.append(tag("coordinates", 3, 5, coords.reshape(-1)))
+    if extra_tags:
+        vtags.append(tag("class_id", 1, 2, np.zeros(nv, dtype=np.int32)))
+    s += struct.pack("<i", len(vtags)) + b"".join(vtags)
+    for n in (len(ev2v), fe2e.size // 3, rf2f.size // 4):   # tags of edges, triangles, tets
+        s += struct.pack("<i", 1) + tag("class_dim", 1, 0, np.full(n, 3, dtype=np.int8))
+    if bare_stream:
+        with open(path, "wb") as f:
+            f.write(s)
+        return
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "nparts"), "w") as f:
+        f.write("1\n")
+    with open(os.path.join(path, "version"), "w") as f:
+        f.write("%d\n" % version)
+    with open(os.path.join(path, "0.osh"), "wb") as f:
+        f.write(s)

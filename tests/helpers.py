@@ -77,7 +77,7 @@ def emul_lib():
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp",
                                    "-I", os.path.join(ROOT, "pumiumtally_b200", "csrc"),
-                                   "-I", os.path.join(ROOT, "include"), *srcs, "-o", so])
+                                   "-I", os.path.join(ROOT, "include"), *srcs, "-o", so, "-lz"])
         L = C.CDLL(so)
         L.ptb_emul_create.restype = C.c_void_p
         L.ptb_emul_create.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int]
@@ -109,7 +109,8 @@ class HostEmulTally:
             t2v = np.ascontiguousarray(tet2vert, dtype=np.int32)
             self._h = self._L.ptb_emul_create(coords.ctypes.data, coords.shape[0], t2v.ctypes.data, t2v.shape[0],
                                               self.num_particles)
-        assert self._h, "mesh rejected"
+        if not self._h:
+            raise RuntimeError("mesh rejected")
         sz = np.zeros(2, dtype=np.int64)
         self._L.ptb_emul_sizes(self._h, sz.ctypes.data)
         self.num_verts, self.num_elements = int(sz[0]), int(sz[1])

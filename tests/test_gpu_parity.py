@@ -238,6 +238,27 @@ def test_raw_mesh_file_and_box_spec(tmp_path):
     np.testing.assert_allclose(a.flux, b.flux, rtol=1e-13)
 
 
+@pytest.mark.parametrize("fmt", ["osh", "osh_uncompressed", "msh"])
+def test_mesh_file_formats_drive_the_engine_like_the_oracle(tmp_path, fmt):
+    """The ctor's mesh argument as a user would pass it (PumiTally.h:40-47): an Omega_h .osh
+    directory or the Gmsh file it was converted from.  Unstructured mesh, three moves, parity
+    against the oracle built from the same arrays."""
+    from pumiumtally_b200.mesh import save_gmsh, save_osh
+
+    coords, t2v = delaunay_box(400)
+    if fmt == "msh":
+        path = str(tmp_path / "mesh.msh")
+        save_gmsh(path, coords, t2v, version="4.1")
+    else:
+        path = str(tmp_path / "mesh.osh")
+        save_osh(path, coords, t2v, compressed=(fmt == "osh"))
+    n = 20_000
+    eng, orc = PumiTally(path, n), OraclePumiTally(coords, t2v, n)
+    assert eng.num_elements == len(t2v)
+    wl = SyntheticWorkload(box=(1.0, 1.0, 1.0), num_particles=n, mean_length=0.3)
+    run_workload(eng, orc, wl, steps=3, label=fmt)
+
+
 def test_device_pointer_entry_points_match_host_path():
     import torch
 

@@ -3,6 +3,8 @@ per-ray state machine, seed-grid relocation), compiled for the host by g++ as a
 TEST-ONLY build, checked against the oracle.  This is what can be verified
 without a GPU; the `-m gpu` tests repeat the same comparisons through
 libpumitally.so."""
+import os
+
 import numpy as np
 import pytest
 
@@ -51,6 +53,69 @@ def test_gmsh_ingest(tmp_path, version):
     np.testing.assert_array_equal(tm, t)
     np.testing.assert_array_equal(cm, c)
     np.testing.assert_allclose(vm, tet_volumes(c, t), rtol=1e-13)
+
+
+OSH_CASES = [dict(), dict(compressed=False), dict(version=9, tag_layout="direct"),
+             dict(version=10, tag_layout="class_ids"), dict(version=10, tag_layout="class_ids", compressed=False),
+             dict(version=4, tag_layout="flags"), dict(extra_tags=False), dict(bare_stream=True, version=10)]
+
+
+@pytest.mark.parametrize("kw", OSH_CASES, ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()) or "default")
+def test_osh_ingest(tmp_path, kw):
+    """Omega_h .osh directory (restated stream layout, csrc/osh_reader.cpp): element order and
+    coordinates survive, tet vertex SETS are recovered from tet->tri->edge->vert."""
+    from pumiumtally_b200.mesh import save_osh
+
+    c, t = delaunay_box(60)
+    path = str(tmp_path / "mesh.osh")
+    save_osh(path, c, t, **kw)
+    e = HostEmulTally(spec=path, num_particles=1)
+    cm, tm, vm = e.mesh_arrays()
+    np.testing.assert_array_equal(np.sort(tm, axis=1), np.sort(t, axis=1))
+    np.testing.assert_array_equal(cm, c)
+    np.testing.assert_allclose(vm, tet_volumes(c, t), rtol=1e-12)
+    o = OraclePumiTally(c, t, 1)  # local face order follows local vertex order: compare as sets
+    np.testing.assert_array_equal(np.sort(e.adjacency, axis=1), np.sort(o.adjacency, axis=1))
+
+
+def test_osh_t1_cube_walks_like_the_reference_fixture(tmp_path):
+    """The reference test writes its 6-tet cube to mesh.osh and reads it back
+    (test_pumi_tally_impl_methods.cpp:45-46); same round trip here, then the T1 move."""
+    from pumiumtally_b200.mesh import save_osh
+
+    c, t = kuhn_box(1, 1, 1)
+    path = str(tmp_path / "mesh.osh")
+    save_osh(path, c, t)
+    e = HostEmulTally(spec=path, num_particles=5)
+    e.CopyInitialPosition(np.tile([0.1, 0.4, 0.5], 5))
+    assert (e.elem_ids == 2).all()
+    fly = np.ones(5, dtype=np.int8)
+    e.MoveToNextLocation(np.tile([0.1, 0.4, 0.5], 5), np.tile([1.2, 0.4, 0.5], 5), fly, np.ones(5))
+    np.testing.assert_allclose(e.flux, [0, 0, 1.5, 0.5, 2.5, 0], atol=1e-12)
+
+
+@pytest.mark.parametrize("damage", ["magic", "truncate", "nparts", "dim", "zlib"])
+def test_osh_ingest_rejects_damaged_input(tmp_path, damage):
+    from pumiumtally_b200.mesh import save_osh
+
+    c, t = kuhn_box(2, 2, 1)
+    path = str(tmp_path / "mesh.osh")
+    save_osh(path, c, t)
+    stream = os.path.join(path, "0.osh")
+    raw = bytearray(open(stream, "rb").read())
+    if damage == "magic":
+        raw[0] = 0
+    elif damage == "truncate":
+        raw = raw[: len(raw) // 3]
+    elif damage == "nparts":
+        open(os.path.join(path, "nparts"), "w").write("4\n")
+    elif damage == "dim":
+        raw[4] = 2                      # magic(2) compressed(1) family(1) dim(1)
+    elif damage == "zlib":
+        raw[40:48] = b"\xff" * 8
+    open(stream, "wb").write(bytes(raw))
+    with pytest.raises(RuntimeError):
+        HostEmulTally(spec=path, num_particles=1)
 
 
 @pytest.mark.parametrize("mesh", ["kuhn", "jitter", "delaunay"])

@@ -389,14 +389,14 @@ def run_gpu(args, rank, local_rank, world):
                      "frac": (achieved / peak) if achieved else None,
                      "traffic": recorded_traffic() if (args.config == "c2" and not args.particles) else None,
                      "kernel": "walk kernel (variant %d%s), %d launches, %.3f ms each" % (
-                         variant_used, " incl. binning pass" if variant_used in (15, 16, 17) else "", args.steps,
+                         variant_used, " incl. binning pass" if variant_used in (15, 16, 17, 21) else "", args.steps,
                          kernel_ms / max(args.steps, 1)),
                      "algorithmic_bytes_per_launch": alg_bytes / max(args.steps, 1), "peak_source": peak_src},
         "cpu_baseline": cpu,
         "e2e": e2e,
         # kernels of this repo inside the timed region: one fused walk kernel per move, plus the five
         # binning kernels (count, 3-kernel scan, scatter) when the binned variant is in use
-        "gpu_launches": args.steps * (6 if variant_used in (15, 16, 17) else 1),
+        "gpu_launches": args.steps * (6 if variant_used in (15, 16, 17, 21) else 1),
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

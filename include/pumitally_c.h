@@ -91,6 +91,7 @@ typedef struct pumitally_stats {
   uint64_t moves;         /* MoveToNextLocation calls */
   double kernel_ms;       /* device time of the walk kernels (CUDA events), cumulative */
   double h2d_bytes;       /* bytes uploaded by the host-pointer entry points, cumulative */
+  uint64_t plane_fallbacks; /* compact-layout walk: rays coplanar with a mesh edge, finished on the plane records */
 } pumitally_stats;
 int pumitally_get_stats(pumitally_engine *e, pumitally_stats *out);
 

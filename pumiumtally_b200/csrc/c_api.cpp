@@ -145,6 +145,7 @@ int pumitally_get_stats(pumitally_engine *e, pumitally_stats *out) {
     out->moves = s.moves;
     out->kernel_ms = s.kernel_ms;
     out->h2d_bytes = s.h2d_bytes;
+    out->plane_fallbacks = s.plane_fallbacks;
     return 0;
   });
 }

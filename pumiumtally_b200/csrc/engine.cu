@@ -75,6 +75,7 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
 
   cuda_or_throw(cudaMemcpy(d_tets_, mesh_.records.data(), E * sizeof(TetRecord), cudaMemcpyHostToDevice), "upload tets");
   cuda_or_throw(cudaMemcpy(d_volume_, mesh_.volume.data(), E * sizeof(double), cudaMemcpyHostToDevice), "upload volume");
+  upload_compact();
   cuda_or_throw(cudaMemset(d_flux_, 0, E * sizeof(double)), "memset");
   cuda_or_throw(cudaMemset(d_stats_, 0, sizeof(DeviceStats)), "memset");
   // InitializeParticlesInElement0 (PumiTallyImpl.cpp:492-528)
@@ -90,6 +91,27 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
          (long long)mesh_.ntets, n_, device_);
 }
 
+// Compact layout: TetLinks (32 B per tet) + vertices (32 B each) are what the edge-function walk
+// reads per crossing; TetStart lines (128 B per tet) are read once per ray.
+void Engine::upload_compact() {
+  std::string err;
+  if (!mesh_.build_compact(&err)) {
+    printf("[INFO] pumitally-b200: compact layout not built (%s); plane records only\n", err.c_str());
+    return;
+  }
+  const size_t E = size_t(mesh_.ntets), V = size_t(mesh_.nverts);
+  std::vector<TetLinks> links(E);
+  for (size_t e = 0; e < E; ++e) links[e] = mesh_.starts[e].links;
+  dev_alloc(&d_links_, E, "tet links");
+  dev_alloc(&d_verts_, V, "vertices");
+  dev_alloc(&d_starts_, E, "tet start lines");
+  cuda_or_throw(cudaMemcpy(d_links_, links.data(), E * sizeof(TetLinks), cudaMemcpyHostToDevice), "upload links");
+  cuda_or_throw(cudaMemcpy(d_verts_, mesh_.cverts.data(), V * sizeof(VertexRec), cudaMemcpyHostToDevice), "upload vertices");
+  cuda_or_throw(cudaMemcpy(d_starts_, mesh_.starts.data(), E * sizeof(TetStart), cudaMemcpyHostToDevice), "upload start lines");
+  std::vector<TetStart>().swap(mesh_.starts);
+  std::vector<VertexRec>().swap(mesh_.cverts);
+}
+
 Engine::~Engine() {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
@@ -98,6 +120,7 @@ Engine::~Engine() {
   for (auto &t : timers_free_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto &t : timers_busy_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto &e : chunk_events_) cudaEventDestroy(e);
+  cudaFree(d_links_); cudaFree(d_verts_); cudaFree(d_starts_);
   cudaFree(d_tets_); cudaFree(d_flux_); cudaFree(d_volume_); cudaFree(d_scratch_);
   cudaFree(d_state_);
   cudaFree(d_origin_); cudaFree(d_dest_); cudaFree(d_weights_); cudaFree(d_flying_);
@@ -171,8 +194,11 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
                          const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream,
                          bool timed) {
   if (end <= begin) return 0;
-  WalkParams p;
+  WalkParams p{};
   p.tets = d_tets_;
+  p.links = d_links_;
+  p.verts = d_verts_;
+  p.starts = d_starts_;
   p.flux = d_flux_;
   p.state = d_state_;
   p.origin = d_origin;
@@ -201,7 +227,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
     PTB_CUDA_OK(cudaEventRecord(t.a, stream));
   }
   if (variant_ == kVariantPersistGather || variant_ == kVariantPersistGatherL1 ||
-      variant_ == kVariantPersistGatherPlain) {
+      variant_ == kVariantPersistGatherPlain || variant_ == kVariantEdgeGather) {
     // counting sort of the range's flying particles by seed-grid cell of their origin
     unsigned int *wc = d_work_count_ + (ticket_next_ % kTicketRing);
     const double *key = d_origin ? d_origin : d_dest;
@@ -418,6 +444,7 @@ int Engine::get_stats(EngineStats *out) {
   out->moves = moves_;
   out->kernel_ms = kernel_ms_;
   out->h2d_bytes = h2d_bytes_;
+  out->plane_fallbacks = s.fallbacks;
   if (s.lost)  // reference wording, PumiTallyImpl.cpp:455-458
     printf("ERROR: Not all particles are found. May need more loops in search\n");
   return 0;
@@ -447,6 +474,7 @@ int Engine::set_option(const std::string &name, int64_t v) {
   if (name == "variant") {
     if (v == -1) { variant_ = choose_variant(); return 0; }  // automatic
     if (v < 0 || v >= kNumVariants) return 1;
+    if ((v == kVariantEdge || v == kVariantEdgeOcc6 || v == kVariantEdgeGather) && !d_links_) return 1;
     variant_ = int(v);
   } else if (name == "block") {
     if (v != 64 && v != 128 && v != 256) return 1;

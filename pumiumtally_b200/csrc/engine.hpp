@@ -20,6 +20,7 @@ struct EngineStats {
   uint64_t segments = 0, tracks = 0, relocations = 0, lost = 0, moves = 0;
   double kernel_ms = 0.0;
   double h2d_bytes = 0.0;
+  uint64_t plane_fallbacks = 0;
 };
 
 class Engine {
@@ -70,6 +71,7 @@ class Engine {
   void maybe_register(const void *p, size_t bytes);
   void collect_timers(bool wait);
   void build_seed_grid();
+  void upload_compact();
 
   HostMesh mesh_;
   int32_t n_ = 0;
@@ -89,6 +91,9 @@ class Engine {
 
   // device memory
   TetRecord *d_tets_ = nullptr;
+  TetLinks *d_links_ = nullptr;    // compact layout (walk_compact.cuh); null when the mesh exceeds its id ranges
+  VertexRec *d_verts_ = nullptr;
+  TetStart *d_starts_ = nullptr;
   double *d_flux_ = nullptr, *d_volume_ = nullptr, *d_scratch_ = nullptr;
   ParticleState *d_state_ = nullptr;  // persistent position + parent element, 32 B per particle
   double *d_origin_ = nullptr, *d_dest_ = nullptr, *d_weights_ = nullptr;  // staging

@@ -287,4 +287,67 @@ bool HostMesh::finalize(std::string *err) {
   return true;
 }
 
+// ---- compact layout -----------------------------------------------------------------------
+bool HostMesh::build_compact(std::string *err) {
+  if (nverts > int64_t(kVertMask)) { *err = "too many vertices for the compact layout (28-bit ids)"; return false; }
+  // vertices in order of first use by the (spatially ordered) internal tets
+  std::vector<int32_t> vnew(static_cast<size_t>(nverts), -1);
+  int32_t next = 0;
+  for (size_t i = 0; i < t2v.size(); ++i)
+    if (vnew[t2v[i]] < 0) vnew[t2v[i]] = next++;
+  for (int64_t v = 0; v < nverts; ++v)
+    if (vnew[v] < 0) vnew[v] = next++;
+  cverts.assign(static_cast<size_t>(nverts), VertexRec{0, 0, 0, 0});
+  for (int64_t v = 0; v < nverts; ++v)
+    cverts[vnew[v]] = VertexRec{coords[3 * v], coords[3 * v + 1], coords[3 * v + 2], 0.0};
+
+  // slot s of tet e = local vertex (s ^ flip) for s >= 2: swapping the last two makes det > 0
+  std::vector<uint8_t> flip(static_cast<size_t>(ntets));
+#pragma omp parallel for schedule(static)
+  for (int64_t e = 0; e < ntets; ++e) {
+    const double *V[4];
+    for (int i = 0; i < 4; ++i) V[i] = &coords[3 * size_t(t2v[4 * e + i])];
+    double a[3], b[3], c[3];
+    for (int d = 0; d < 3; ++d) { a[d] = V[1][d] - V[0][d]; b[d] = V[2][d] - V[0][d]; c[d] = V[3][d] - V[0][d]; }
+    const double det = a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) +
+                       a[2] * (b[0] * c[1] - b[1] * c[0]);
+    flip[e] = det < 0.0;
+  }
+  auto local_of_slot = [&](int64_t e, int s) { return (flip[e] && s >= 2) ? (s ^ 1) : s; };  // involution
+
+  starts.resize(static_cast<size_t>(ntets));
+  bool bad = false;
+#pragma omp parallel for schedule(static) reduction(|| : bad)
+  for (int64_t e = 0; e < ntets; ++e) {
+    TetStart &S = starts[e];
+    for (int s = 0; s < 4; ++s) {
+      const int32_t v = t2v[4 * e + local_of_slot(e, s)];
+      for (int d = 0; d < 3; ++d) S.v[3 * s + d] = coords[3 * size_t(v) + d];
+    }
+    for (int k = 0; k < 4; ++k) {
+      const int32_t nb = t2t[4 * e + local_of_slot(e, k)];
+      if (nb < 0) { S.links.nbr[k] = 0x3fffffffu; S.links.opp[k] = 0; continue; }
+      int back = -1;
+      for (int q = 0; q < 4; ++q)
+        if (t2t[4 * size_t(nb) + q] == int32_t(e)) back = q;
+      if (back < 0) { bad = true; continue; }
+      uint32_t map[3] = {0, 0, 0};
+      int j = 0;
+      for (int s = 0; s < 4; ++s) {
+        if (s == k) continue;
+        const int32_t vid = t2v[4 * e + local_of_slot(e, s)];
+        int where = -1;
+        for (int q = 0; q < 4; ++q)
+          if (t2v[4 * size_t(nb) + q] == vid) where = q;
+        if (where < 0 || where == back) bad = true;
+        map[j++] = uint32_t(local_of_slot(nb, where < 0 ? 0 : where));
+      }
+      S.links.nbr[k] = uint32_t(nb) | (map[0] << 30);
+      S.links.opp[k] = uint32_t(vnew[t2v[4 * size_t(nb) + back]]) | ((map[1] | (map[2] << 2)) << 28);
+    }
+  }
+  if (bad) { *err = "inconsistent face adjacency while building the compact layout"; return false; }
+  return true;
+}
+
 }  // namespace ptb

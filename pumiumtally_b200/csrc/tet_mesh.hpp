@@ -31,6 +31,33 @@ struct alignas(128) TetRecord {
 };
 static_assert(sizeof(TetRecord) == 128, "TetRecord must be one 128-byte line");
 
+// Compact (vertex-indexed) layout read by the edge-function walk; see walk_compact.cuh.
+// Per tet, indexed by local face k = face opposite local vertex ("slot") k.  Slots are ordered
+// so that the tet is positively oriented: det(v1-v0, v2-v0, v3-v0) > 0.
+//   nbr[k]  bits 0..29  neighbour across face k (all ones = hull)
+//           bits 30..31 map[0]
+//   opp[k]  bits 0..27  vertex of that neighbour opposite the shared face
+//           bits 28..31 map[1] | map[2] << 2
+// map[j] = the neighbour's slot of this tet's j-th slot other than k (ascending).
+struct alignas(32) TetLinks {
+  uint32_t nbr[4];
+  uint32_t opp[4];
+};
+static_assert(sizeof(TetLinks) == 32, "TetLinks must be one sector");
+
+struct alignas(32) VertexRec {
+  double x, y, z, pad;
+};
+
+// First tet of a ray: the four vertices in slot order + the links, one 128-byte line.
+struct alignas(128) TetStart {
+  double v[12];
+  TetLinks links;
+};
+static_assert(sizeof(TetStart) == 128, "TetStart must be one 128-byte line");
+
+constexpr uint32_t kVertMask = 0x0fffffffu;  // vertex ids are 28-bit in the compact layout
+
 struct HostMesh {
   int64_t nverts = 0;
   int64_t ntets = 0;
@@ -39,6 +66,8 @@ struct HostMesh {
   std::vector<int32_t> t2t;      // [4*ntets], neighbour across face opposite vertex f, -1 hull
   std::vector<double> volume;    // [ntets]
   std::vector<TetRecord> records;  // [ntets]
+  std::vector<TetStart> starts;    // [ntets]  compact layout (build_compact())
+  std::vector<VertexRec> cverts;   // [nverts] vertices in order of first use by the internal tet order
   double centroid0[3] = {0, 0, 0};  // centroid of (the caller's) element 0 (PumiTallyImpl.cpp:500-509)
 
   // INTERNAL ELEMENT ORDER.  finalize() renumbers the tets by the z-major index of the
@@ -74,6 +103,8 @@ struct HostMesh {
                    std::string *err);
   // adjacency + volumes + packed records; called by load()/from_arrays().
   bool finalize(std::string *err);
+  // compact layout (starts[].links is the TetLinks table); needs finalize() first.
+  bool build_compact(std::string *err);
 };
 
 // Generators / readers (tet_mesh.cpp, osh_reader.cpp)

@@ -116,9 +116,13 @@ struct DeviceStats {
   unsigned long long tracks;       // flying particles in weighted phases
   unsigned long long relocations;  // crossings walked with tallying off
   unsigned long long lost;         // walks stopped by the iteration limit
+  unsigned long long fallbacks;    // compact layout: rays handed to the plane records (coplanar edge)
 };
 
 struct TetRecord;
+struct TetLinks;
+struct VertexRec;
+struct TetStart;
 
 // Persistent per-particle state: position + parent element in one 32-byte, 32-byte aligned
 // record = one DRAM/L2 sector.  A particle is read with one 256-bit load and written back with
@@ -186,6 +190,9 @@ PTB_HD void seed_point(const SeedGrid &g, int cx, int cy, int cz, double &x, dou
 // One launch = one particle range of one MoveToNextLocation / CopyInitialPosition.
 struct WalkParams {
   const TetRecord *tets;   // [E] packed records
+  const TetLinks *links;   // [E] compact layout (walk_compact.cuh); nullptr when not uploaded
+  const VertexRec *verts;  // [V]
+  const TetStart *starts;  // [E]
   double *flux;            // [E] raw tally
   ParticleState *state;    // [N] persistent particle position + parent element
   const double *origin;    // [3N] AoS relocation target (phase 1), nullptr = skip phase
@@ -222,7 +229,7 @@ struct Ray {
 };
 
 struct Counters {
-  unsigned segs = 0, tracks = 0, relocs = 0, lost = 0;
+  unsigned segs = 0, tracks = 0, relocs = 0, lost = 0, fallbacks = 0;
 };
 
 PTB_HD void set_ray(Ray &r, double x, double y, double z, double tx, double ty, double tz) {

@@ -16,6 +16,7 @@
 #include <cstddef>
 #include <cstdint>
 
+#include "walk_compact.cuh"
 #include "walk_core.cuh"
 
 namespace ptb {
@@ -26,7 +27,9 @@ __device__ __forceinline__ void flush_counters(const WalkParams &P, const Counte
   const unsigned tracks = __reduce_add_sync(0xffffffffu, c.tracks);
   const unsigned relocs = __reduce_add_sync(0xffffffffu, c.relocs);
   const unsigned lost = __reduce_add_sync(0xffffffffu, c.lost);
+  const unsigned fallbacks = __reduce_add_sync(0xffffffffu, c.fallbacks);
   if ((threadIdx.x & 31) == 0) {
+    if (fallbacks) atomicAdd(&P.stats->fallbacks, (unsigned long long)fallbacks);
     if (segs) atomicAdd(&P.stats->segments, (unsigned long long)segs);
     if (tracks) atomicAdd(&P.stats->tracks, (unsigned long long)tracks);
     if (relocs) atomicAdd(&P.stats->relocations, (unsigned long long)relocs);
@@ -290,7 +293,9 @@ __device__ __forceinline__ void begin_from_stage(const WalkParams &P, const Part
 //      profiles/r01/README.md section c/d, and removed)
 //   5  as 1 but the tet loads allocate in L1 (worth it once particles are processed in
 //      spatial order and neighbouring lanes/warps revisit the same records)
-enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3, kFetchCoop = 4, kFetchPolicyL1 = 5 };
+//   6  compact layout + edge-function exit test (walk_compact.cuh): one 32-byte TetLinks sector and
+//      one 32-byte vertex per crossing, both L2-resident; degenerate rays finish on the plane records
+enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3, kFetchCoop = 4, kFetchPolicyL1 = 5, kFetchEdge = 6 };
 
 __device__ __forceinline__ uint64_t l2_policy_keep() {
   uint64_t p;
@@ -387,6 +392,94 @@ __device__ __forceinline__ void stage_gather(const WalkParams &P, int id, int co
   cp_async_arrive_noinc(bar);
 }
 
+// One crossing on the plane records.  Entry-face elision: after a crossing the face the ray came
+// in through is known (r.entry) and can never be the exit, so only the other three 32-byte
+// sectors of the record are fetched; the first tet of a ray needs all four.
+template <int FETCH>
+__device__ __forceinline__ void plane_step(const WalkParams &P, int my_i, Ray &r, Counters &c, uint64_t pol) {
+  ExitScan sc;
+  const double *rec = P.tets[r.e].d;
+  const int en = r.entry;
+  double q[3][4], q3[4];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int fk = k + ((en >= 0 && k >= en) ? 1 : 0);
+    load_face<FETCH>(rec + 4 * fk, pol, q[k][0], q[k][1], q[k][2], q[k][3]);
+  }
+  if (en < 0) load_face<FETCH>(rec + 12, pol, q3[0], q3[1], q3[2], q3[3]);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int fk = k + ((en >= 0 && k >= en) ? 1 : 0);
+    int32_t nb, bk;
+    face_payload(q[k][0], q[k][1], q[k][2], q[k][3], r.e, fk, nb, bk);
+    scan_face(sc, q[k][0], q[k][1], q[k][2], q[k][3], nb, bk, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
+  }
+  if (en < 0) {
+    int32_t nb, bk;
+    face_payload(q3[0], q3[1], q3[2], q3[3], r.e, 3, nb, bk);
+    scan_face(sc, q3[0], q3[1], q3[2], q3[3], nb, bk, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
+  }
+  advance(P, my_i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
+}
+
+// ---- compact layout (kFetchEdge) ----------------------------------------------------------
+constexpr int kPlaneMode = -2;  // EdgeRay::dv of a ray that is finishing on the plane records
+
+__device__ __forceinline__ void ld256_b64(const void *p, uint64_t pol, unsigned long long &a,
+                                          unsigned long long &b, unsigned long long &c, unsigned long long &d) {
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b64 {%0,%1,%2,%3}, [%4], %5;"
+               : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol));
+}
+
+// First tet of a ray, out of line: its register footprint (four vertices, six edge functions)
+// must not set the allocation of the per-crossing path.  Streams the TetStart line past the L2.
+__device__ __noinline__ bool edge_first_step(const TetStart *S, const Ray &r, EdgeRay &g, uint64_t strm,
+                                             double &texit, int32_t &next, int32_t &roles) {
+  unsigned long long w0, w1, w2, w3;
+  double v[12];
+  ld256_b64(&S->links, strm, w0, w1, w2, w3);
+  load_face<kFetchPolicy>(S->v, strm, v[0], v[1], v[2], v[3]);
+  load_face<kFetchPolicy>(S->v + 4, strm, v[4], v[5], v[6], v[7]);
+  load_face<kFetchPolicy>(S->v + 8, strm, v[8], v[9], v[10], v[11]);
+  TetLinks L;
+  L.nbr[0] = (uint32_t)w0; L.nbr[1] = (uint32_t)(w0 >> 32); L.nbr[2] = (uint32_t)w1; L.nbr[3] = (uint32_t)(w1 >> 32);
+  L.opp[0] = (uint32_t)w2; L.opp[1] = (uint32_t)(w2 >> 32); L.opp[2] = (uint32_t)w3; L.opp[3] = (uint32_t)(w3 >> 32);
+  return edge_first(r, g, L, v, texit, next, roles);
+}
+
+// One crossing of the edge-function walk: the TetLinks sector of the current tet + the one new
+// vertex (keep policy; vertices also allocate in L1), both requested before either is used.
+__device__ __forceinline__ void edge_persist_step(const WalkParams &P, int my_i, Ray &r, EdgeRay &g,
+                                                  Counters &c, uint64_t keep, uint64_t strm) {
+  if (g.dv == kPlaneMode) {
+    plane_step<kFetchPolicy>(P, my_i, r, c, strm);
+    if (r.iters == 0) g.dv = 0;  // a new ray (phase 2 after phase 1) starts on the fast path again
+    return;
+  }
+  double texit;
+  int32_t next, roles;
+  bool ok;
+  if (r.entry < 0) {
+    ok = edge_first_step(P.starts + r.e, r, g, strm, texit, next, roles);
+  } else {
+    unsigned long long w0, w1, w2, w3;
+    double dx, dy, dz, dpad;
+    ld256_b64(P.links + r.e, keep, w0, w1, w2, w3);
+    load_face<kFetchPolicyL1>(reinterpret_cast<const double *>(P.verts + g.dv), keep, dx, dy, dz, dpad);
+    TetLinks L;
+    L.nbr[0] = (uint32_t)w0; L.nbr[1] = (uint32_t)(w0 >> 32); L.nbr[2] = (uint32_t)w1; L.nbr[3] = (uint32_t)(w1 >> 32);
+    L.opp[0] = (uint32_t)w2; L.opp[1] = (uint32_t)(w2 >> 32); L.opp[2] = (uint32_t)w3; L.opp[3] = (uint32_t)(w3 >> 32);
+    ok = edge_step(r, g, L, dx, dy, dz, texit, next, roles);
+  }
+  if (ok) {
+    advance(P, my_i, r, texit, next, roles, c, true);
+  } else {  // coplanar edge: redo this tet, and the rest of the ray, with the planes
+    g.dv = kPlaneMode;
+    r.entry = -1;
+    c.fallbacks++;
+  }
+}
+
 constexpr int kClaimRun = 4;  // gather mode: a warp takes up to this many consecutive chunks per ticket
 
 // REFILL_T: idle lanes are topped up only when at least this many have finished -- the
@@ -476,6 +569,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
 
   Counters c;
   Ray r;
+  EdgeRay g;  // only live in the compact-layout instantiation
+  g.dv = 0;
   r.stage = kStageDone;
   int my_i = 0;
   for (;;) {
@@ -485,6 +580,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
       if (r.stage == kStageDone && slot < cur_count) {
         my_i = GATHER ? stages[warp][cur].id[slot] : P.begin + chunk_cur * kChunk + slot;
         begin_from_stage(P, &stages[warp][cur], slot, r, c);
+        if constexpr (FETCH == kFetchEdge) g.dv = 0;
       }
       __syncwarp();
       cursor += __popc(idle);
@@ -518,8 +614,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
       parity ^= 4u;
     }
     if (r.stage != kStageDone) {
-      ExitScan sc;
-      if constexpr (kRows) {
+      if constexpr (FETCH == kFetchEdge) {
+        edge_persist_step(P, my_i, r, g, c, keep, strm);
+      } else if constexpr (kRows) {
+        ExitScan sc;
         double raw[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -527,33 +625,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
                        : "=d"(raw[2 * j]), "=d"(raw[2 * j + 1])
                        : "r"(row + 16 * j));
         scan_record(raw, r.e, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, sc);
+        advance(P, my_i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
       } else {
-        // entry-face elision: after a crossing the face the ray came in through is known
-        // (r.entry) and can never be the exit, so only the other three 32-byte sectors of the
-        // record are fetched; the first tet of a ray needs all four.
-        const double *rec = P.tets[r.e].d;
-        const int en = r.entry;
-        double q[3][4], q3[4];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int fk = k + ((en >= 0 && k >= en) ? 1 : 0);
-          load_face<FETCH>(rec + 4 * fk, keep, q[k][0], q[k][1], q[k][2], q[k][3]);
-        }
-        if (en < 0) load_face<FETCH>(rec + 12, keep, q3[0], q3[1], q3[2], q3[3]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int fk = k + ((en >= 0 && k >= en) ? 1 : 0);
-          int32_t nb, bk;
-          face_payload(q[k][0], q[k][1], q[k][2], q[k][3], r.e, fk, nb, bk);
-          scan_face(sc, q[k][0], q[k][1], q[k][2], q[k][3], nb, bk, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
-        }
-        if (en < 0) {
-          int32_t nb, bk;
-          face_payload(q3[0], q3[1], q3[2], q3[3], r.e, 3, nb, bk);
-          scan_face(sc, q3[0], q3[1], q3[2], q3[3], nb, bk, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
-        }
+        plane_step<FETCH>(P, my_i, r, c, keep);
       }
-      advance(P, my_i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
     }
   }
   flush_counters(P, c);
@@ -667,6 +742,15 @@ cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_
       return launch_persist<128, kFetchBulk, 7>(p, n, stream);
     case kVariantPersistRefill8:
       return launch_persist<128, kFetchPolicy, 7, 8>(p, n, stream);
+    case kVariantEdge:
+      if (!p.links) return cudaErrorInvalidValue;
+      return launch_persist<128, kFetchEdge, 5, 8, false, 40>(p, n, stream);
+    case kVariantEdgeOcc6:
+      if (!p.links) return cudaErrorInvalidValue;
+      return launch_persist<128, kFetchEdge, 6, 8, false, 40>(p, n, stream);
+    case kVariantEdgeGather:
+      if (!p.links) return cudaErrorInvalidValue;
+      return launch_persist<128, kFetchEdge, 5, 8, true, 40>(p, n, stream);
     default:
       return cudaErrorInvalidValue;
   }

@@ -24,7 +24,10 @@ enum WalkVariant : int {
   kVariantPersistGather = 15,        // 8 on spatially binned particles (order[] from launch_bin_particles)
   kVariantPersistGatherL1 = 16,      // 15 with L1-allocating tet loads (default, mesh >> L2)
   kVariantPersistGatherPlain = 17,   // 15 with plain tet loads (no L2 policy)
-  kNumVariants = 18
+  kVariantEdge = 20,        // compact layout + edge-function exit test (walk_compact.cuh), streaming order
+  kVariantEdgeGather = 21,  // 20 on spatially binned particles
+  kVariantEdgeOcc6 = 22,    // 20 compiled for 6 resident blocks (80 registers, a few spills)
+  kNumVariants = 23
 };
 
 

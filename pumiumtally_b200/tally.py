@@ -28,7 +28,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("segments", C.c_uint64), ("tracks", C.c_uint64), ("relocations", C.c_uint64),
         ("lost", C.c_uint64), ("moves", C.c_uint64), ("kernel_ms", C.c_double),
-        ("h2d_bytes", C.c_double),
+        ("h2d_bytes", C.c_double), ("plane_fallbacks", C.c_uint64),
     ]
 
 

@@ -73,7 +73,7 @@ def emul_lib():
                 os.path.join(ROOT, "pumiumtally_b200", "csrc", "tet_mesh.cpp"),
                 os.path.join(ROOT, "pumiumtally_b200", "csrc", "osh_reader.cpp"),
                 os.path.join(ROOT, "pumiumtally_b200", "csrc", "gmsh_reader.cpp")]
-        deps = srcs + [os.path.join(ROOT, "pumiumtally_b200", "csrc", h) for h in ("walk_core.cuh", "tet_mesh.hpp", "seed_grid.hpp")]
+        deps = srcs + [os.path.join(ROOT, "pumiumtally_b200", "csrc", h) for h in ("walk_core.cuh", "walk_compact.cuh", "tet_mesh.hpp", "seed_grid.hpp")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp",
                                    "-I", os.path.join(ROOT, "pumiumtally_b200", "csrc"),
@@ -90,6 +90,9 @@ def emul_lib():
         L.ptb_emul_sizes.argtypes = [C.c_void_p, C.c_void_p]
         L.ptb_emul_build_grid.argtypes = [C.c_void_p]
         L.ptb_emul_grid_dims.argtypes = [C.c_void_p, C.c_void_p]
+        L.ptb_emul_set_layout.argtypes = [C.c_void_p, C.c_int]
+        L.ptb_emul_degenerate_rays.restype = C.c_ulonglong
+        L.ptb_emul_degenerate_rays.argtypes = [C.c_void_p]
         L.ptb_emul_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _EMUL = L
     return _EMUL
@@ -98,7 +101,7 @@ def emul_lib():
 class HostEmulTally:
     """The CUDA kernels' per-ray state machine compiled for the host (tests only)."""
 
-    def __init__(self, coords=None, tet2vert=None, num_particles=0, spec=None, seed_grid=False):
+    def __init__(self, coords=None, tet2vert=None, num_particles=0, spec=None, seed_grid=False, layout="planes"):
         self._L = emul_lib()
         self._want_grid = seed_grid
         self.num_particles = int(num_particles)
@@ -114,6 +117,8 @@ class HostEmulTally:
         sz = np.zeros(2, dtype=np.int64)
         self._L.ptb_emul_sizes(self._h, sz.ctypes.data)
         self.num_verts, self.num_elements = int(sz[0]), int(sz[1])
+        if layout == "edge" and self._L.ptb_emul_set_layout(self._h, 1) != 0:
+            raise RuntimeError("compact layout rejected")
         self.grid_valid_cells = self._L.ptb_emul_build_grid(self._h) if seed_grid else 0
 
     def grid_dims(self):
@@ -147,6 +152,11 @@ class HostEmulTally:
     elem_ids = property(lambda s: s._get()[1])
     positions = property(lambda s: s._get()[2])
     adjacency = property(lambda s: s._get()[4])
+
+    @property
+    def degenerate_rays(self):
+        """Rays the edge-function walk handed to the plane records (layout="edge")."""
+        return int(self._L.ptb_emul_degenerate_rays(self._h))
 
     def stats(self):
         st = self._get()[3]
@@ -209,3 +219,4 @@ def edge_case_scenario(make_engine):
     np.testing.assert_allclose(eng.flux.sum(), before, atol=1e-13)
     np.testing.assert_allclose(eng.positions[0], [2.0, 0.2, 0.1], atol=1e-13)
     np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+    return eng

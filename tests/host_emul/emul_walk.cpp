@@ -12,6 +12,7 @@
 
 #include "seed_grid.hpp"
 #include "tet_mesh.hpp"
+#include "walk_compact.cuh"
 #include "walk_core.cuh"
 
 using namespace ptb;
@@ -26,6 +27,8 @@ struct Emul {
   int n = 0;
   SeedGrid grid{};
   std::vector<int32_t> cell_tet;
+  unsigned long long degenerate_rays = 0;
+  bool edge = false;  // compact layout + edge-function exit test (walk_compact.cuh)
   // same construction as Engine::build_seed_grid(): localise every seed point from the
   // centroid of element 0, keep the tet where the point was reached
   void build_grid() {
@@ -64,7 +67,31 @@ struct Emul {
       Counters c;
       Ray r;
       begin_particle(P, i, r, c, true);
+      EdgeRay g{};
+      bool planes = !edge;  // per ray: a degenerate ray finishes on the plane records
       while (r.stage != kStageDone) {
+        if (!planes) {
+          // mirror of the compact kernel: first tet of a ray reads the TetStart line, every
+          // later one the TetLinks sector + the one new vertex
+          double texit;
+          int32_t next, roles;
+          const TetStart &S = mesh.starts[r.e];
+          bool ok;
+          if (r.entry < 0) {
+            ok = edge_first(r, g, S.links, S.v, texit, next, roles);
+          } else {
+            const VertexRec &D = mesh.cverts[g.dv];
+            ok = edge_step(r, g, S.links, D.x, D.y, D.z, texit, next, roles);
+          }
+          if (!ok) {  // coplanar edge: redo this tet, and the rest of the ray, with the planes
+            planes = true;
+            r.entry = -1;
+            ++degenerate_rays;
+          } else {
+            advance(P, i, r, texit, next, roles, c, true);
+          }
+          continue;
+        }
         // mirror of the persistent kernel's fetch: the entry face's sector is never read
         const double *rec = recs[r.e].d;
         const int en = r.entry;
@@ -77,6 +104,7 @@ struct Emul {
                     r.oz, r.ux, r.uy, r.uz);
         }
         advance(P, i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
+        if (r.iters == 0) planes = !edge;  // a new ray (phase 2 after phase 1) starts on the fast path again
       }
       stats.segments += c.segs; stats.tracks += c.tracks;
       stats.relocations += c.relocs; stats.lost += c.lost;
@@ -113,6 +141,14 @@ int ptb_emul_build_grid(void *h) {
   for (int32_t t : e->cell_tet) valid += t >= 0;
   return valid;
 }
+int ptb_emul_set_layout(void *h, int edge) {
+  auto *e = static_cast<Emul *>(h);
+  std::string err;
+  if (edge && e->mesh.starts.empty() && !e->mesh.build_compact(&err)) return 1;
+  e->edge = edge != 0;
+  return 0;
+}
+unsigned long long ptb_emul_degenerate_rays(void *h) { return static_cast<Emul *>(h)->degenerate_rays; }
 void ptb_emul_grid_dims(void *h, int32_t *out) {
   auto *e = static_cast<Emul *>(h);
   out[0] = e->grid.nx; out[1] = e->grid.ny; out[2] = e->grid.nz;

@@ -17,8 +17,9 @@ from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
 from test_oracle_golden import check_c1_fixture, golden_scenario
 
 pytestmark = pytest.mark.gpu
-VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 13, 15, 16, 17]
-BIG_VARIANTS = [0, 6, 8, 16]
+VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 13, 15, 16, 17, 20, 21, 22]
+BIG_VARIANTS = [0, 6, 8, 16, 20, 21]
+EDGE_VARIANTS = [20, 21, 22]  # compact layout + edge-function exit test
 
 
 def gpu_engine(variant, block=128, chunk=None, seed_grid=True):
@@ -169,7 +170,22 @@ def test_contention_many_particles_few_tets():
     run_workload(eng, orc, wl, steps=2, check_each_step=False, label="c3-mini")
 
 
-@pytest.mark.parametrize("variant", [0, 8, 16])
+@pytest.mark.parametrize("variant", EDGE_VARIANTS)
+def test_edge_walk_takes_the_plane_records_only_for_coplanar_rays(variant):
+    """Generic rays never leave the compact layout; rays coplanar with a mesh edge (axis-parallel
+    tracks in a Kuhn mesh, tracks inside a face plane) are finished on the plane records and still
+    match the oracle element for element (walk_compact.cuh)."""
+    coords, t2v, wl = box_case((6, 6, 5), 20_000)
+    eng, orc = gpu_engine(variant)(coords, t2v, wl.n), OraclePumiTally(coords, t2v, wl.n)
+    run_workload(eng, orc, wl, steps=3, label=f"generic v{variant}")
+    assert eng.stats()["plane_fallbacks"] == 0
+    deg = edge_case_scenario(gpu_engine(variant))
+    assert deg.stats()["plane_fallbacks"] > 0
+    golden = golden_scenario(gpu_engine(variant))  # T1: axis-parallel tracks through the 6-tet cube
+    assert golden.stats()["plane_fallbacks"] > 0
+
+
+@pytest.mark.parametrize("variant", [0, 8, 16, 20, 21])
 def test_chunked_upload_pipeline_equals_single_range(variant):
     """Host-pointer path cut into many upload/compute ranges (the binned variant bins each range)."""
     coords, t2v, wl = box_case((6, 6, 5), 50_000)

@@ -14,19 +14,20 @@ from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, tet_v
 from pumiumtally_b200.workload import SyntheticWorkload
 from test_oracle_golden import check_c1_fixture, golden_scenario
 
-SEED = [False, True]
+SEED = [pytest.param(dict(seed_grid=False), id="planes"), pytest.param(dict(seed_grid=True), id="planes-seeded"),
+        pytest.param(dict(layout="edge"), id="edge"), pytest.param(dict(seed_grid=True, layout="edge"), id="edge-seeded")]
 
 
 @pytest.mark.parametrize("seed", SEED)
 def test_reference_known_answers_device_logic(seed):
-    eng = golden_scenario(lambda c, t, n: HostEmulTally(c, t, n, seed_grid=seed))
+    eng = golden_scenario(lambda c, t, n: HostEmulTally(c, t, n, **seed))
     st = eng.stats()
     assert st["lost"] == 0 and st["tracks"] == 7 and st["segments"] == 18
 
 
 @pytest.mark.parametrize("seed", SEED)
 def test_device_logic_matches_committed_c1_fixture(seed):
-    eng, segs, tracks = check_c1_fixture(lambda c, t, n: HostEmulTally(c, t, n, seed_grid=seed))
+    eng, segs, tracks = check_c1_fixture(lambda c, t, n: HostEmulTally(c, t, n, **seed))
     assert eng.stats()["segments"] == segs and eng.stats()["tracks"] == tracks
 
 
@@ -148,13 +149,13 @@ def test_seed_grid_covers_a_box_mesh():
 def test_config_c1_parity(seed):
     """BASELINE.json configs[0]: ~1k-tet cube, 10k particles (plumbing config)."""
     coords, t2v, wl = box_case((6, 6, 5), 10_000)
-    eng = HostEmulTally(coords, t2v, wl.n, seed_grid=seed)
+    eng = HostEmulTally(coords, t2v, wl.n, **seed)
     orc = OraclePumiTally(coords, t2v, wl.n)
     run_workload(eng, orc, wl, steps=4, label="c1")
     st = eng.stats()
     assert st["segments"] == orc.n_segments and st["tracks"] == orc.n_tracks and st["lost"] == 0
-    if seed:  # the seeded walks are the point: far fewer tally-off crossings than the reference walk
-        plain = HostEmulTally(coords, t2v, wl.n)
+    if seed.get("seed_grid"):  # the seeded walks are the point: far fewer tally-off crossings than the reference walk
+        plain = HostEmulTally(coords, t2v, wl.n, layout=seed.get("layout", "planes"))
         wl2 = SyntheticWorkload(box=(6.0, 6.0, 5.0), num_particles=wl.n)
         run_workload(plain, OraclePumiTally(coords, t2v, wl.n), wl2, steps=4, check_each_step=False)
         assert st["relocations"] < 0.6 * plain.stats()["relocations"]
@@ -171,7 +172,7 @@ def test_unstructured_parity(mesh, seed):
         box = (1.0, 1.0, 1.0)
     n = 4000
     wl = SyntheticWorkload(box=box, num_particles=n, mean_length=0.5 * min(box), seed=3)
-    eng, orc = HostEmulTally(c, t, n, seed_grid=seed), OraclePumiTally(c, t, n)
+    eng, orc = HostEmulTally(c, t, n, **seed), OraclePumiTally(c, t, n)
     run_workload(eng, orc, wl, steps=3, label=mesh)
     assert eng.stats()["segments"] == orc.n_segments
 
@@ -180,14 +181,14 @@ def test_unstructured_parity(mesh, seed):
 def test_long_axial_tracks(seed):
     """Config c4 in miniature: forward-peaked tracks crossing many tets."""
     coords, t2v, wl = box_case((4, 4, 40), 1500, mean_length=60.0, mu_min=0.9)
-    eng, orc = HostEmulTally(coords, t2v, wl.n, seed_grid=seed), OraclePumiTally(coords, t2v, wl.n)
+    eng, orc = HostEmulTally(coords, t2v, wl.n, **seed), OraclePumiTally(coords, t2v, wl.n)
     run_workload(eng, orc, wl, steps=2, label="c4-mini")
     assert eng.stats()["segments"] / max(eng.stats()["tracks"], 1) > 15
 
 
 @pytest.mark.parametrize("seed", SEED)
 def test_edge_cases(seed):
-    edge_case_scenario(lambda c, t, n: HostEmulTally(c, t, n, seed_grid=seed))
+    edge_case_scenario(lambda c, t, n: HostEmulTally(c, t, n, **seed))
 
 
 @pytest.mark.parametrize("seed", SEED)
@@ -198,7 +199,7 @@ def test_out_of_mesh_origin_falls_back_to_reference_walk(seed):
     n = 64
     rng = np.random.default_rng(5)
     init = rng.uniform(0.2, 3.8, size=(n, 3))
-    eng, orc = HostEmulTally(coords, t2v, n, seed_grid=seed), OraclePumiTally(coords, t2v, n)
+    eng, orc = HostEmulTally(coords, t2v, n, **seed), OraclePumiTally(coords, t2v, n)
     for e in (eng, orc):
         e.CopyInitialPosition(init.reshape(-1).copy())
     origin = rng.uniform(-3.0, 7.0, size=(n, 3))  # many outside the box, far from the old position
@@ -211,3 +212,21 @@ def test_out_of_mesh_origin_falls_back_to_reference_walk(seed):
     np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
     np.testing.assert_allclose(eng.positions, orc.positions, atol=1e-12)
     assert eng.stats()["lost"] == 0
+
+
+def test_edge_walk_uses_plane_records_only_for_coplanar_rays():
+    """walk_compact.cuh: an edge function is exactly zero only when the ray is coplanar with a mesh
+    edge.  Random tracks never are; the axis-parallel tracks of the reference fixture and of the
+    edge-case scenario are, and finish on the plane records with oracle-identical results."""
+    coords, t2v, wl = box_case((6, 6, 5), 10_000)
+    eng = HostEmulTally(coords, t2v, wl.n, layout="edge", seed_grid=True)
+    run_workload(eng, OraclePumiTally(coords, t2v, wl.n), wl, steps=3, label="generic")
+    assert eng.degenerate_rays == 0
+    c, t = delaunay_box(300)
+    n = 5000
+    wl = SyntheticWorkload(box=(1.0, 1.0, 1.0), num_particles=n, mean_length=0.4, seed=5)
+    eng = HostEmulTally(c, t, n, layout="edge")
+    run_workload(eng, OraclePumiTally(c, t, n), wl, steps=3, label="delaunay")
+    assert eng.degenerate_rays == 0
+    assert edge_case_scenario(lambda c, t, n: HostEmulTally(c, t, n, layout="edge")).degenerate_rays > 0
+    assert golden_scenario(lambda c, t, n: HostEmulTally(c, t, n, layout="edge")).degenerate_rays > 0

@@ -474,7 +474,7 @@ int Engine::set_option(const std::string &name, int64_t v) {
   if (name == "variant") {
     if (v == -1) { variant_ = choose_variant(); return 0; }  // automatic
     if (v < 0 || v >= kNumVariants) return 1;
-    if ((v == kVariantEdge || v == kVariantEdgeOcc6 || v == kVariantEdgeGather) && !d_links_) return 1;
+    if ((v >= kVariantEdge && v <= kVariantEdgeOcc6) && !d_links_) return 1;
     variant_ = int(v);
   } else if (name == "block") {
     if (v != 64 && v != 128 && v != 256) return 1;

@@ -13,13 +13,13 @@
 // u . n (n = the triangle's normal in that orientation) and the crossing parameter is
 //     t = P_i . (P_j x P_k) / (m(i,j) + m(j,k) + m(k,i)).
 // The walk keeps the face it entered through as an ordered triple (a,b,c) with all three edge
-// functions >= 0.  In the next tet only the three edge functions of the NEW vertex d are
+// functions > 0.  In the next tet only the three edge functions of the NEW vertex d are
 // evaluated, s_r = m(d, r) = (u x P_d) . P_r, and their signs alone pick the exit face:
 //     (a,b,d) iff s_a >= 0 > s_b      (b,c,d) iff s_b >= 0 > s_c      (c,a,d) iff s_c >= 0 > s_a
-// The exit triple inherits one edge function from the entry triple and two from the s_r, so every
-// edge function is computed once per ray and all tets around that edge use the same value: the
-// walk is watertight by construction, with no canonical vertex ordering and no division except
-// the one for t.  This replaces the arithmetic of the reference's external tracer
+// The exit triple inherits the sign of one edge function from the entry triple and of two from
+// the s_r, so every edge is classified once per ray and all tets around it see the same answer:
+// the walk is watertight by construction, with no canonical vertex ordering and no division
+// except the one for t.  This replaces the arithmetic of the reference's external tracer
 // (PumiTallyImpl.cpp:454; contract PumiTallyImpl.h:74-85) like the plane form does; tally,
 // clipping and advance are the shared advance() of walk_core.cuh.
 //
@@ -42,8 +42,8 @@ namespace ptb {
 // roles in the current tet, 2 bits each (roles 0,1,2 = entry triple a,b,c; role 3 = d), or -1
 // on the first tet of a ray.
 struct EdgeRay {
-  double ax, ay, az, bx, by, bz, cx, cy, cz;  // entry-face vertices minus the ray origin
-  double mab, mbc, mca;                       // their edge functions, all >= 0
+  double ax, ay, az, bx, by, bz, cx, cy, cz;  // entry-face vertices minus the ray origin, ordered
+                                              // so that their three edge functions are > 0
   int32_t dv;                                 // vertex id of role 3 in the current tet
 };
 
@@ -66,12 +66,18 @@ PTB_HD void cross_face(const TetLinks &L, int k, int s0, int s1, int s2, int32_t
   dv = (int32_t)(b & kVertMask);
 }
 
-// Crossing parameter of the exit triple now held in g (its three edge functions are > 0).
-PTB_HD double edge_exit_parameter(const EdgeRay &g) {
-  const double den = g.mab + g.mbc + g.mca;
-  const double wx = g.by * g.cz - g.bz * g.cy, wy = g.bz * g.cx - g.bx * g.cz, wz = g.bx * g.cy - g.by * g.cx;
-  const double num = g.ax * wx + g.ay * wy + g.az * wz;
-  return (num < den) ? num / den : __builtin_huge_val();
+// Crossing parameter of the exit triple now held in g: with n = (b-a) x (c-a), t = n.a / n.u
+// (n.u = the sum of the triple's edge functions > 0; n.a = a . (b x c)).  Only the signs of the
+// edge functions steer the walk, so t needs no agreement between neighbouring tets.  Returns
+// false when rounding left n.u <= 0 (face parallel to the ray within rounding).
+PTB_HD bool edge_exit_parameter(const Ray &r, const EdgeRay &g, double &texit) {
+  const double e1x = g.bx - g.ax, e1y = g.by - g.ay, e1z = g.bz - g.az;
+  const double e2x = g.cx - g.ax, e2y = g.cy - g.ay, e2z = g.cz - g.az;
+  const double nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
+  const double den = nx * r.ux + ny * r.uy + nz * r.uz;
+  const double num = nx * g.ax + ny * g.ay + nz * g.az;
+  texit = (num < den) ? num / den : __builtin_huge_val();
+  return den > 0.0;
 }
 
 // Tet after the first: vertex d = (dx,dy,dz) is the only new one.
@@ -91,20 +97,19 @@ PTB_HD bool edge_step(const Ray &r, EdgeRay &g, const TetLinks &L, double dx, do
   int s0 = e & 3, s1 = (e >> 2) & 3, s2 = (e >> 4) & 3;
   const int s3 = (e >> 6) & 3;
   int k;
-  if (z == 2) {         // (a,b,d)
+  EdgeRay h = g;
+  if (z == 2) {         // (a,b,d): edge functions m(a,b) inherited, m(b,d) = -sb, m(d,a) = sa
     k = s2; s2 = s3;
-    g.cx = px; g.cy = py; g.cz = pz;
-    g.mbc = -sb; g.mca = sa;
-  } else if (z == 0) {  // (d,b,c)
+    h.cx = px; h.cy = py; h.cz = pz;
+  } else if (z == 0) {  // (d,b,c): m(d,b) = sb, m(b,c) inherited, m(c,d) = -sc
     k = s0; s0 = s3;
-    g.ax = px; g.ay = py; g.az = pz;
-    g.mab = sb; g.mca = -sc;
-  } else {              // (a,d,c)
+    h.ax = px; h.ay = py; h.az = pz;
+  } else {              // (a,d,c): m(a,d) = -sa, m(d,c) = sc, m(c,a) inherited
     k = s1; s1 = s3;
-    g.bx = px; g.by = py; g.bz = pz;
-    g.mab = -sa; g.mbc = sc;
+    h.bx = px; h.by = py; h.bz = pz;
   }
-  texit = edge_exit_parameter(g);
+  if (!edge_exit_parameter(r, h, texit)) return false;
+  g = h;
   cross_face(L, k, s0, s1, s2, next, roles, g.dv);
   return true;
 }
@@ -128,17 +133,17 @@ PTB_UNROLL
   // is the one whose edge functions are all > 0 (the entry face has them all < 0).  No such face:
   // a zero (coplanar edge, u = 0) or a start point outside the tet by rounding -> planes.
   int ia, ib, ic, f;
-  if (m12 > 0.0 && m23 > 0.0 && m13 < 0.0)      { f = 0; ia = 1; ib = 2; ic = 3; g.mab = m12; g.mbc = m23; g.mca = -m13; }
-  else if (m03 > 0.0 && m23 < 0.0 && m02 < 0.0) { f = 1; ia = 0; ib = 3; ic = 2; g.mab = m03; g.mbc = -m23; g.mca = -m02; }
-  else if (m01 > 0.0 && m13 > 0.0 && m03 < 0.0) { f = 2; ia = 0; ib = 1; ic = 3; g.mab = m01; g.mbc = m13; g.mca = -m03; }
-  else if (m02 > 0.0 && m12 < 0.0 && m01 < 0.0) { f = 3; ia = 0; ib = 2; ic = 1; g.mab = m02; g.mbc = -m12; g.mca = -m01; }
+  if (m12 > 0.0 && m23 > 0.0 && m13 < 0.0)      { f = 0; ia = 1; ib = 2; ic = 3; }
+  else if (m03 > 0.0 && m23 < 0.0 && m02 < 0.0) { f = 1; ia = 0; ib = 3; ic = 2; }
+  else if (m01 > 0.0 && m13 > 0.0 && m03 < 0.0) { f = 2; ia = 0; ib = 1; ic = 3; }
+  else if (m02 > 0.0 && m12 < 0.0 && m01 < 0.0) { f = 3; ia = 0; ib = 2; ic = 1; }
   else return false;
   if (m01 == 0.0 || m02 == 0.0 || m03 == 0.0 || m12 == 0.0 || m13 == 0.0 || m23 == 0.0) return false;
   auto pick = [&](int i, int d) { return i == 0 ? p[0][d] : (i == 1 ? p[1][d] : (i == 2 ? p[2][d] : p[3][d])); };
   g.ax = pick(ia, 0); g.ay = pick(ia, 1); g.az = pick(ia, 2);
   g.bx = pick(ib, 0); g.by = pick(ib, 1); g.bz = pick(ib, 2);
   g.cx = pick(ic, 0); g.cy = pick(ic, 1); g.cz = pick(ic, 2);
-  texit = edge_exit_parameter(g);
+  if (!edge_exit_parameter(r, g, texit)) return false;
   cross_face(L, f, ia, ib, ic, next, roles, g.dv);
   return true;
 }

@@ -298,9 +298,17 @@ PTB_HD void begin_particle(const WalkParams &P, int i, Ray &r, Counters &c, bool
 }
 
 // The current ray ended (target reached, hull hit, or iteration limit).
+// kReloadTarget: the caller does not keep Ray::tx,ty,tz alive in registers (the compact-layout
+// kernel); the target is read back from the caller's array, where it came from: dest[] in the
+// tally phase, origin[] in phase 1.  Same values, six registers fewer in the crossing loop.
+template <bool kReloadTarget = false>
 PTB_HD void end_ray(const WalkParams &P, int i, Ray &r, bool reached, double tnew, Counters &c,
                     bool writer) {
   double x, y, z;
+  if (kReloadTarget && (reached || r.stage == kStageSeed)) {
+    const double *t = (r.stage == kStageTally ? P.dest : P.origin) + 3 * (size_t)i;
+    r.tx = PTB_LDG(t); r.ty = PTB_LDG(t + 1); r.tz = PTB_LDG(t + 2);
+  }
   if (r.stage == kStageSeed && !reached) {
     // the target is not reachable from the seed inside the mesh (it lies outside the hull):
     // redo phase 1 exactly as the reference does, from the particle's stored position
@@ -327,6 +335,7 @@ PTB_HD void end_ray(const WalkParams &P, int i, Ray &r, bool reached, double tne
 }
 
 // Functor body for one crossing, given the tracer's answer (texit, next).
+template <bool kReloadTarget = false>
 PTB_HD void advance(const WalkParams &P, int i, Ray &r, double texit, int32_t next, int32_t back,
                     Counters &c, bool writer) {
   const bool reached = !(texit < 1.0);  // last_exit == -1: destination inside this tet
@@ -344,7 +353,7 @@ PTB_HD void advance(const WalkParams &P, int i, Ray &r, double texit, int32_t ne
   const bool over = r.iters >= P.max_iters;
   if (reached || hull || over) {
     if (over && !reached && !hull && writer && r.stage != kStageSeed) c.lost++;
-    end_ray(P, i, r, reached, tnew, c, writer);
+    end_ray<kReloadTarget>(P, i, r, reached, tnew, c, writer);
   } else {
     r.e = next;  // UpdateCurrentElement (Impl.cpp:247-253)
     r.entry = back;

@@ -307,6 +307,13 @@ __device__ __forceinline__ uint64_t l2_policy_stream() {
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+// same value, created where it is used: keeps the policy out of the registers that stay live
+// across the crossing loop of the compact-layout kernel
+__device__ __forceinline__ uint64_t l2_policy_stream_now() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uint32_t bytes,
                                               uint32_t bar, uint64_t pol) {
   asm volatile(
@@ -432,51 +439,119 @@ __device__ __forceinline__ void ld256_b64(const void *p, uint64_t pol, unsigned 
 }
 
 // First tet of a ray, out of line: its register footprint (four vertices, six edge functions)
-// must not set the allocation of the per-crossing path.  Streams the TetStart line past the L2.
-__device__ __noinline__ bool edge_first_step(const TetStart *S, const Ray &r, EdgeRay &g, uint64_t strm,
-                                             double &texit, int32_t &next, int32_t &roles) {
-  unsigned long long w0, w1, w2, w3;
-  double v[12];
-  ld256_b64(&S->links, strm, w0, w1, w2, w3);
-  load_face<kFetchPolicy>(S->v, strm, v[0], v[1], v[2], v[3]);
-  load_face<kFetchPolicy>(S->v + 4, strm, v[4], v[5], v[6], v[7]);
-  load_face<kFetchPolicy>(S->v + 8, strm, v[8], v[9], v[10], v[11]);
+// must not set the allocation of the per-crossing path.  The TetStart line has already been
+// loaded by the caller (together with the other lanes' per-crossing loads, so the warp waits for
+// memory once per iteration); everything crosses the call by value.
+struct FirstOut {
+  EdgeRay g;
+  double texit;
+  int32_t next, roles, ok;
+};
+__device__ __noinline__ FirstOut edge_first_compute(double v0, double v1, double v2, double v3, double v4, double v5,
+                                                    double v6, double v7, double v8, double v9, double v10,
+                                                    double v11, unsigned long long w0, unsigned long long w1,
+                                                    unsigned long long w2, unsigned long long w3, double ox, double oy,
+                                                    double oz, double ux, double uy, double uz) {
+  const double v[12] = {v0, v1, v2, v3, v4, v5, v6, v7, v8, v9, v10, v11};
   TetLinks L;
   L.nbr[0] = (uint32_t)w0; L.nbr[1] = (uint32_t)(w0 >> 32); L.nbr[2] = (uint32_t)w1; L.nbr[3] = (uint32_t)(w1 >> 32);
   L.opp[0] = (uint32_t)w2; L.opp[1] = (uint32_t)(w2 >> 32); L.opp[2] = (uint32_t)w3; L.opp[3] = (uint32_t)(w3 >> 32);
-  return edge_first(r, g, L, v, texit, next, roles);
+  Ray r;
+  r.ox = ox; r.oy = oy; r.oz = oz; r.ux = ux; r.uy = uy; r.uz = uz;
+  FirstOut o;
+  o.g.dv = 0;
+  o.texit = 0.0;
+  o.next = -1;
+  o.roles = 0;
+  o.ok = edge_first(r, o.g, L, v, o.texit, o.next, o.roles) ? 1 : 0;
+  return o;
 }
 
-// One crossing of the edge-function walk: the TetLinks sector of the current tet + the one new
-// vertex (keep policy; vertices also allocate in L1), both requested before either is used.
+// A ray that met a coplanar edge finishes on the plane records.  Out of line and by value for the
+// same reason as edge_first_step: rare, and its registers must not count against the crossing loop.
+struct PlaneOut {
+  double texit;
+  int32_t next, back;
+};
+__device__ __noinline__ PlaneOut plane_fallback_step(const TetRecord *tets, int32_t e, int32_t en, double ox,
+                                                     double oy, double oz, double ux, double uy, double uz) {
+  const uint64_t pol = l2_policy_stream_now();
+  ExitScan sc;
+  const double *rec = tets[e].d;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) {
+    if (f == en) continue;
+    double a, b, c, d;
+    load_face<kFetchPolicy>(rec + 4 * f, pol, a, b, c, d);
+    int32_t nb, bk;
+    face_payload(a, b, c, d, e, f, nb, bk);
+    scan_face(sc, a, b, c, d, nb, bk, ox, oy, oz, ux, uy, uz);
+  }
+  PlaneOut o;
+  o.texit = exit_parameter(sc);
+  o.next = sc.nbr;
+  o.back = sc.back;
+  return o;
+}
+
+// One crossing of the edge-function walk.  Requests first, for every lane at once: the TetLinks
+// sector of the current tet + the one new vertex (keep policy; vertices also allocate in L1), or on
+// the first tet of a ray the four sectors of its TetStart line (streaming policy).  `tgt` is the
+// lane's shared-memory slot holding the ray's target (Ray::tx,ty,tz are not kept in registers).
 __device__ __forceinline__ void edge_persist_step(const WalkParams &P, int my_i, Ray &r, EdgeRay &g,
-                                                  Counters &c, uint64_t keep, uint64_t strm) {
-  if (g.dv == kPlaneMode) {
-    plane_step<kFetchPolicy>(P, my_i, r, c, strm);
-    if (r.iters == 0) g.dv = 0;  // a new ray (phase 2 after phase 1) starts on the fast path again
-    return;
+                                                  Counters &c, uint64_t keep, double *tgt) {
+  const bool plane = g.dv == kPlaneMode;
+  const bool first = r.entry < 0;
+  unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+  double v[12];
+  if (!plane) {
+    const TetStart *S = P.starts + r.e;
+    const void *pa = first ? (const void *)&S->links : (const void *)(P.links + r.e);
+    const double *pb = first ? S->v : reinterpret_cast<const double *>(P.verts + g.dv);
+    const uint64_t pol = first ? l2_policy_stream_now() : keep;
+    ld256_b64(pa, pol, w0, w1, w2, w3);
+    load_face<kFetchPolicyL1>(pb, pol, v[0], v[1], v[2], v[3]);
+    if (first) {
+      load_face<kFetchPolicy>(S->v + 4, pol, v[4], v[5], v[6], v[7]);
+      load_face<kFetchPolicy>(S->v + 8, pol, v[8], v[9], v[10], v[11]);
+    }
   }
   double texit;
   int32_t next, roles;
-  bool ok;
-  if (r.entry < 0) {
-    ok = edge_first_step(P.starts + r.e, r, g, strm, texit, next, roles);
+  bool ok = true;
+  if (plane) {
+    const PlaneOut o = plane_fallback_step(P.tets, r.e, r.entry, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
+    texit = o.texit;
+    next = o.next;
+    roles = o.back;
+  } else if (first) {
+    const FirstOut o = edge_first_compute(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11],
+                                          w0, w1, w2, w3, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
+    g = o.g;
+    texit = o.texit;
+    next = o.next;
+    roles = o.roles;
+    ok = o.ok != 0;
   } else {
-    unsigned long long w0, w1, w2, w3;
-    double dx, dy, dz, dpad;
-    ld256_b64(P.links + r.e, keep, w0, w1, w2, w3);
-    load_face<kFetchPolicyL1>(reinterpret_cast<const double *>(P.verts + g.dv), keep, dx, dy, dz, dpad);
     TetLinks L;
     L.nbr[0] = (uint32_t)w0; L.nbr[1] = (uint32_t)(w0 >> 32); L.nbr[2] = (uint32_t)w1; L.nbr[3] = (uint32_t)(w1 >> 32);
     L.opp[0] = (uint32_t)w2; L.opp[1] = (uint32_t)(w2 >> 32); L.opp[2] = (uint32_t)w3; L.opp[3] = (uint32_t)(w3 >> 32);
-    ok = edge_step(r, g, L, dx, dy, dz, texit, next, roles);
+    ok = edge_step(r, g, L, v[0], v[1], v[2], texit, next, roles);
   }
   if (ok) {
+    // the ray ends in this step (reached / hull / iteration limit): end_ray() needs its target
+    if (!(texit < 1.0) || next < 0 || r.iters + 1 >= P.max_iters) {
+      r.tx = tgt[0]; r.ty = tgt[1]; r.tz = tgt[2];
+    }
     advance(P, my_i, r, texit, next, roles, c, true);
+    if (r.iters == 0 && r.stage != kStageDone) {  // a new ray (phase 2 after phase 1)
+      tgt[0] = r.tx; tgt[1] = r.ty; tgt[2] = r.tz;
+      if (plane) g.dv = 0;  // it starts on the fast path again
+    }
   } else {  // coplanar edge: redo this tet, and the rest of the ray, with the planes
     g.dv = kPlaneMode;
     r.entry = -1;
-    c.fallbacks++;
+    atomicAdd(&P.stats->fallbacks, 1ull);
   }
 }
 
@@ -493,6 +568,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
   __shared__ ParticleStage stages[WARPS][2];
   __shared__ __align__(8) unsigned long long bars[WARPS][3];
   __shared__ __align__(128) unsigned char rows[kRows ? WARPS : 1][kRows ? 32 * kRowBytes : 16];
+  constexpr bool kEdge = FETCH == kFetchEdge;
+  __shared__ double targets[kEdge ? BLOCK : 1][3];  // compact layout: each lane's ray target
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t bar0 = smem_u32(&bars[warp][0]);
   const uint32_t bar_row = bar0 + 16;
@@ -506,7 +583,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
   }
   __syncwarp();
   const uint64_t keep = FETCH != kFetchPlain ? l2_policy_keep() : 0;
-  const uint64_t strm = (FETCH != kFetchPlain || GATHER) ? l2_policy_stream() : 0;
+  const uint64_t strm = (FETCH == kFetchEdge) ? 0 : ((FETCH != kFetchPlain || GATHER) ? l2_policy_stream() : 0);
   const int total = GATHER ? (int)__ldg(P.work_count) : P.end - P.begin;
   const int nchunks = (total + kChunk - 1) / kChunk;
   // Gather mode: a ticket is a run of kClaimRun chunks = 64 particles whose ids sit in two
@@ -529,11 +606,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
     if constexpr (GATHER) {
       const int k = chunk - run_base;  // chunk's position in the current ticket (warp-uniform)
       const int id = __shfl_sync(0xffffffffu, (k >> 1) ? ids1 : ids0, ((k & 1) << 4) | (lane & 15));
-      stage_gather(P, id, min(kChunk, total - chunk * kChunk), st, bar, lane, strm);
+      stage_gather(P, id, min(kChunk, total - chunk * kChunk), st, bar, lane,
+                   FETCH == kFetchEdge ? l2_policy_stream_now() : strm);
     } else if constexpr (FETCH == kFetchPlain) {
       stage_load(P, chunk, st, bar, lane);
     } else {
-      stage_load_hint(P, chunk, st, bar, lane, strm);
+      stage_load_hint(P, chunk, st, bar, lane, FETCH == kFetchEdge ? l2_policy_stream_now() : strm);
     }
   };
   auto claim = [&]() -> int {
@@ -580,7 +658,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
       if (r.stage == kStageDone && slot < cur_count) {
         my_i = GATHER ? stages[warp][cur].id[slot] : P.begin + chunk_cur * kChunk + slot;
         begin_from_stage(P, &stages[warp][cur], slot, r, c);
-        if constexpr (FETCH == kFetchEdge) g.dv = 0;
+        if constexpr (FETCH == kFetchEdge) {
+          g.dv = 0;
+          if (r.stage != kStageDone) {
+            targets[threadIdx.x][0] = r.tx; targets[threadIdx.x][1] = r.ty; targets[threadIdx.x][2] = r.tz;
+          }
+        }
       }
       __syncwarp();
       cursor += __popc(idle);
@@ -615,7 +698,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
     }
     if (r.stage != kStageDone) {
       if constexpr (FETCH == kFetchEdge) {
-        edge_persist_step(P, my_i, r, g, c, keep, strm);
+        edge_persist_step(P, my_i, r, g, c, keep, &targets[kEdge ? threadIdx.x : 0][0]);
       } else if constexpr (kRows) {
         ExitScan sc;
         double raw[16];
@@ -744,13 +827,16 @@ cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_
       return launch_persist<128, kFetchPolicy, 7, 8>(p, n, stream);
     case kVariantEdge:
       if (!p.links) return cudaErrorInvalidValue;
+      return launch_persist<128, kFetchEdge, 4, 8, false, 40>(p, n, stream);
+    case kVariantEdgeOcc5:
+      if (!p.links) return cudaErrorInvalidValue;
       return launch_persist<128, kFetchEdge, 5, 8, false, 40>(p, n, stream);
     case kVariantEdgeOcc6:
       if (!p.links) return cudaErrorInvalidValue;
       return launch_persist<128, kFetchEdge, 6, 8, false, 40>(p, n, stream);
     case kVariantEdgeGather:
       if (!p.links) return cudaErrorInvalidValue;
-      return launch_persist<128, kFetchEdge, 5, 8, true, 40>(p, n, stream);
+      return launch_persist<128, kFetchEdge, 4, 8, true, 40>(p, n, stream);
     default:
       return cudaErrorInvalidValue;
   }

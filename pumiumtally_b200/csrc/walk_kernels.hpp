@@ -26,8 +26,9 @@ enum WalkVariant : int {
   kVariantPersistGatherPlain = 17,   // 15 with plain tet loads (no L2 policy)
   kVariantEdge = 20,        // compact layout + edge-function exit test (walk_compact.cuh), streaming order
   kVariantEdgeGather = 21,  // 20 on spatially binned particles
-  kVariantEdgeOcc6 = 22,    // 20 compiled for 6 resident blocks (80 registers, a few spills)
-  kNumVariants = 23
+  kVariantEdgeOcc5 = 22,    // 20 compiled for 5 resident blocks (96 registers, a few spills)
+  kVariantEdgeOcc6 = 23,    // 20 compiled for 6 resident blocks (80 registers, more spills)
+  kNumVariants = 24
 };
 
 

@@ -17,9 +17,9 @@ from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
 from test_oracle_golden import check_c1_fixture, golden_scenario
 
 pytestmark = pytest.mark.gpu
-VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 13, 15, 16, 17, 20, 21, 22]
+VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 13, 15, 16, 17, 20, 21, 22, 23]
 BIG_VARIANTS = [0, 6, 8, 16, 20, 21]
-EDGE_VARIANTS = [20, 21, 22]  # compact layout + edge-function exit test
+EDGE_VARIANTS = [20, 21, 22, 23]  # compact layout + edge-function exit test
 
 
 def gpu_engine(variant, block=128, chunk=None, seed_grid=True):

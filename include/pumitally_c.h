@@ -100,7 +100,10 @@ int pumitally_set_output_name(pumitally_engine *e, const char *filename);
 /* Options: "variant" (-1 = the engine picks the walk kernel from the mesh size, the default),
  * "block", "chunk", "seed_grid", "morton", "claim_run", and "register_host" (1 = page-lock the
  * caller's pageable buffers with cudaHostRegister the first time they are seen; also enabled by
- * the environment variable PUMITALLY_REGISTER_HOST=1). */
+ * the environment variable PUMITALLY_REGISTER_HOST=1), "delta_upload" (0 = off, the default;
+ * 1 = send only the origins that differ from the previous call's destinations, with a self-check
+ * that switches it off when the host-side comparison costs more than it saves; 2 = always),
+ * "delta_threads". */
 int pumitally_set_option(pumitally_engine *e, const char *name, int64_t value);
 int64_t pumitally_get_option(const pumitally_engine *e, const char *name);
 

@@ -1,7 +1,10 @@
 // Engine: device state + batch orchestration (see engine.hpp).
 #include "engine.hpp"
 
+#include <omp.h>
+
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -120,6 +123,8 @@ Engine::~Engine() {
   for (auto &t : timers_free_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto &t : timers_busy_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto &e : chunk_events_) cudaEventDestroy(e);
+  if (h_patch_) cudaFreeHost(h_patch_);
+  cudaFree(d_patch_);
   cudaFree(d_links_); cudaFree(d_verts_); cudaFree(d_starts_);
   cudaFree(d_tets_); cudaFree(d_flux_); cudaFree(d_volume_); cudaFree(d_scratch_);
   cudaFree(d_state_);
@@ -303,9 +308,64 @@ int Engine::copy_initial_position_device(const double *d_xyz, int32_t size, cuda
   return 0;
 }
 
-// MoveToNextLocation (PumiTallyImpl.cpp:66-149), host pointers.  The four
-// uploads are cut into particle ranges; range k is walked while range k+1 is
-// still on the wire.
+constexpr int kPatchSlots = 4;          // pinned patch lists in flight
+constexpr double kPatchMaxFraction = 0.4;  // above this share of changed origins a chunk is sent whole
+
+int Engine::ensure_patch_buffers(int nchunks) {
+  const size_t cap = size_t(double(std::min<int64_t>(chunk_, n_)) * kPatchMaxFraction) + 1;
+  if (h_patch_ && patch_cap_ == cap && patch_chunks_ >= nchunks) return 0;
+  PTB_CUDA_OK(cudaDeviceSynchronize());
+  if (h_patch_) cudaFreeHost(h_patch_);
+  if (d_patch_) cudaFree(d_patch_);
+  h_patch_ = nullptr;
+  d_patch_ = nullptr;
+  patch_cap_ = cap;
+  patch_chunks_ = nchunks;
+  PTB_CUDA_OK(cudaHostAlloc(reinterpret_cast<void **>(&h_patch_), cap * kPatchSlots * sizeof(PatchEntry), cudaHostAllocDefault));
+  PTB_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&d_patch_), cap * size_t(nchunks) * sizeof(PatchEntry)));
+  if (patch_threads_ <= 0) patch_threads_ = std::max(1, std::min(omp_get_max_threads(), 32));
+  return 0;
+}
+
+// Particles of [b,e) whose origin differs (bitwise) from the previous move's destination ->
+// patch list; the mirror then takes this move's destinations.  One pass over the three arrays:
+// every thread collects its sub-range's entries privately, then the (short) lists are packed
+// into the pinned slot.  Returns the list length, or -1 when it would exceed the chunk's
+// capacity (the caller then uploads the origin slice whole).
+int Engine::build_patch(const double *origin, const double *dest, int32_t b, int32_t e, PatchEntry *out) {
+  const int nt = patch_threads_;
+  if (int(patch_tls_.size()) != nt) patch_tls_.assign(size_t(nt), std::vector<PatchEntry>());
+  std::vector<int64_t> first(size_t(nt) + 1, 0);
+  double *mir = mirror_.data();
+#pragma omp parallel num_threads(nt)
+  {
+    const int t = omp_get_thread_num();
+    const int64_t len = int64_t(e) - b;
+    const int64_t lo = b + len * t / nt, hi = b + len * (t + 1) / nt;
+    std::vector<PatchEntry> &mine = patch_tls_[size_t(t)];
+    mine.clear();
+    for (int64_t i = lo; i < hi; ++i) {
+      uint64_t a[3], m[3];
+      std::memcpy(a, origin + 3 * i, 24);
+      std::memcpy(m, mir + 3 * i, 24);
+      if (((a[0] ^ m[0]) | (a[1] ^ m[1]) | (a[2] ^ m[2])) != 0)
+        mine.push_back(PatchEntry{origin[3 * i], origin[3 * i + 1], origin[3 * i + 2], int32_t(i), 0});
+      std::memcpy(mir + 3 * i, dest + 3 * i, 24);
+    }
+    first[size_t(t) + 1] = int64_t(mine.size());
+  }
+  for (int k = 0; k < nt; ++k) first[size_t(k) + 1] += first[size_t(k)];
+  if (first[size_t(nt)] > int64_t(patch_cap_)) return -1;
+  for (int k = 0; k < nt; ++k)
+    if (!patch_tls_[size_t(k)].empty())
+      std::memcpy(out + first[size_t(k)], patch_tls_[size_t(k)].data(), patch_tls_[size_t(k)].size() * sizeof(PatchEntry));
+  return int(first[size_t(nt)]);
+}
+
+// MoveToNextLocation (PumiTallyImpl.cpp:66-149), host pointers.  The uploads are cut into
+// particle ranges; range k is walked while range k+1 is still on the wire.  With delta upload the
+// origin array is not sent: the device's copy of the previous destinations becomes the origin
+// array and only the origins that changed are patched in (see engine.hpp).
 int Engine::move_to_next_location(const double *origin, const double *dest, int8_t *flying,
                                   const double *weights, int32_t size) {
   if (int64_t(size) != 3 * int64_t(n_)) {
@@ -328,23 +388,77 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
     PTB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     chunk_events_.push_back(e);
   }
+  const bool delta = delta_upload_ && mirror_valid_ && n_ > 0;
+  mirror_valid_ = false;  // until this move has gone through completely
+  if (delta_upload_ && n_ > 0) {
+    if (mirror_.size() != 3 * size_t(n_)) mirror_.resize(3 * size_t(n_));
+    if (ensure_patch_buffers(nchunks)) return 1;
+  }
   cudaEvent_t ev_prev_done = chunk_events_[nchunks], ev_fly = chunk_events_[nchunks + 1];
   // staging buffers are free once the previous move's kernels have finished
   PTB_CUDA_OK(cudaEventRecord(ev_prev_done, compute_));
   PTB_CUDA_OK(cudaStreamWaitEvent(copy_, ev_prev_done, 0));
+  // the previous destinations, still on the device, are this move's origins before patching
+  if (delta) std::swap(d_origin_, d_dest_);
   PTB_CUDA_OK(cudaMemcpyAsync(d_flying_, flying, size_t(n_), cudaMemcpyHostToDevice, copy_));
   PTB_CUDA_OK(cudaEventRecord(ev_fly, copy_));
+  double host_s = 0.0, sent = double(n_);
   for (int k = 0; k < nchunks; ++k) {
     const int32_t b = int32_t(int64_t(k) * chunk_), e = int32_t(std::min<int64_t>(n_, int64_t(b) + chunk_));
     const size_t cnt = size_t(e - b);
-    PTB_CUDA_OK(cudaMemcpyAsync(d_origin_ + 3 * size_t(b), origin + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+    int npatch = -1;
+    PatchEntry *hp = nullptr, *dp = nullptr;
+    if (delta) {
+      // the pinned slot is free once the copies of chunk k - kPatchSlots have been issued and done
+      if (k >= kPatchSlots) PTB_CUDA_OK(cudaEventSynchronize(chunk_events_[k - kPatchSlots]));
+      hp = h_patch_ + size_t(k % kPatchSlots) * patch_cap_;
+      dp = d_patch_ + size_t(k) * patch_cap_;
+      const auto t0 = std::chrono::steady_clock::now();
+      npatch = build_patch(origin, dest, b, e, hp);
+      host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (npatch < 0) {
+      PTB_CUDA_OK(cudaMemcpyAsync(d_origin_ + 3 * size_t(b), origin + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+      sent += 24.0 * double(cnt);
+    } else if (npatch > 0) {
+      PTB_CUDA_OK(cudaMemcpyAsync(dp, hp, size_t(npatch) * sizeof(PatchEntry), cudaMemcpyHostToDevice, copy_));
+      sent += double(npatch) * sizeof(PatchEntry);
+    }
     PTB_CUDA_OK(cudaMemcpyAsync(d_dest_ + 3 * size_t(b), dest + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
     PTB_CUDA_OK(cudaMemcpyAsync(d_weights_ + b, weights + b, cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+    sent += 32.0 * double(cnt);
     PTB_CUDA_OK(cudaEventRecord(chunk_events_[k], copy_));
     PTB_CUDA_OK(cudaStreamWaitEvent(compute_, chunk_events_[k], 0));
+    if (npatch > 0) PTB_CUDA_OK(launch_patch_origins(d_origin_, dp, npatch, compute_));
     if (launch_range(d_origin_, d_dest_, d_flying_, d_weights_, b, e, compute_, true)) return 1;
   }
-  h2d_bytes_ += double(n_) * (2 * 24 + 8 + 1);
+  h2d_bytes_ += sent;
+  if (delta_upload_ && n_ > 0) {
+    if (!delta) {  // first host move (or one after a device move): start the mirror
+      const auto t0 = std::chrono::steady_clock::now();
+      const int64_t total = 3 * int64_t(n_);
+#pragma omp parallel for num_threads(patch_threads_) schedule(static)
+      for (int64_t blk = 0; blk < (total + 65535) / 65536; ++blk) {
+        const int64_t lo = blk * 65536, hi = std::min<int64_t>(total, lo + 65536);
+        std::memcpy(mirror_.data() + lo, dest + lo, size_t(hi - lo) * sizeof(double));
+      }
+      host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      mirror_valid_ = true;
+    } else {
+      // self-check: if comparing costs the host more than the bytes it saves cost the link
+      // (many ranks sharing one memory system), fall back to plain uploads
+      delta_host_s_ = host_s;
+      delta_saved_bytes_ = double(n_) * 57.0 - sent;
+      const double saved_s = delta_saved_bytes_ / 50e9;
+      delta_strikes_ = (host_s > 1.5 * saved_s) ? delta_strikes_ + 1 : 0;
+      mirror_valid_ = true;
+      if (delta_strikes_ >= 3 && delta_auto_) {
+        delta_upload_ = false;
+        mirror_valid_ = false;
+        std::vector<double>().swap(mirror_);
+      }
+    }
+  }
   // reset the caller's flags once they are on the device (PumiTallyImpl.cpp:169-172)
   PTB_CUDA_OK(cudaEventSynchronize(ev_fly));
   if (n_) std::memset(flying, 0, size_t(n_));
@@ -363,6 +477,7 @@ int Engine::move_to_next_location_device(const double *d_origin, const double *d
   }
   PTB_CUDA_OK(cudaSetDevice(device_));
   collect_timers(false);
+  mirror_valid_ = false;  // the staging buffers no longer hold the previous host move's destinations
   if (launch_range(d_origin, d_dest, d_flying, d_weights, 0, n_, stream, true)) return 1;
   ++moves_;
   return 0;
@@ -467,6 +582,9 @@ int64_t Engine::get_option(const std::string &name) const {
   if (name == "block") return block_;
   if (name == "chunk") return chunk_;
   if (name == "seed_grid") return use_seed_grid_ ? 1 : 0;
+  if (name == "delta_upload") return delta_upload_ ? (delta_auto_ ? 1 : 2) : 0;
+  if (name == "delta_host_us") return int64_t(delta_host_s_ * 1e6);       // last move: host time spent comparing
+  if (name == "delta_saved_bytes") return int64_t(delta_saved_bytes_);   // last move: bytes not sent
   return -1;
 }
 
@@ -486,6 +604,13 @@ int Engine::set_option(const std::string &name, int64_t v) {
     use_seed_grid_ = v != 0;
   } else if (name == "register_host") {
     register_host_ = v != 0;
+  } else if (name == "delta_threads") {
+    if (v < 1 || v > 1024) return 1;
+    patch_threads_ = int(v);
+  } else if (name == "delta_upload") {  // 0 off, 1 on unless it stops paying (self-check), 2 always on
+    delta_upload_ = v != 0;
+    delta_auto_ = v != 2;
+    if (!delta_upload_) { mirror_valid_ = false; std::vector<double>().swap(mirror_); }
   } else if (name == "morton") {
     morton_ = v != 0;
   } else if (name == "claim_run") {

@@ -118,6 +118,29 @@ class Engine {
   bool register_host_ = false;
   double kernel_ms_ = 0.0, h2d_bytes_ = 0.0;
 
+  // Delta upload (host-pointer path).  A transport code's next origin is, for every particle that
+  // was not re-sourced, bit for bit the destination it passed in the previous call.  The device
+  // still holds those destinations (d_dest_ of the previous move), so only the origins that differ
+  // from the host-side mirror of the previous dest array travel over PCIe, as a patch list.
+  // OFF by default: on the B200 boxes measured, comparing 10 M origins against the mirror costs the
+  // host 11 ms (memory-bound, ~0.96 GB of traffic) to save 4 ms of PCIe time
+  // (profiles/r01/README.md); option "delta_upload" = 1 turns it on with a self-check that
+  // switches it off again when it does not pay, 2 forces it.
+  bool delta_upload_ = false;
+  bool mirror_valid_ = false;         // mirror_ == the dest array of the previous host move == d_dest_
+  std::vector<double> mirror_;        // [3N]
+  PatchEntry *h_patch_ = nullptr;     // pinned ring of kPatchSlots chunk-sized lists
+  PatchEntry *d_patch_ = nullptr;     // one list per chunk of a move
+  size_t patch_cap_ = 0;              // entries per chunk
+  int patch_chunks_ = 0;              // lists d_patch_ has room for
+  int patch_threads_ = 0;  // 0 = pick at first use
+  std::vector<std::vector<PatchEntry>> patch_tls_;
+  bool delta_auto_ = true;
+  double delta_host_s_ = 0.0, delta_saved_bytes_ = 0.0;  // last move: host time spent comparing, bytes not sent
+  int delta_strikes_ = 0;
+  int build_patch(const double *origin, const double *dest, int32_t b, int32_t e, PatchEntry *out);
+  int ensure_patch_buffers(int nchunks);
+
   // NCCL (resolved with dlopen at comm_init time)
   void *nccl_comm_ = nullptr;
   int rank_ = 0, nranks_ = 1;

@@ -187,6 +187,14 @@ PTB_HD void seed_point(const SeedGrid &g, int cx, int cy, int cz, double &x, dou
   z = fma(cz + 0.31830988618, g.h, g.z0);
 }
 
+// One entry of the origin patch list (host-pointer path, delta upload): particle idx starts this
+// move at (x,y,z) instead of at the previous move's destination.  32 bytes = one sector.
+struct alignas(32) PatchEntry {
+  double x, y, z;
+  int32_t idx;
+  int32_t pad;
+};
+
 // One launch = one particle range of one MoveToNextLocation / CopyInitialPosition.
 struct WalkParams {
   const TetRecord *tets;   // [E] packed records

@@ -773,6 +773,19 @@ __global__ void seed_finalize_kernel(const double *xyz, const ParticleState *sta
   }
 }
 
+// Delta upload of the host-pointer path: the origin array on the device starts as the previous
+// move's destinations; only the particles whose caller-side origin differs are patched.
+__global__ void patch_origins_kernel(double *origin, const PatchEntry *list, int32_t count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double x, y, z, w;
+  load_face_256(reinterpret_cast<const double *>(list + i), x, y, z, w);
+  const int32_t idx = (int32_t)((unsigned long long)__double_as_longlong(w) & 0xffffffffull);
+  origin[3 * (size_t)idx] = x;
+  origin[3 * (size_t)idx + 1] = y;
+  origin[3 * (size_t)idx + 2] = z;
+}
+
 // K13 (PumiTallyImpl.cpp:393-405) with volumes precomputed at mesh build.
 __global__ void normalize_kernel(const double *flux, const double *volume, double *out, int64_t n) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -859,6 +872,12 @@ cudaError_t launch_seed_points(const SeedGrid &g, double *xyz, cudaStream_t stre
 cudaError_t launch_seed_finalize(const double *xyz, const ParticleState *state, int32_t *cell_tet,
                                  int32_t ncell, cudaStream_t stream) {
   seed_finalize_kernel<<<(ncell + 255) / 256, 256, 0, stream>>>(xyz, state, cell_tet, ncell);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_patch_origins(double *origin, const PatchEntry *list, int32_t count, cudaStream_t stream) {
+  if (count <= 0) return cudaSuccess;
+  patch_origins_kernel<<<(count + 255) / 256, 256, 0, stream>>>(origin, list, count);
   return cudaGetLastError();
 }
 

@@ -42,6 +42,8 @@ cudaError_t launch_seed_finalize(const double *xyz, const ParticleState *state, 
                                  int32_t ncell, cudaStream_t stream);
 cudaError_t launch_init_particles(ParticleState *state, int32_t n, double cx, double cy, double cz,
                                   int32_t elem, cudaStream_t stream);
+// origin[3*idx..] = (x,y,z) for every entry of the patch list
+cudaError_t launch_patch_origins(double *origin, const PatchEntry *list, int32_t count, cudaStream_t stream);
 cudaError_t launch_normalize(const double *flux, const double *volume, double *out, int64_t n,
                              cudaStream_t stream);
 

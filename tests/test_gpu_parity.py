@@ -195,6 +195,68 @@ def test_chunked_upload_pipeline_equals_single_range(variant):
     assert a.stats()["segments"] == orc.n_segments
 
 
+@pytest.mark.parametrize("resample", [0.05, 0.9])
+def test_delta_upload_of_origins_is_exact(resample):
+    """Host-pointer path: origins equal to the previous call's destinations are not sent again
+    (the device still holds them); the changed ones travel as a patch list, or the whole slice when
+    most of a chunk changed.  Results must be identical to plain uploads, bytes must drop."""
+    coords, t2v = kuhn_box(6, 6, 5)
+    n = 40_000
+    rng = np.random.default_rng(11)
+    engs = []
+    for mode in (0, 2):
+        e = gpu_engine(8, chunk=8192)(coords, t2v, n)
+        e.set_option("delta_upload", mode)
+        engs.append(e)
+    orc = OraclePumiTally(coords, t2v, n)
+    pos = rng.uniform(0.05, 4.95, size=(n, 3))
+    for e in engs + [orc]:
+        e.CopyInitialPosition(pos.reshape(-1).copy())
+    prev_dest = pos.copy()
+    for step in range(4):
+        origin = prev_dest.copy()
+        moved = rng.random(n) < resample                 # re-sourced particles get a fresh origin
+        origin[moved] = rng.uniform(0.05, 4.95, size=(int(moved.sum()), 3))
+        # per-axis bounds: equal clipped coordinates would put particles exactly on a diagonal face plane
+        dest = np.clip(origin + rng.normal(0, 1.0, size=(n, 3)), [0.011, 0.013, 0.017], [4.987, 4.983, 4.979])
+        fly = (rng.random(n) < 0.9).astype(np.int8)
+        w = rng.uniform(0.5, 1.0, n)
+        for e in engs + [orc]:
+            e.MoveToNextLocation(origin.reshape(-1).copy(), dest.reshape(-1).copy(), fly.copy(), w.copy())
+        prev_dest = dest
+    off, on = engs
+    np.testing.assert_array_equal(on.elem_ids, off.elem_ids)
+    np.testing.assert_array_equal(on.positions, off.positions)
+    np.testing.assert_allclose(on.flux, off.flux, rtol=1e-12)
+    assert_flux_close(on.flux, orc.flux, "delta upload")
+    np.testing.assert_array_equal(on.elem_ids, orc.elem_ids)
+    assert on.stats()["h2d_bytes"] < (0.75 if resample < 0.4 else 1.01) * off.stats()["h2d_bytes"]
+
+
+def test_delta_upload_survives_interleaved_device_moves():
+    import torch
+
+    coords, t2v, wl = box_case((6, 6, 5), 20_000)
+    a, b = gpu_engine(8)(coords, t2v, wl.n), gpu_engine(8)(coords, t2v, wl.n)
+    a.set_option("delta_upload", 2)
+    b.set_option("delta_upload", 0)
+    init = wl.initial_positions().reshape(-1)
+    for e in (a, b):
+        e.CopyInitialPosition(init.copy())
+    for step in range(5):
+        o, d, f, w = wl.next_step()
+        for e in (a, b):
+            if step == 2:  # a device-pointer move in between invalidates the host-side mirror
+                t = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (o, d, f, w)]
+                e.move_device(*(x.data_ptr() for x in t), torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+            else:
+                e.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy())
+    np.testing.assert_array_equal(a.elem_ids, b.elem_ids)
+    np.testing.assert_array_equal(a.positions, b.positions)
+    np.testing.assert_allclose(a.flux, b.flux, rtol=1e-12)
+
+
 def test_pageable_buffers_with_host_registration():
     """register_host=1: the caller's pageable numpy buffers are page-locked once and reused."""
     coords, t2v, wl = box_case((6, 6, 5), 60_000)

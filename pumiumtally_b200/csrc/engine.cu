@@ -78,7 +78,6 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
 
   cuda_or_throw(cudaMemcpy(d_tets_, mesh_.records.data(), E * sizeof(TetRecord), cudaMemcpyHostToDevice), "upload tets");
   cuda_or_throw(cudaMemcpy(d_volume_, mesh_.volume.data(), E * sizeof(double), cudaMemcpyHostToDevice), "upload volume");
-  upload_compact();
   cuda_or_throw(cudaMemset(d_flux_, 0, E * sizeof(double)), "memset");
   cuda_or_throw(cudaMemset(d_stats_, 0, sizeof(DeviceStats)), "memset");
   // InitializeParticlesInElement0 (PumiTallyImpl.cpp:492-528)
@@ -95,12 +94,14 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
 }
 
 // Compact layout: TetLinks (32 B per tet) + vertices (32 B each) are what the edge-function walk
-// reads per crossing; TetStart lines (128 B per tet) are read once per ray.
-void Engine::upload_compact() {
+// reads per crossing; TetStart lines (128 B per tet) are read once per ray.  Built and uploaded the
+// first time one of the edge-walk variants is selected (the default kernels never touch it).
+bool Engine::upload_compact() {
+  if (d_links_) return true;
   std::string err;
   if (!mesh_.build_compact(&err)) {
     printf("[INFO] pumitally-b200: compact layout not built (%s); plane records only\n", err.c_str());
-    return;
+    return false;
   }
   const size_t E = size_t(mesh_.ntets), V = size_t(mesh_.nverts);
   std::vector<TetLinks> links(E);
@@ -113,6 +114,7 @@ void Engine::upload_compact() {
   cuda_or_throw(cudaMemcpy(d_starts_, mesh_.starts.data(), E * sizeof(TetStart), cudaMemcpyHostToDevice), "upload start lines");
   std::vector<TetStart>().swap(mesh_.starts);
   std::vector<VertexRec>().swap(mesh_.cverts);
+  return true;
 }
 
 Engine::~Engine() {
@@ -592,7 +594,15 @@ int Engine::set_option(const std::string &name, int64_t v) {
   if (name == "variant") {
     if (v == -1) { variant_ = choose_variant(); return 0; }  // automatic
     if (v < 0 || v >= kNumVariants) return 1;
-    if ((v >= kVariantEdge && v <= kVariantEdgeOcc6) && !d_links_) return 1;
+    if (v >= kVariantEdge && v <= kVariantEdgeOcc6) {
+      if (synchronize()) return 1;
+      try {
+        if (!upload_compact()) return 1;
+      } catch (const std::exception &ex) {
+        fprintf(stderr, "%s\n", ex.what());
+        return 1;
+      }
+    }
     variant_ = int(v);
   } else if (name == "block") {
     if (v != 64 && v != 128 && v != 256) return 1;

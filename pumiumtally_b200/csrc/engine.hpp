@@ -71,7 +71,7 @@ class Engine {
   void maybe_register(const void *p, size_t bytes);
   void collect_timers(bool wait);
   void build_seed_grid();
-  void upload_compact();
+  bool upload_compact();
 
   HostMesh mesh_;
   int32_t n_ = 0;

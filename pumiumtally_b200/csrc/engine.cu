@@ -584,6 +584,10 @@ int64_t Engine::get_option(const std::string &name) const {
   if (name == "block") return block_;
   if (name == "chunk") return chunk_;
   if (name == "seed_grid") return use_seed_grid_ ? 1 : 0;
+  if (name == "l2_fetch") {
+    size_t g = 0;
+    return cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity) == cudaSuccess ? int64_t(g) : -1;
+  }
   if (name == "delta_upload") return delta_upload_ ? (delta_auto_ ? 1 : 2) : 0;
   if (name == "delta_host_us") return int64_t(delta_host_s_ * 1e6);       // last move: host time spent comparing
   if (name == "delta_saved_bytes") return int64_t(delta_saved_bytes_);   // last move: bytes not sent
@@ -614,6 +618,9 @@ int Engine::set_option(const std::string &name, int64_t v) {
     use_seed_grid_ = v != 0;
   } else if (name == "register_host") {
     register_host_ = v != 0;
+  } else if (name == "l2_fetch") {  // bytes an L2 miss fetches from DRAM: 32, 64 or 128 (device-wide limit)
+    if (v != 32 && v != 64 && v != 128) return 1;
+    if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(v)) != cudaSuccess) { cudaGetLastError(); return 1; }
   } else if (name == "delta_threads") {
     if (v < 1 || v > 1024) return 1;
     patch_threads_ = int(v);

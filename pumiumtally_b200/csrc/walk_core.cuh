@@ -27,7 +27,15 @@
 
 #if defined(__CUDA_ARCH__)
 #define PTB_LDG(p) __ldg(p)
-#define PTB_TALLY_ADD(ptr, v) atomicAdd((ptr), (v))  // RED.E.ADD.F64 (Kokkos::atomic_add, Impl.cpp:376)
+// RED.E.ADD.F64 (Kokkos::atomic_add, Impl.cpp:376) carrying the same L2 evict_last priority as
+// the tet records: with the default priority the (small, extremely hot) flux lines are the first
+// victims of the evict_last tet stream and every second reduction misses in L2.
+__device__ __forceinline__ void tally_add(double *ptr, double v) {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(ptr), "d"(v), "l"(pol) : "memory");
+}
+#define PTB_TALLY_ADD(ptr, v) tally_add((ptr), (v))
 #else
 #define PTB_LDG(p) (*(p))
 #define PTB_TALLY_ADD(ptr, v) (*(ptr) += (v))  // test-only host build is single threaded

@@ -487,26 +487,28 @@ def _box_clip_length(o, d, box):
     return t1.clamp(min=0.0) * u.norm(dim=1)
 
 
-@pytest.mark.parametrize("variant", BIG_VARIANTS)
-def test_config_c2_full_size_properties(variant):
-    """BASELINE.json configs[1] (998,250 tets, 10M particles): too big for the oracle in
-    seconds, so check what must hold at any size: total tally == sum of weighted in-box
-    track lengths (conservation), every particle ends inside its parent tet, final
-    positions equal the clipped destinations, and one variant-0 run is the cross-check
-    for the other variants."""
+def _full_size_properties(cfg_name, variant, n=None, cross_check=None, steps=2):
+    """What must hold at any size, checked at BASELINE.json's full sizes where the oracle would
+    need minutes: total tally == sum of weighted in-box track lengths (conservation), every
+    particle ends inside its parent tet, final positions equal the clipped destinations, and
+    optionally a second kernel variant must reproduce flux, elements and segment count."""
     import torch
 
-    cfg = CONFIGS["c2"]
-    cells, n = cfg["cells"], cfg["particles"]
+    cfg = CONFIGS[cfg_name]
+    cells = cfg["cells"]
+    n = n or cfg["particles"]
     box = tuple(float(c) for c in cells)
+    kw = dict(box=box, num_particles=n, mean_length=cfg["mean_length"], backend="torch", device="cuda")
+    if "mu_min" in cfg:
+        kw["mu_min"] = cfg["mu_min"]
     eng = PumiTally(f"box:{cells[0]},{cells[1]},{cells[2]}", n)
     eng.set_option("variant", variant)
-    wl = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], backend="torch", device="cuda")
+    wl = SyntheticWorkload(**kw)
     init = wl.initial_positions().contiguous()
     s = torch.cuda.current_stream().cuda_stream
     eng.copy_initial_position_device(init.data_ptr(), s)
     expect_total = 0.0
-    for step in range(2):
+    for step in range(steps):
         o, d, f, w = (x.contiguous() for x in wl.next_step())
         eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), s)
         fly = f == 1
@@ -514,7 +516,7 @@ def test_config_c2_full_size_properties(variant):
     torch.cuda.synchronize()
     flux = eng.flux
     st = eng.stats()
-    assert st["lost"] == 0 and st["tracks"] > 0.9 * 2 * n
+    assert st["lost"] == 0 and st["tracks"] > 0.9 * steps * n
     np.testing.assert_allclose(flux.sum(), expect_total, rtol=1e-9)
     assert (flux >= 0).all()
     # containment of a 200k-particle sample: barycentric coordinates of the stored position
@@ -522,7 +524,7 @@ def test_config_c2_full_size_properties(variant):
     coords, t2v = kuhn_box(*cells)
     elem, pos = eng.elem_ids, eng.positions
     assert elem.min() >= 0 and elem.max() < len(t2v)
-    idx = np.random.default_rng(0).choice(n, 200_000, replace=False)
+    idx = np.random.default_rng(0).choice(n, min(n, 200_000), replace=False)
     v = coords[t2v[elem[idx]]]
     T = np.transpose(v[:, 1:] - v[:, :1], (0, 2, 1))
     lam = np.linalg.solve(T, (pos[idx] - v[:, 0])[..., None])[..., 0]
@@ -536,15 +538,38 @@ def test_config_c2_full_size_properties(variant):
     out = idx[fly_np[idx] & ~inside[idx]]
     on_hull = (np.isclose(pos[out], 0.0, atol=1e-9) | np.isclose(pos[out], np.array(box), atol=1e-9)).any(1)
     assert on_hull.all()
-    if variant != 0:
+    if cross_check is not None and cross_check != variant:
         ref = PumiTally(f"box:{cells[0]},{cells[1]},{cells[2]}", n)
-        wl2 = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], backend="torch", device="cuda")
+        ref.set_option("variant", cross_check)
+        wl2 = SyntheticWorkload(**kw)
         i2 = wl2.initial_positions().contiguous()
         ref.copy_initial_position_device(i2.data_ptr(), s)
-        for step in range(2):
+        for step in range(steps):
             o, d, f, w = (x.contiguous() for x in wl2.next_step())
             ref.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), s)
         torch.cuda.synchronize()
-        assert_flux_close(flux, ref.flux, f"variant {variant} vs 0")
+        assert_flux_close(flux, ref.flux, f"{cfg_name}: variant {variant} vs {cross_check}")
         np.testing.assert_array_equal(elem, ref.elem_ids)
         assert st["segments"] == ref.stats()["segments"]
+    return st
+
+
+@pytest.mark.parametrize("variant", BIG_VARIANTS)
+def test_config_c2_full_size_properties(variant):
+    """BASELINE.json configs[1] (998,250 tets, 10 M particles); variant 0 (thread per particle,
+    plain loads) is the cross-check for the others."""
+    _full_size_properties("c2", variant, cross_check=0)
+
+
+@pytest.mark.parametrize("variant", [-1, 20])
+def test_config_c4_full_size_properties(variant):
+    """BASELINE.json configs[3]: ~1 M tets, 1 M particles, near-axial tracks crossing hundreds of tets."""
+    st = _full_size_properties("c4", variant, cross_check=0)
+    assert st["segments"] > 100 * st["tracks"]
+
+
+def test_config_c5_per_gpu_share_full_size_properties():
+    """BASELINE.json configs[4], one GPU's share: 9.86 M tets (1.26 GB of records, the binned kernel is
+    chosen automatically), 12.5 M particles; cross-checked against the streaming kernel."""
+    cfg = CONFIGS["c5"]
+    _full_size_properties("c5", -1, n=cfg["particles"] // cfg["gpus"], cross_check=8, steps=1)

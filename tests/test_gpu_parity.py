@@ -573,3 +573,9 @@ def test_config_c5_per_gpu_share_full_size_properties():
     chosen automatically), 12.5 M particles; cross-checked against the streaming kernel."""
     cfg = CONFIGS["c5"]
     _full_size_properties("c5", -1, n=cfg["particles"] // cfg["gpus"], cross_check=8, steps=1)
+
+
+def test_config_c3_full_size_properties():
+    """BASELINE.json configs[2]: 48,000 tets, 100 M particles (about 2,000 particles per tet and move
+    hammering the same flux words)."""
+    _full_size_properties("c3", -1, cross_check=0, steps=1)

@@ -103,7 +103,8 @@ int pumitally_set_output_name(pumitally_engine *e, const char *filename);
  * the environment variable PUMITALLY_REGISTER_HOST=1), "delta_upload" (0 = off, the default;
  * 1 = send only the origins that differ from the previous call's destinations, with a self-check
  * that switches it off when the host-side comparison costs more than it saves; 2 = always),
- * "delta_threads". */
+ * "delta_threads", "max_iters" (crossing limit per walk; 0 = number of elements + 16, the
+ * default), "l2_fetch". */
 int pumitally_set_option(pumitally_engine *e, const char *name, int64_t value);
 int64_t pumitally_get_option(const pumitally_engine *e, const char *name);
 

@@ -214,7 +214,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   p.weights = d_weights;
   p.begin = begin;
   p.end = end;
-  p.max_iters = int32_t(std::min<int64_t>(mesh_.ntets + 16, INT_MAX));
+  p.max_iters = max_iters_ > 0 ? max_iters_ : int32_t(std::min<int64_t>(mesh_.ntets + 16, INT_MAX));
   p.stats = d_stats_;
   p.grid = grid_;
   if (!use_seed_grid_) p.grid.cell_tet = nullptr;
@@ -584,6 +584,7 @@ int64_t Engine::get_option(const std::string &name) const {
   if (name == "block") return block_;
   if (name == "chunk") return chunk_;
   if (name == "seed_grid") return use_seed_grid_ ? 1 : 0;
+  if (name == "max_iters") return max_iters_;
   if (name == "l2_fetch") {
     size_t g = 0;
     return cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity) == cudaSuccess ? int64_t(g) : -1;
@@ -618,6 +619,9 @@ int Engine::set_option(const std::string &name, int64_t v) {
     use_seed_grid_ = v != 0;
   } else if (name == "register_host") {
     register_host_ = v != 0;
+  } else if (name == "max_iters") {  // crossing limit per walk (the tracer's loop limit); 0 = number of tets + 16
+    if (v < 0 || v > INT_MAX) return 1;
+    max_iters_ = int32_t(v);
   } else if (name == "l2_fetch") {  // bytes an L2 miss fetches from DRAM: 32, 64 or 128 (device-wide limit)
     if (v != 32 && v != 64 && v != 128) return 1;
     if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(v)) != cudaSuccess) { cudaGetLastError(); return 1; }

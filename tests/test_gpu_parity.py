@@ -579,3 +579,42 @@ def test_config_c3_full_size_properties():
     """BASELINE.json configs[2]: 48,000 tets, 100 M particles (about 2,000 particles per tet and move
     hammering the same flux words)."""
     _full_size_properties("c3", -1, cross_check=0, steps=1)
+
+
+@pytest.mark.parametrize("variant", [0, 8, 16, 20])
+def test_walks_cut_short_by_the_crossing_limit_are_reported_and_recoverable(variant):
+    """Reference: "ERROR: Not all particles are found. May need more loops in search" and execution
+    continues (PumiTallyImpl.cpp:455-458).  Here a walk that runs into the limit is counted as lost and
+    stops where it is: its stored position lies in its stored element, nothing is tallied twice, and the
+    next move relocates it like any other particle."""
+    coords, t2v, wl = box_case((8, 8, 8), 20_000, mean_length=6.0)
+    eng = gpu_engine(variant)(coords, t2v, wl.n)
+    orc = OraclePumiTally(coords, t2v, wl.n)
+    init = wl.initial_positions().reshape(-1)
+    for e in (eng, orc):
+        e.CopyInitialPosition(init.copy())
+    eng.set_option("max_iters", 5)
+    o, d, f, w = wl.next_step()
+    eng.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy())
+    st = eng.stats()
+    assert st["lost"] > 100
+    elem, pos = eng.elem_ids, eng.positions
+    v = coords[t2v[elem]]
+    T = np.transpose(v[:, 1:] - v[:, :1], (0, 2, 1))
+    lam = np.linalg.solve(T, (pos - v[:, 0])[..., None])[..., 0]
+    assert min(lam.min(), (1.0 - lam.sum(1)).min()) > -1e-9
+    fly = f == 1
+    full = float((np.linalg.norm(np.clip(d[fly], 0, 8) - o[fly], axis=1) * w[fly]).sum())
+    assert 0.0 < eng.flux.sum() < full
+    # back to the normal limit: the oracle continues from the engine's state
+    eng.set_option("max_iters", 0)
+    eng.reset_tally()
+    orc2 = OraclePumiTally(coords, t2v, wl.n)
+    orc2.CopyInitialPosition(pos.reshape(-1).copy())  # (stopped particles sit on a face: either tet is theirs)
+    o, d, f, w = wl.next_step()
+    for e in (eng, orc2):
+        e.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy())
+    assert eng.stats()["lost"] == 0
+    assert_flux_close(eng.flux, orc2.flux, "after recovery")
+    moved = f == 1  # particles that did not fly still sit on their face
+    np.testing.assert_array_equal(eng.elem_ids[moved], orc2.elem_ids[moved])

@@ -242,6 +242,7 @@ def run_gpu(args, rank, local_rank, world):
         eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
     barrier()
     st0 = eng.stats()
+    launches0 = eng.get_option("launches")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -289,6 +290,7 @@ def run_gpu(args, rank, local_rank, world):
     value = total_segs / (ms_max * 1e-3)
     flux_sum = float(eng.flux.sum())
     variant_used = eng.get_option("variant")
+    gpu_launches = eng.get_option("launches") - launches0  # kernels the engine launched in the timed region
     del eng
 
     # ---------------- end-to-end arm through the host-pointer C ABI: `e2e` ------
@@ -389,14 +391,14 @@ def run_gpu(args, rank, local_rank, world):
                      "frac": (achieved / peak) if achieved else None,
                      "traffic": recorded_traffic() if (args.config == "c2" and not args.particles) else None,
                      "kernel": "walk kernel (variant %d%s), %d launches, %.3f ms each" % (
-                         variant_used, " incl. binning pass" if variant_used in (15, 16, 17, 21) else "", args.steps,
+                         variant_used, " incl. binning pass" if variant_used in (15, 16, 17, 21, 24, 25, 26) else "", args.steps,
                          kernel_ms / max(args.steps, 1)),
                      "algorithmic_bytes_per_launch": alg_bytes / max(args.steps, 1), "peak_source": peak_src},
         "cpu_baseline": cpu,
         "e2e": e2e,
         # kernels of this repo inside the timed region: one fused walk kernel per move, plus the five
         # binning kernels (count, 3-kernel scan, scatter) when the binned variant is in use
-        "gpu_launches": args.steps * (6 if variant_used in (15, 16, 17, 21) else 1),
+        "gpu_launches": gpu_launches,
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

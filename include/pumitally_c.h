@@ -104,7 +104,8 @@ int pumitally_set_output_name(pumitally_engine *e, const char *filename);
  * 1 = send only the origins that differ from the previous call's destinations, with a self-check
  * that switches it off when the host-side comparison costs more than it saves; 2 = always),
  * "delta_threads", "max_iters" (crossing limit per walk; 0 = number of elements + 16, the
- * default), "l2_fetch". */
+ * default), "l2_fetch", "autotune" (1 = default: while "variant" is automatic the engine times the
+ * streaming and the sorted/packed kernel on moves 1-4 of every 64 and keeps the faster one). */
 int pumitally_set_option(pumitally_engine *e, const char *name, int64_t value);
 int64_t pumitally_get_option(const pumitally_engine *e, const char *name);
 

@@ -112,7 +112,52 @@ __global__ void bin_scatter_kernel(const int32_t *__restrict__ pcell, int32_t be
   if (c >= 0) order[atomicAdd(cursor + c, 1u)] = i;
 }
 
+// pass 2, packed flavour: the particle's inputs and parent element go to its slot as one 64-byte row
+__global__ void bin_pack_kernel(const int32_t *__restrict__ pcell, int32_t begin, int32_t end,
+                                unsigned int *__restrict__ cursor, const double *__restrict__ origin,
+                                const double *__restrict__ dest, const double *__restrict__ weights,
+                                const ParticleState *__restrict__ state, PackedRow *__restrict__ rows) {
+  const int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= end) return;
+  const int32_t c = pcell[i];
+  if (c < 0) return;
+  const ParticleState s = load_state(state + i);
+  const double ox = origin[3 * (size_t)i], oy = origin[3 * (size_t)i + 1], oz = origin[3 * (size_t)i + 2];
+  const double dx = dest[3 * (size_t)i], dy = dest[3 * (size_t)i + 1], dz = dest[3 * (size_t)i + 2];
+  const double w = weights[i];
+  const bool moved = ox != s.x || oy != s.y || oz != s.z;  // same test as begin_particle()
+  const unsigned long long tail = (unsigned long long)(uint32_t)i |
+                                  ((unsigned long long)(((uint32_t)s.elem & kIdMask) | (moved ? 0x80000000u : 0u)) << 32);
+  PackedRow *row = rows + atomicAdd(cursor + c, 1u);
+  asm volatile("st.global.L1::no_allocate.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(row),
+               "l"(__double_as_longlong(ox)), "l"(__double_as_longlong(oy)), "l"(__double_as_longlong(oz)),
+               "l"(__double_as_longlong(dx))
+               : "memory");
+  asm volatile("st.global.L1::no_allocate.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<char *>(row) + 32),
+               "l"(__double_as_longlong(dy)), "l"(__double_as_longlong(dz)), "l"(__double_as_longlong(w)), "l"(tail)
+               : "memory");
+}
+
 }  // namespace
+
+cudaError_t launch_bin_pack_particles(const SeedGrid &g, const double *origin, const double *dest,
+                                      const double *weights, const int8_t *flying, const ParticleState *state,
+                                      int32_t begin, int32_t end, int32_t *pcell, unsigned int *count,
+                                      unsigned int *sums, PackedRow *rows, unsigned int *work_count,
+                                      cudaStream_t stream) {
+  const int32_t ncell = g.nx * g.ny * g.nz;
+  const int n = end - begin;
+  if (n <= 0) return cudaMemsetAsync(work_count, 0, sizeof(unsigned int), stream);
+  cudaError_t e = cudaMemsetAsync(count, 0, size_t(ncell) * sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return e;
+  bin_count_kernel<<<(n + 255) / 256, 256, 0, stream>>>(g, origin, flying, begin, end, pcell, count);
+  const int nb = (ncell + kScanBlock - 1) / kScanBlock;
+  scan_block_kernel<<<nb, 256, 0, stream>>>(count, sums, ncell);
+  scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, nb, work_count);
+  scan_add_kernel<<<(ncell + 255) / 256, 256, 0, stream>>>(count, sums, ncell);
+  bin_pack_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pcell, begin, end, count, origin, dest, weights, state, rows);
+  return cudaGetLastError();
+}
 
 // count: [ncell] scratch (zeroed here), sums: [ceil(ncell/1024)] scratch, order: [end-begin]
 // compact output, work_count: device scalar receiving the number of flying particles.

@@ -125,6 +125,7 @@ Engine::~Engine() {
   for (auto &t : timers_free_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto &t : timers_busy_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto &e : chunk_events_) cudaEventDestroy(e);
+  cudaFree(d_rows_);
   if (h_patch_) cudaFreeHost(h_patch_);
   cudaFree(d_patch_);
   cudaFree(d_links_); cudaFree(d_verts_); cudaFree(d_starts_);
@@ -188,12 +189,53 @@ void Engine::collect_timers(bool wait) {
     if (cudaEventQuery(t.b) == cudaSuccess) {
       float ms = 0.f;
       if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) kernel_ms_ += ms;
+      if (t.tag >= 0) {
+        explore_ms_[t.tag] += ms;
+        if (--explore_pending_ == 0 && explore_complete_) {  // all four exploration moves measured
+          // the streaming kernel keeps the job unless sorting buys more than 3 %
+          tuned_variant_ = explore_ms_[1] < 0.97 * explore_ms_[0] ? kVariantPacked : kVariantPersistRefill8;
+          explore_complete_ = false;
+        }
+      }
       timers_free_.push_back(t);
       timers_busy_[k] = timers_busy_.back();
       timers_busy_.pop_back();
     } else {
       ++k;
     }
+  }
+}
+
+// Picks the kernel for the move that is about to be launched (see the auto-tuner note in engine.hpp).
+void Engine::begin_move() {
+  collect_timers(false);
+  move_variant_ = variant_;
+  move_tag_ = -1;
+  if (!auto_variant_ || !autotune_ || variant_ != kVariantPersistRefill8) return;
+  // sorting costs per particle, walking per crossing: with thousands of particles per tet (config c3) the
+  // sorted variant cannot win and two exploration moves would cost more than an epoch can pay back
+  if (int64_t(n_) > 16 * mesh_.ntets) return;
+  // exploration moves 1..4 of every epoch in the order streaming, packed, packed, streaming (move 0 of a
+  // run is atypical: nothing has been re-sourced yet); decision when all four have been timed
+  const uint64_t k = moves_ % kTuneEpoch;
+  if (k >= 1 && k <= 4) {
+    if (k == 1) { explore_ms_[0] = explore_ms_[1] = 0.0; explore_complete_ = false; }
+    move_tag_ = (k == 2 || k == 3) ? 1 : 0;
+    move_variant_ = move_tag_ ? kVariantPacked : kVariantPersistRefill8;
+  } else {
+    if (k == 5) {
+      explore_complete_ = true;  // every exploration launch has been issued
+      // a caller that queues moves back to back has not let the four timed moves finish yet: wait for
+      // them once per epoch (a bubble of at most one move) rather than decide an epoch late
+      for (auto &t : timers_busy_)
+        if (t.tag >= 0) cudaEventSynchronize(t.b);
+      collect_timers(false);
+      if (explore_complete_ && explore_pending_ == 0) {
+        tuned_variant_ = explore_ms_[1] < 0.97 * explore_ms_[0] ? kVariantPacked : kVariantPersistRefill8;
+        explore_complete_ = false;
+      }
+    }
+    move_variant_ = tuned_variant_;
   }
 }
 
@@ -223,6 +265,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   p.bulk_ok = (begin % 16 == 0) && aligned16(d_origin) && aligned16(d_dest) && aligned16(d_flying) &&
               aligned16(d_weights);
   TimerPair t{};
+  t.tag = -1;
   if (timed) {
     if (timers_free_.empty()) {
       PTB_CUDA_OK(cudaEventCreate(&t.a));
@@ -231,10 +274,34 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
       t = timers_free_.back();
       timers_free_.pop_back();
     }
+    t.tag = move_tag_;
+    if (t.tag >= 0) ++explore_pending_;
     PTB_CUDA_OK(cudaEventRecord(t.a, stream));
   }
-  if (variant_ == kVariantPersistGather || variant_ == kVariantPersistGatherL1 ||
-      variant_ == kVariantPersistGatherPlain || variant_ == kVariantEdgeGather) {
+  int variant = move_variant_;
+  const bool packed = variant == kVariantPacked || variant == kVariantPackedL1 || variant == kVariantPackedL1Occ6;
+  if (packed && !(d_origin && d_dest && d_weights)) variant = kVariantPersistRefill8;  // localisation
+  if (packed && variant == move_variant_) {
+    // counting sort by seed-grid cell, the scatter pass writing one 64-byte row per flying particle
+    if (!d_rows_) {
+      if (cudaMalloc(reinterpret_cast<void **>(&d_rows_), std::max<size_t>(size_t(n_), 1) * sizeof(PackedRow)) != cudaSuccess) {
+        fprintf(stderr, "[pumitally] ERROR: no device memory for the packed particle rows\n");
+        return 1;
+      }
+    }
+    unsigned int *wc = d_work_count_ + (ticket_next_ % kTicketRing);
+    SeedGrid bin_grid = grid_;
+    if (!morton_) bin_grid.cell_rank = nullptr;
+    PTB_CUDA_OK(launch_bin_pack_particles(bin_grid, d_origin, d_dest, d_weights, d_flying, d_state_, begin, end,
+                                          d_pcell_, d_cell_count_, d_cell_sums_, d_rows_ + begin, wc, stream));
+    p.rows = d_rows_ + begin;
+    p.work_count = wc;
+    last_work_count_ = wc;
+    p.flying = nullptr;  // only flying particles have rows
+    launches_ += 5;  // count, 3-kernel scan, pack
+  }
+  if (variant == kVariantPersistGather || variant == kVariantPersistGatherL1 ||
+      variant == kVariantPersistGatherPlain || variant == kVariantEdgeGather) {
     // counting sort of the range's flying particles by seed-grid cell of their origin
     unsigned int *wc = d_work_count_ + (ticket_next_ % kTicketRing);
     const double *key = d_origin ? d_origin : d_dest;
@@ -246,9 +313,11 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
     p.order = d_order_ + begin;
     p.work_count = wc;
     last_work_count_ = wc;
+    launches_ += 5;  // count, 3-kernel scan, scatter
     p.flying = nullptr;  // order[] holds flying particles only
   }
-  PTB_CUDA_OK(launch_walk(p, variant_, block_, stream));
+  PTB_CUDA_OK(launch_walk(p, variant, block_, stream));
+  ++launches_;
   if (timed) {
     PTB_CUDA_OK(cudaEventRecord(t.b, stream));
     timers_busy_.push_back(t);
@@ -293,6 +362,8 @@ int Engine::copy_initial_position(const double *xyz, int32_t size) {
   PTB_CUDA_OK(cudaSetDevice(device_));
   PTB_CUDA_OK(cudaMemcpyAsync(d_origin_, xyz, size_t(size) * sizeof(double), cudaMemcpyHostToDevice, compute_));
   h2d_bytes_ += double(size) * sizeof(double);
+  move_variant_ = variant_;
+  move_tag_ = -1;
   if (launch_range(d_origin_, nullptr, nullptr, nullptr, 0, n_, compute_, true)) return 1;
   PTB_CUDA_OK(cudaStreamSynchronize(compute_));
   initialized_ = true;
@@ -305,6 +376,8 @@ int Engine::copy_initial_position_device(const double *d_xyz, int32_t size, cuda
     return 1;
   }
   PTB_CUDA_OK(cudaSetDevice(device_));
+  move_variant_ = variant_;
+  move_tag_ = -1;
   if (launch_range(d_xyz, nullptr, nullptr, nullptr, 0, n_, stream, true)) return 1;
   initialized_ = true;
   return 0;
@@ -317,6 +390,7 @@ int Engine::ensure_patch_buffers(int nchunks) {
   const size_t cap = size_t(double(std::min<int64_t>(chunk_, n_)) * kPatchMaxFraction) + 1;
   if (h_patch_ && patch_cap_ == cap && patch_chunks_ >= nchunks) return 0;
   PTB_CUDA_OK(cudaDeviceSynchronize());
+  cudaFree(d_rows_);
   if (h_patch_) cudaFreeHost(h_patch_);
   if (d_patch_) cudaFree(d_patch_);
   h_patch_ = nullptr;
@@ -379,7 +453,7 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
     return 1;
   }
   PTB_CUDA_OK(cudaSetDevice(device_));
-  collect_timers(false);
+  begin_move();
   maybe_register(origin, size_t(size) * sizeof(double));
   maybe_register(dest, size_t(size) * sizeof(double));
   maybe_register(weights, size_t(n_) * sizeof(double));
@@ -431,7 +505,10 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
     sent += 32.0 * double(cnt);
     PTB_CUDA_OK(cudaEventRecord(chunk_events_[k], copy_));
     PTB_CUDA_OK(cudaStreamWaitEvent(compute_, chunk_events_[k], 0));
-    if (npatch > 0) PTB_CUDA_OK(launch_patch_origins(d_origin_, dp, npatch, compute_));
+    if (npatch > 0) {
+      PTB_CUDA_OK(launch_patch_origins(d_origin_, dp, npatch, compute_));
+      ++launches_;
+    }
     if (launch_range(d_origin_, d_dest_, d_flying_, d_weights_, b, e, compute_, true)) return 1;
   }
   h2d_bytes_ += sent;
@@ -478,7 +555,7 @@ int Engine::move_to_next_location_device(const double *d_origin, const double *d
     return 1;
   }
   PTB_CUDA_OK(cudaSetDevice(device_));
-  collect_timers(false);
+  begin_move();
   mirror_valid_ = false;  // the staging buffers no longer hold the previous host move's destinations
   if (launch_range(d_origin, d_dest, d_flying, d_weights, 0, n_, stream, true)) return 1;
   ++moves_;
@@ -580,7 +657,10 @@ int Engine::choose_variant() const {
 }
 
 int64_t Engine::get_option(const std::string &name) const {
-  if (name == "variant") return variant_;
+  if (name == "variant")  // the kernel the next move will use outside the auto-tuner's exploration moves
+    return (auto_variant_ && autotune_ && variant_ == kVariantPersistRefill8) ? tuned_variant_ : variant_;
+  if (name == "launches") return int64_t(launches_);
+  if (name == "autotune") return autotune_ ? 1 : 0;
   if (name == "block") return block_;
   if (name == "chunk") return chunk_;
   if (name == "seed_grid") return use_seed_grid_ ? 1 : 0;
@@ -597,7 +677,11 @@ int64_t Engine::get_option(const std::string &name) const {
 
 int Engine::set_option(const std::string &name, int64_t v) {
   if (name == "variant") {
-    if (v == -1) { variant_ = choose_variant(); return 0; }  // automatic
+    if (v == -1) {  // automatic
+      variant_ = choose_variant();
+      auto_variant_ = true;
+      return 0;
+    }
     if (v < 0 || v >= kNumVariants) return 1;
     if (v >= kVariantEdge && v <= kVariantEdgeOcc6) {
       if (synchronize()) return 1;
@@ -609,6 +693,9 @@ int Engine::set_option(const std::string &name, int64_t v) {
       }
     }
     variant_ = int(v);
+    auto_variant_ = false;
+  } else if (name == "autotune") {
+    autotune_ = v != 0;
   } else if (name == "block") {
     if (v != 64 && v != 128 && v != 256) return 1;
     block_ = int(v);

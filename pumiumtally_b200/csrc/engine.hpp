@@ -83,6 +83,20 @@ class Engine {
   // options
   int variant_ = kVariantPersistRefill8;  // chosen in the constructor from mesh size vs L2 (choose_variant)
   int choose_variant() const;
+  // Auto-tuner (only while the engine picks the kernel itself and the mesh is in the streaming regime):
+  // whether processing the particles in spatial order pays depends on the particle data (it does for
+  // collimated long tracks, config c4; it ties for isotropic ones), so the first four moves of every
+  // kTuneEpoch alternate between the streaming kernel and the packed/sorted one, and the rest of the
+  // epoch uses whichever had the lower kernel time.
+  static constexpr uint64_t kTuneEpoch = 64;
+  bool auto_variant_ = true, autotune_ = true;
+  int tuned_variant_ = kVariantPersistRefill8;
+  int move_variant_ = kVariantPersistRefill8, move_tag_ = -1;
+  double explore_ms_[2] = {0.0, 0.0};
+  int explore_pending_ = 0;
+  bool explore_complete_ = false;
+  uint64_t launches_ = 0;  // kernels launched by the move / localisation entry points
+  void begin_move();
   int block_ = 128;
   int32_t chunk_ = 1 << 20;  // particles per H2D/compute pipeline stage
   bool use_seed_grid_ = true;
@@ -107,11 +121,12 @@ class Engine {
   int32_t *d_cell_rank_ = nullptr;
   // spatial binning of the flying particles (gather-mode kernels)
   int32_t *d_pcell_ = nullptr, *d_order_ = nullptr;
+  PackedRow *d_rows_ = nullptr;  // packed variant: one 64-byte row per flying particle, allocated at first use
   unsigned int *last_work_count_ = nullptr;
   unsigned int *d_cell_count_ = nullptr, *d_cell_sums_ = nullptr, *d_work_count_ = nullptr;
 
   cudaStream_t compute_ = nullptr, copy_ = nullptr;
-  struct TimerPair { cudaEvent_t a, b; };
+  struct TimerPair { cudaEvent_t a, b; int tag; };  // tag: auto-tuner slot the time belongs to, -1 = none
   std::vector<TimerPair> timers_free_, timers_busy_;
   std::vector<cudaEvent_t> chunk_events_;
   // caller buffers pinned with cudaHostRegister (option "register_host"): base -> bytes

@@ -203,6 +203,20 @@ struct alignas(32) PatchEntry {
   int32_t pad;
 };
 
+// One row of the packed, spatially sorted particle batch (variant "packed"): everything a flying
+// particle needs for this move in one 64-byte line, written by the binning pass in cell order and
+// streamed by the walk kernel with one bulk copy per chunk.  The stored position is not carried:
+// for every continuing particle it equals `origin` bit for bit; the others (bit 31 of `elem` set)
+// read their ParticleState when they start.
+struct alignas(64) PackedRow {
+  double ox, oy, oz;  // origin (= position before the move unless the relocate bit is set)
+  double dx, dy, dz;  // destination
+  double w;
+  int32_t id;         // particle index in the caller's arrays
+  uint32_t elem;      // bits 0..29 parent element, bit 31: origin differs from the stored position
+};
+static_assert(sizeof(PackedRow) == 64, "PackedRow must be one 64-byte line");
+
 // One launch = one particle range of one MoveToNextLocation / CopyInitialPosition.
 struct WalkParams {
   const TetRecord *tets;   // [E] packed records
@@ -222,6 +236,7 @@ struct WalkParams {
   const int32_t *order;        // gather mode: ids of the flying particles in processing order
   const unsigned int *work_count;  // gather mode: number of entries in order[] (device scalar)
   int32_t claim_run;           // gather mode: chunks per ticket (1, 2 or 4)
+  const PackedRow *rows;       // packed mode: work_count rows in processing order
   DeviceStats *stats;
   SeedGrid grid;
 };

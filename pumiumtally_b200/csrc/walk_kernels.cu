@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) walk_quad_kernel(const WalkParams P) {
 constexpr int kChunk = 16;  // particles per staged chunk (all slice sizes stay multiples of 16 bytes)
 constexpr uint32_t kB8 = 8u * kChunk, kB24 = 24u * kChunk, kB32 = 32u * kChunk, kB1 = 1u * kChunk;
 
-struct __align__(32) ParticleStage {
+struct __align__(64) ParticleStage {
   double origin[3 * kChunk];
   double dest[3 * kChunk];
   ParticleState state[kChunk];
@@ -218,7 +218,7 @@ struct __align__(32) ParticleStage {
   int8_t fly[kChunk];
   int32_t id[kChunk];  // gather mode: particle id of each slot
 };
-static_assert(sizeof(ParticleStage) % 32 == 0 && offsetof(ParticleStage, state) % 32 == 0 && offsetof(ParticleStage, w) % 16 == 0 && offsetof(ParticleStage, fly) % 16 == 0, "stage layout");
+static_assert(sizeof(ParticleStage) >= kChunk * sizeof(PackedRow) && sizeof(ParticleStage) % 32 == 0 && offsetof(ParticleStage, state) % 32 == 0 && offsetof(ParticleStage, w) % 16 == 0 && offsetof(ParticleStage, fly) % 16 == 0, "stage layout");
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -281,6 +281,26 @@ __device__ __forceinline__ void begin_from_stage(const WalkParams &P, const Part
     r.stage = kStageTally;
     c.tracks++;
   }
+}
+
+// begin_particle() for a packed row (only flying particles have rows).  Returns the particle id.
+__device__ __forceinline__ int begin_from_row(const WalkParams &P, const PackedRow *row, Ray &r, Counters &c) {
+  const int id = row->id;
+  const uint32_t el = row->elem;
+  const double ox = row->ox, oy = row->oy, oz = row->oz;
+  if (el >> 31) {  // re-sourced: phase 1 from the stored position (rare)
+    const ParticleState s0 = load_state(P.state + id);
+    r.e = s0.elem;
+    start_reloc(P, r, s0.x, s0.y, s0.z, ox, oy, oz);
+    return id;
+  }
+  r.e = (int32_t)(el & kIdMask);
+  set_ray(r, ox, oy, oz, row->dx, row->dy, row->dz);
+  const double len = sqrt(r.ux * r.ux + r.uy * r.uy + r.uz * r.uz);
+  r.wl = row->w * len;
+  r.stage = kStageTally;
+  c.tracks++;
+  return id;
 }
 
 // Fetch modes of the persistent kernel (how a lane gets its 128-byte tet record):
@@ -560,8 +580,12 @@ constexpr int kClaimRun = 4;  // gather mode: a warp takes up to this many conse
 // REFILL_T: idle lanes are topped up only when at least this many have finished -- the
 // refill code then runs with REFILL_T+ active lanes instead of the ~3 that finish per
 // iteration, at the price of a few idle lanes in the walk step.
-template <int BLOCK, int FETCH, int MINB, int REFILL_T, bool GATHER>
+// STAGING: 0 = particle arrays streamed in storage order (TMA bulk copies of the SoA/AoS slices),
+// 1 = gather through order[] (binned), 2 = packed rows written by the binning pass (binned, streamed).
+template <int BLOCK, int FETCH, int MINB, int REFILL_T, int STAGING>
 __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkParams P) {
+  constexpr bool GATHER = STAGING == 1;
+  constexpr bool PACKED = STAGING == 2;
   constexpr int WARPS = BLOCK / 32;
   constexpr bool kBulkTets = FETCH == kFetchBulk;
   constexpr bool kRows = FETCH == kFetchBulk;
@@ -584,7 +608,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
   __syncwarp();
   const uint64_t keep = FETCH != kFetchPlain ? l2_policy_keep() : 0;
   const uint64_t strm = (FETCH == kFetchEdge) ? 0 : ((FETCH != kFetchPlain || GATHER) ? l2_policy_stream() : 0);
-  const int total = GATHER ? (int)__ldg(P.work_count) : P.end - P.begin;
+  const int total = (GATHER || PACKED) ? (int)__ldg(P.work_count) : P.end - P.begin;
   const int nchunks = (total + kChunk - 1) / kChunk;
   // Gather mode: a ticket is a run of kClaimRun chunks = 64 particles whose ids sit in two
   // registers per lane.  The *next* ticket is claimed, and its ids requested, one run ahead, so
@@ -603,7 +627,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
     pend1 = p1 < pe ? __ldg(P.order + p1) : 0;
   };
   auto load_stage = [&](int chunk, ParticleStage *st, uint32_t bar) {
-    if constexpr (GATHER) {
+    if constexpr (PACKED) {
+      // one bulk copy: the chunk's rows are contiguous and every row is 64 bytes, ragged tail included
+      if (lane == 0) {
+        const uint32_t bytes = 64u * (uint32_t)min(kChunk, total - chunk * kChunk);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s_hint(smem_u32(st), P.rows + (size_t)chunk * kChunk, bytes, bar, strm);
+      }
+    } else if constexpr (GATHER) {
       const int k = chunk - run_base;  // chunk's position in the current ticket (warp-uniform)
       const int id = __shfl_sync(0xffffffffu, (k >> 1) ? ids1 : ids0, ((k & 1) << 4) | (lane & 15));
       stage_gather(P, id, min(kChunk, total - chunk * kChunk), st, bar, lane,
@@ -656,8 +687,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
     while (cur_count > 0 && (int)__popc(idle) >= REFILL_T) {
       const int slot = cursor + __popc(idle & ((1u << lane) - 1u));
       if (r.stage == kStageDone && slot < cur_count) {
-        my_i = GATHER ? stages[warp][cur].id[slot] : P.begin + chunk_cur * kChunk + slot;
-        begin_from_stage(P, &stages[warp][cur], slot, r, c);
+        if constexpr (PACKED) {
+          my_i = begin_from_row(P, reinterpret_cast<const PackedRow *>(&stages[warp][cur]) + slot, r, c);
+        } else {
+          my_i = GATHER ? stages[warp][cur].id[slot] : P.begin + chunk_cur * kChunk + slot;
+          begin_from_stage(P, &stages[warp][cur], slot, r, c);
+        }
         if constexpr (FETCH == kFetchEdge) {
           g.dv = 0;
           if (r.stage != kStageDone) {
@@ -717,7 +752,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
   flush_counters(P, c);
 }
 
-template <int BLOCK, int FETCH, int MINB, int REFILL_T = 1, bool GATHER = false, int CARVE = -1>
+template <int BLOCK, int FETCH, int MINB, int REFILL_T = 1, int GATHER = 0, int CARVE = -1>
 cudaError_t launch_persist(const WalkParams &p, long long n, cudaStream_t stream) {
   static int sms = 0, occ = 0;
   if (!sms) {
@@ -838,6 +873,15 @@ cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_
       return launch_persist<128, kFetchBulk, 7>(p, n, stream);
     case kVariantPersistRefill8:
       return launch_persist<128, kFetchPolicy, 7, 8>(p, n, stream);
+    case kVariantPacked:
+      if (!p.rows) return cudaErrorInvalidValue;
+      return launch_persist<128, kFetchPolicy, 7, 8, 2>(p, n, stream);
+    case kVariantPackedL1:
+      if (!p.rows) return cudaErrorInvalidValue;
+      return launch_persist<128, kFetchPolicyL1, 7, 8, 2, 40>(p, n, stream);
+    case kVariantPackedL1Occ6:
+      if (!p.rows) return cudaErrorInvalidValue;
+      return launch_persist<128, kFetchPolicyL1, 6, 8, 2, 40>(p, n, stream);
     case kVariantEdge:
       if (!p.links) return cudaErrorInvalidValue;
       return launch_persist<128, kFetchEdge, 4, 8, false, 40>(p, n, stream);

@@ -28,7 +28,10 @@ enum WalkVariant : int {
   kVariantEdgeGather = 21,  // 20 on spatially binned particles
   kVariantEdgeOcc5 = 22,    // 20 compiled for 5 resident blocks (96 registers, a few spills)
   kVariantEdgeOcc6 = 23,    // 20 compiled for 6 resident blocks (80 registers, more spills)
-  kNumVariants = 24
+  kVariantPacked = 24,      // 8 on a packed, spatially sorted copy of the flying particles' inputs (bin + pack pass)
+  kVariantPackedL1 = 25,    // 24 with L1-allocating tet loads (neighbouring lanes share records once particles are sorted)
+  kVariantPackedL1Occ6 = 26,
+  kNumVariants = 27
 };
 
 
@@ -37,6 +40,13 @@ cudaError_t launch_bin_particles(const SeedGrid &g, const double *origin, const 
                                  int32_t begin, int32_t end, int32_t *pcell, unsigned int *count,
                                  unsigned int *sums, int32_t *order, unsigned int *work_count,
                                  cudaStream_t stream);
+// Like launch_bin_particles, but instead of the id list the scatter pass writes one PackedRow per
+// flying particle (origin, dest, weight, id, parent element + relocate flag) in cell order.
+cudaError_t launch_bin_pack_particles(const SeedGrid &g, const double *origin, const double *dest,
+                                      const double *weights, const int8_t *flying, const ParticleState *state,
+                                      int32_t begin, int32_t end, int32_t *pcell, unsigned int *count,
+                                      unsigned int *sums, PackedRow *rows, unsigned int *work_count,
+                                      cudaStream_t stream);
 cudaError_t launch_seed_points(const SeedGrid &g, double *xyz, cudaStream_t stream);
 cudaError_t launch_seed_finalize(const double *xyz, const ParticleState *state, int32_t *cell_tet,
                                  int32_t ncell, cudaStream_t stream);

@@ -17,8 +17,8 @@ from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
 from test_oracle_golden import check_c1_fixture, golden_scenario
 
 pytestmark = pytest.mark.gpu
-VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 13, 15, 16, 17, 20, 21, 22, 23]
-BIG_VARIANTS = [0, 6, 8, 16, 20, 21]
+VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 13, 15, 16, 17, 20, 21, 22, 23, 24, 25]
+BIG_VARIANTS = [0, 6, 8, 16, 20, 21, 24]
 EDGE_VARIANTS = [20, 21, 22, 23]  # compact layout + edge-function exit test
 
 
@@ -185,7 +185,7 @@ def test_edge_walk_takes_the_plane_records_only_for_coplanar_rays(variant):
     assert golden.stats()["plane_fallbacks"] > 0
 
 
-@pytest.mark.parametrize("variant", [0, 8, 16, 20, 21])
+@pytest.mark.parametrize("variant", [0, 8, 16, 20, 21, 24])
 def test_chunked_upload_pipeline_equals_single_range(variant):
     """Host-pointer path cut into many upload/compute ranges (the binned variant bins each range)."""
     coords, t2v, wl = box_case((6, 6, 5), 50_000)

@@ -618,3 +618,21 @@ def test_walks_cut_short_by_the_crossing_limit_are_reported_and_recoverable(vari
     assert_flux_close(eng.flux, orc2.flux, "after recovery")
     moved = f == 1  # particles that did not fly still sit on their face
     np.testing.assert_array_equal(eng.elem_ids[moved], orc2.elem_ids[moved])
+
+
+def test_autotuner_switches_kernels_without_changing_results():
+    """Default engine (variant chosen automatically): moves 1-4 alternate the streaming and the packed/sorted
+    kernel, later moves use the faster one.  Whatever it picks, every move must match the oracle."""
+    coords, t2v, wl = box_case((8, 8, 40), 30_000, mean_length=60.0, mu_min=0.99)
+    eng = PumiTally.from_arrays(coords, t2v, wl.n)
+    assert eng.get_option("autotune") == 1
+    orc = OraclePumiTally(coords, t2v, wl.n)
+    run_workload(eng, orc, wl, steps=8, label="autotune")
+    assert eng.get_option("variant") in (8, 24)
+    assert eng.get_option("launches") >= 8 + 1 + 2 * 5  # 8 moves + localisation + two packed exploration moves
+    assert eng.stats()["segments"] == orc.n_segments
+    pinned = PumiTally.from_arrays(coords, t2v, wl.n)
+    pinned.set_option("autotune", 0)
+    wl2 = SyntheticWorkload(box=(8.0, 8.0, 40.0), num_particles=wl.n, mean_length=60.0, mu_min=0.99)
+    run_workload(pinned, OraclePumiTally(coords, t2v, wl.n), wl2, steps=6, label="autotune off")
+    assert pinned.get_option("variant") == 8 and pinned.get_option("launches") == 6 + 1

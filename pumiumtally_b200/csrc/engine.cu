@@ -281,14 +281,22 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   int variant = move_variant_;
   const bool packed = variant == kVariantPacked || variant == kVariantPackedL1 || variant == kVariantPackedL1Occ6;
   if (packed && !(d_origin && d_dest && d_weights)) variant = kVariantPersistRefill8;  // localisation
-  if (packed && variant == move_variant_) {
-    // counting sort by seed-grid cell, the scatter pass writing one 64-byte row per flying particle
-    if (!d_rows_) {
-      if (cudaMalloc(reinterpret_cast<void **>(&d_rows_), std::max<size_t>(size_t(n_), 1) * sizeof(PackedRow)) != cudaSuccess) {
-        fprintf(stderr, "[pumitally] ERROR: no device memory for the packed particle rows\n");
-        return 1;
-      }
+  bool use_packed = packed && variant == move_variant_;
+  if (use_packed && !d_rows_ &&
+      cudaMalloc(reinterpret_cast<void **>(&d_rows_), std::max<size_t>(size_t(n_), 1) * sizeof(PackedRow)) != cudaSuccess) {
+    cudaGetLastError();
+    d_rows_ = nullptr;
+    if (auto_variant_) {  // the auto-tuner wanted to try it: carry on with the streaming kernel for good
+      autotune_ = false;
+      tuned_variant_ = variant = move_variant_ = kVariantPersistRefill8;
+      use_packed = false;
+    } else {
+      fprintf(stderr, "[pumitally] ERROR: no device memory for the packed particle rows\n");
+      return 1;
     }
+  }
+  if (use_packed) {
+    // counting sort by seed-grid cell, the scatter pass writing one 64-byte row per flying particle
     unsigned int *wc = d_work_count_ + (ticket_next_ % kTicketRing);
     SeedGrid bin_grid = grid_;
     if (!morton_) bin_grid.cell_rank = nullptr;

@@ -101,7 +101,7 @@ class Engine {
   int32_t chunk_ = 1 << 20;  // particles per H2D/compute pipeline stage
   bool use_seed_grid_ = true;
   int32_t max_iters_ = 0;  // crossing limit per walk; 0 = ntets + 16
-  bool morton_ = false;   // binning key: Morton rank of the cell instead of its z-major index
+  bool morton_ = true;    // binning key: Morton rank of the cell (matches the tet storage order) instead of its z-major index
   int claim_run_ = 4;     // chunks per ticket in gather mode
 
   // device memory

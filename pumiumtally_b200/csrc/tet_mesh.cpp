@@ -168,6 +168,11 @@ bool HostMesh::finalize(std::string *err) {
     auto dim = [&](double l) { return int64_t(std::min(std::max(std::ceil(l / h), 1.0), 1024.0)); };
     const int64_t gx = dim(lx), gy = dim(ly), gz = dim(lz);
     std::vector<std::pair<int64_t, int32_t>> key(static_cast<size_t>(ntets));
+    // Z-curve through the cells by default (a window of consecutive tets is a compact 3-D block: the binned
+    // kernels process particles in the same order, engine.hpp `morton_`); PUMITALLY_TET_ORDER=zmajor restores
+    // the slab order for experiments
+    const char *order_env = std::getenv("PUMITALLY_TET_ORDER");
+    const bool morton_order = !(order_env && std::string(order_env) == "zmajor");
 #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < ntets; ++e) {
       double c[3] = {0, 0, 0};
@@ -176,7 +181,20 @@ bool HostMesh::finalize(std::string *err) {
       auto cell = [&](double x, double lo, int64_t n) {
         return std::min<int64_t>(std::max<int64_t>(int64_t((x - lo) / h), 0), n - 1);
       };
-      const int64_t k = (cell(c[2], bbox_lo[2], gz) * gy + cell(c[1], bbox_lo[1], gy)) * gx + cell(c[0], bbox_lo[0], gx);
+      const int64_t cx = cell(c[0], bbox_lo[0], gx), cy = cell(c[1], bbox_lo[1], gy), cz = cell(c[2], bbox_lo[2], gz);
+      int64_t k = (cz * gy + cy) * gx + cx;
+      if (morton_order) {
+        auto spread = [](uint64_t v) {
+          v &= 0x1fffff;
+          v = (v | v << 32) & 0x1f00000000ffffull;
+          v = (v | v << 16) & 0x1f0000ff0000ffull;
+          v = (v | v << 8) & 0x100f00f00f00f00full;
+          v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+          v = (v | v << 2) & 0x1249249249249249ull;
+          return v;
+        };
+        k = int64_t(spread(uint64_t(cx)) | spread(uint64_t(cy)) << 1 | spread(uint64_t(cz)) << 2);
+      }
       key[e] = {k, int32_t(e)};
     }
     std::sort(key.begin(), key.end());  // ties keep the caller's relative order (second = id)

@@ -70,12 +70,12 @@ struct HostMesh {
   std::vector<VertexRec> cverts;   // [nverts] vertices in order of first use by the internal tet order
   double centroid0[3] = {0, 0, 0};  // centroid of (the caller's) element 0 (PumiTallyImpl.cpp:500-509)
 
-  // INTERNAL ELEMENT ORDER.  finalize() renumbers the tets by the z-major index of the
-  // background-grid cell that holds their centroid, so that tets that are close in space are
-  // close in memory whatever numbering the mesh file came with (the spatially binned walk streams
-  // through the mesh slab by slab).  t2v, t2t, volume and records are stored in this internal
-  // order; everything that leaves the library (flux, element ids, adjacency, VTK) is translated
-  // back to the caller's numbering with these two maps.
+  // INTERNAL ELEMENT ORDER.  finalize() renumbers the tets along a Z-order (Morton) curve through the
+  // cells of a background grid, by the cell that holds their centroid, so that tets that are close in
+  // space are close in memory whatever numbering the mesh file came with (the spatially binned walk
+  // processes particles along the same curve).  t2v, t2t, volume and records are stored in this
+  // internal order; everything that leaves the library (flux, element ids, adjacency, VTK) is
+  // translated back to the caller's numbering with these two maps.
   std::vector<int32_t> orig_of_internal, internal_of_orig;
   int32_t start_elem = 0;  // internal id of the caller's element 0 (where particles are parked)
 

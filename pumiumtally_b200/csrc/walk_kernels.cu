@@ -315,7 +315,7 @@ __device__ __forceinline__ int begin_from_row(const WalkParams &P, const PackedR
 //      spatial order and neighbouring lanes/warps revisit the same records)
 //   6  compact layout + edge-function exit test (walk_compact.cuh): one 32-byte TetLinks sector and
 //      one 32-byte vertex per crossing, both L2-resident; degenerate rays finish on the plane records
-enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3, kFetchCoop = 4, kFetchPolicyL1 = 5, kFetchEdge = 6 };
+enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3, kFetchPolicyL1 = 5, kFetchEdge = 6 };
 
 __device__ __forceinline__ uint64_t l2_policy_keep() {
   uint64_t p;

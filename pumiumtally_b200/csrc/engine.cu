@@ -398,7 +398,6 @@ int Engine::ensure_patch_buffers(int nchunks) {
   const size_t cap = size_t(double(std::min<int64_t>(chunk_, n_)) * kPatchMaxFraction) + 1;
   if (h_patch_ && patch_cap_ == cap && patch_chunks_ >= nchunks) return 0;
   PTB_CUDA_OK(cudaDeviceSynchronize());
-  cudaFree(d_rows_);
   if (h_patch_) cudaFreeHost(h_patch_);
   if (d_patch_) cudaFree(d_patch_);
   h_patch_ = nullptr;

@@ -34,7 +34,11 @@
 // flag bytes, the SCOREC fork adds a class-id list); the reader probes the known layouts and
 // accepts the first one whose array header is consistent (count == nverts*ncomps and, when
 // compressed, a zlib stream that inflates to exactly that size).  Anything inconsistent is
-// reported as an error -- there is no silent guess.
+// reported as an error -- there is no silent guess.  The same goes for the two header details
+// this restatement is least sure of (whether the stream repeats the version after the magic
+// bytes, and from which version on the meta block starts with the mesh family): the expected
+// reading is tried first, the alternatives after it, and a reading only counts if the whole
+// stream up to the coordinates parses consistently under it.
 #include <zlib.h>
 
 #include <algorithm>
@@ -189,14 +193,22 @@ bool read_vertex_tag(Cursor &c, int64_t nverts, std::vector<double> *coords) {
   throw Fail("cannot parse vertex tag '" + name + "': " + why);
 }
 
-void parse_stream(Cursor &c, long version, std::vector<double> *coords, std::vector<int32_t> *t2v) {
+// `version_in_stream`: an int32 version follows the magic bytes (bare streams, old directories).
+// The meta block starts with the mesh family from version 7 on; `flip_family_rule` tries the other
+// reading.  The caller tries the expected combination first; every later check (dimension,
+// communicator, array sizes, the coordinates tag, four distinct vertices per tet) has to pass for a
+// combination to be accepted.
+void parse_stream(Cursor &c, long version, bool version_in_stream, bool flip_family_rule,
+                  std::vector<double> *coords, std::vector<int32_t> *t2v) {
   c.need(2);
   if (c.p[0] != kMagic[0] || c.p[1] != kMagic[1]) throw Fail("not an Omega_h binary stream (magic bytes)");
   c.at = 2;
-  if (version < 0) version = c.get<int32_t>();
+  if (version_in_stream) version = c.get<int32_t>();
   if (version < 1 || version > 64) throw Fail("implausible stream version " + std::to_string(version));
-  c.compressed = c.get<int8_t>() != 0;
-  if (version >= 7) {
+  const int comp = c.get<int8_t>();
+  if (comp != 0 && comp != 1) throw Fail("implausible compression flag");
+  c.compressed = comp != 0;
+  if ((version >= 7) != flip_family_rule) {
     const int family = c.get<int8_t>();
     if (family != 0) throw Fail("mesh family is not simplex");
   }
@@ -282,14 +294,24 @@ bool read_osh_mesh(const std::string &path, std::vector<double> *coords, std::ve
   }
   std::vector<unsigned char> buf;
   if (!slurp(stream_file, &buf)) { *err = "cannot read " + stream_file; return false; }
-  Cursor c{buf.data(), buf.size()};
-  try {
-    parse_stream(c, version, coords, t2v);
-  } catch (const Fail &f) {
-    *err = "Omega_h mesh " + path + ": " + f.what();
-    return false;
+  // layout hypotheses, most likely first: the version comes from the version file when there is one
+  // (else from the stream), family byte by the version rule; then the alternatives
+  const bool have_file_version = version >= 0;
+  std::string first_error;
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    const bool flip_version_place = attempt >= 2, flip_family = attempt & 1;
+    if (flip_version_place && !have_file_version) break;  // without a version file the stream must carry it
+    const bool version_in_stream = have_file_version == flip_version_place;
+    Cursor c{buf.data(), buf.size()};
+    try {
+      parse_stream(c, version, version_in_stream, flip_family, coords, t2v);
+      return true;
+    } catch (const Fail &f) {
+      if (first_error.empty()) first_error = f.what();
+    }
   }
-  return true;
+  *err = "Omega_h mesh " + path + ": " + first_error;
+  return false;
 }
 
 }  // namespace ptb

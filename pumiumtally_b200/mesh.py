@@ -162,7 +162,8 @@ def simplex_downward(tet2vert):
 
 
 def save_osh(path: str, coords, tet2vert, version: int = 10, compressed: bool = True,
-             tag_layout: str = "direct", extra_tags: bool = True, bare_stream: bool = False) -> None:
+             tag_layout: str = "direct", extra_tags: bool = True, bare_stream: bool = False,
+             version_in_stream: bool = False, family_byte: bool = None) -> None:
     """Write an Omega_h-style binary mesh directory (``nparts``, ``version``, ``0.osh``) following
     the stream layout documented in ``csrc/osh_reader.cpp``.  The layout is a restatement from
     memory of Omega_h's published format (no Omega_h here to check against): this writer exists so
@@ -170,7 +171,8 @@ def save_osh(path: str, coords, tet2vert, version: int = 10, compressed: bool = 
     Alignment codes are written as zeros (the reader does not consume them).
 
     tag_layout: "direct" (name, ncomps, type, array), "class_ids" (an i32 class-id count and
-    optional id list before the array) or "flags" (two flag bytes, stream versions < 5)."""
+    optional id list before the array) or "flags" (two flag bytes, stream versions < 5).
+    version_in_stream / family_byte force the two header details the reader is unsure about."""
     import struct
     import zlib
 
@@ -199,10 +201,10 @@ def save_osh(path: str, coords, tet2vert, version: int = 10, compressed: bool = 
         return b + arr(a)
 
     s = bytes([0xA1, 0x1A])
-    if bare_stream:
+    if bare_stream or version_in_stream:
         s += struct.pack("<i", version)
     s += struct.pack("<b", 1 if compressed else 0)
-    if version >= 7:
+    if (version >= 7) if family_byte is None else family_byte:
         s += struct.pack("<b", 0)                       # family: simplex
     s += struct.pack("<biibib", 3, 1, 0, 0, 0, 0)       # dim, comm size/rank, parting, ghost layers, no hints
     s += struct.pack("<i", nv)

@@ -58,7 +58,9 @@ def test_gmsh_ingest(tmp_path, version):
 
 OSH_CASES = [dict(), dict(compressed=False), dict(version=9, tag_layout="direct"),
              dict(version=10, tag_layout="class_ids"), dict(version=10, tag_layout="class_ids", compressed=False),
-             dict(version=4, tag_layout="flags"), dict(extra_tags=False), dict(bare_stream=True, version=10)]
+             dict(version=4, tag_layout="flags"), dict(extra_tags=False), dict(bare_stream=True, version=10),
+             dict(version_in_stream=True), dict(version=8, family_byte=False), dict(version=5, family_byte=True),
+             dict(version_in_stream=True, family_byte=False, compressed=False)]
 
 
 @pytest.mark.parametrize("kw", OSH_CASES, ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()) or "default")

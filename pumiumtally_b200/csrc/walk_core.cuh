@@ -81,6 +81,8 @@ PTB_HD void face_payload(double a, double b, double c, double d, int32_t self, i
 // face compute the identical quotient.  The minimum is selected by cross-multiplication
 // (num_a*den_b < num_b*den_a, both den > 0): one fp64 division per crossing instead of one per
 // face; ties within rounding pick either face, which only reorders a zero-length piece.
+constexpr double kDenMin = 1e-280;
+
 struct ExitScan {
   double bnum = 1.0, bden = 0.0;  // t = +inf
   int32_t nbr = -2, back = -1;
@@ -91,7 +93,11 @@ PTB_HD void scan_face(ExitScan &s, double nx, double ny, double nz, double c, in
                       double uz) {
   const double den = nx * ux + ny * uy + nz * uz;
   const double num = c - (nx * ox + ny * oy + nz * oz);
-  const bool take = (den > 0.0) && (num * s.bden < s.bnum * den);
+  // den > kDenMin, not den > 0: a plane component that is exactly zero carries the payload byte as a
+  // denormal (~1e-321), so a ray exactly parallel to the face (a track along the hull surface or
+  // inside an axis-aligned face) would see den = +-1e-321*|u| instead of 0 and could "leave"
+  // through it.  No real crossing has |den| anywhere near 1e-280.
+  const bool take = (den > kDenMin) && (num * s.bden < s.bnum * den);
   s.bnum = take ? num : s.bnum;
   s.bden = take ? den : s.bden;
   s.nbr = take ? nbr : s.nbr;

@@ -232,3 +232,41 @@ def test_edge_walk_uses_plane_records_only_for_coplanar_rays():
     assert eng.degenerate_rays == 0
     assert edge_case_scenario(lambda c, t, n: HostEmulTally(c, t, n, layout="edge")).degenerate_rays > 0
     assert golden_scenario(lambda c, t, n: HostEmulTally(c, t, n, layout="edge")).degenerate_rays > 0
+
+
+@pytest.mark.parametrize("seed", SEED)
+def test_degenerate_starts_and_tracks_conserve_length(seed):
+    """Particles on mesh vertices, edges and faces, tracks along edges, inside face planes and through
+    vertices: which of the touching tets gets a piece is a tie-break, but no particle may be lost, the
+    total tally must equal the total in-mesh track length and every particle must end in a tet that
+    contains its final position."""
+    coords, t2v = kuhn_box(3, 3, 3)
+    special = np.array([[0, 0, 0], [1, 1, 1], [2, 1, 0], [1.5, 1.5, 1.5], [1.5, 1.0, 1.0], [0.5, 0.5, 1.0],
+                        [1.0, 2.0, 1.0], [2.5, 2.5, 2.5], [1.0, 1.0, 0.5], [3, 3, 3], [0.25, 0.25, 0.25],
+                        [2.0, 0.5, 1.5], [1.25, 1.25, 2.0]], dtype=float)
+    rng = np.random.default_rng(5)
+    pairs = [(a, b) for a in range(len(special)) for b in range(len(special)) if a != b]
+    n = len(pairs)
+    start = np.array([special[a] for a, _ in pairs])
+    dest = np.array([special[b] for _, b in pairs])
+    w = rng.uniform(0.5, 1.0, n)
+    eng = HostEmulTally(coords, t2v, n, **seed)
+    eng.CopyInitialPosition(start.reshape(-1).copy())
+    assert not eng.flux.any()
+    eng.MoveToNextLocation(start.reshape(-1).copy(), dest.reshape(-1).copy(), np.ones(n, dtype=np.int8), w.copy())
+    assert eng.stats()["lost"] == 0
+    np.testing.assert_allclose(eng.flux.sum(), (np.linalg.norm(dest - start, axis=1) * w).sum(), rtol=1e-12)
+    # (a destination exactly on the hull is "reached" or clipped onto itself within the 2^-44 plane payload)
+    np.testing.assert_allclose(eng.positions, dest, rtol=0, atol=1e-12)
+    v = coords[t2v[eng.elem_ids]]
+    T = np.transpose(v[:, 1:] - v[:, :1], (0, 2, 1))
+    lam = np.linalg.solve(T, (eng.positions - v[:, 0])[..., None])[..., 0]
+    assert min(lam.min(), (1.0 - lam.sum(1)).min()) > -1e-12
+    # a second move back to generic points: the degenerate positions are valid starting states
+    back = rng.uniform(0.1, 2.9, size=(n, 3))
+    eng.MoveToNextLocation(dest.reshape(-1).copy(), back.reshape(-1).copy(), np.ones(n, dtype=np.int8), w.copy())
+    assert eng.stats()["lost"] == 0
+    np.testing.assert_array_equal(eng.positions, back)
+    orc = OraclePumiTally(coords, t2v, n)
+    orc.CopyInitialPosition(back.reshape(-1).copy())
+    np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)

@@ -278,15 +278,30 @@ PTB_HD void set_ray(Ray &r, double x, double y, double z, double tx, double ty, 
   r.entry = -1;
 }
 
-PTB_HD void start_tally(const WalkParams &P, int i, Ray &r, double x, double y, double z,
-                        Counters &c, bool writer) {
-  const double tx = PTB_LDG(P.dest + 3 * (size_t)i), ty = PTB_LDG(P.dest + 3 * (size_t)i + 1),
-               tz = PTB_LDG(P.dest + 3 * (size_t)i + 2);
+// NaN or infinity in the caller's numbers must not reach the tally or the stored state: x*0 is 0 for
+// every finite x and NaN otherwise.
+PTB_HD bool all_finite(double a, double b, double c) { return (a * 0.0 + b * 0.0 + c * 0.0) == 0.0; }
+
+// Tally phase towards (tx,ty,tz) with weight w.  A non-finite destination or weight turns the flight
+// into a zero-length one (the particle stays where it is, nothing is tallied) and counts as lost.
+PTB_HD void start_tally_to(Ray &r, double x, double y, double z, double tx, double ty, double tz, double w,
+                           Counters &c, bool writer) {
+  if (!all_finite(tx, ty, tz) || !all_finite(w, 0.0, 0.0)) {
+    tx = x; ty = y; tz = z;
+    w = 0.0;
+    if (writer) c.lost++;
+  }
   set_ray(r, x, y, z, tx, ty, tz);
   const double len = sqrt(r.ux * r.ux + r.uy * r.uy + r.uz * r.uz);
-  r.wl = PTB_LDG(P.weights + i) * len;
+  r.wl = w * len;
   r.stage = kStageTally;
   if (writer) c.tracks++;
+}
+
+PTB_HD void start_tally(const WalkParams &P, int i, Ray &r, double x, double y, double z,
+                        Counters &c, bool writer) {
+  start_tally_to(r, x, y, z, PTB_LDG(P.dest + 3 * (size_t)i), PTB_LDG(P.dest + 3 * (size_t)i + 1),
+                 PTB_LDG(P.dest + 3 * (size_t)i + 2), PTB_LDG(P.weights + i), c, writer);
 }
 
 // Phase 1 for a particle at (x,y,z) in tet r.e whose caller-side origin is (tx,ty,tz).
@@ -327,6 +342,10 @@ PTB_HD void begin_particle(const WalkParams &P, int i, Ray &r, Counters &c, bool
     const double tx = PTB_LDG(P.origin + 3 * (size_t)i), ty = PTB_LDG(P.origin + 3 * (size_t)i + 1),
                  tz = PTB_LDG(P.origin + 3 * (size_t)i + 2);
     if (tx != x || ty != y || tz != z) {
+      if (!all_finite(tx, ty, tz)) {  // unusable origin: the particle sits this move out
+        if (writer) c.lost++;
+        return;
+      }
       start_reloc(P, r, x, y, z, tx, ty, tz);
       return;
     }

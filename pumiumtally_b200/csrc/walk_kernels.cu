@@ -270,17 +270,15 @@ __device__ __forceinline__ void begin_from_stage(const WalkParams &P, const Part
   if (P.origin) {
     const double tx = st->origin[3 * s], ty = st->origin[3 * s + 1], tz = st->origin[3 * s + 2];
     if (tx != x || ty != y || tz != z) {
+      if (!all_finite(tx, ty, tz)) {  // unusable origin: the particle sits this move out
+        c.lost++;
+        return;
+      }
       start_reloc(P, r, x, y, z, tx, ty, tz);
       return;
     }
   }
-  if (P.dest) {
-    set_ray(r, x, y, z, st->dest[3 * s], st->dest[3 * s + 1], st->dest[3 * s + 2]);
-    const double len = sqrt(r.ux * r.ux + r.uy * r.uy + r.uz * r.uz);
-    r.wl = st->w[s] * len;
-    r.stage = kStageTally;
-    c.tracks++;
-  }
+  if (P.dest) start_tally_to(r, x, y, z, st->dest[3 * s], st->dest[3 * s + 1], st->dest[3 * s + 2], st->w[s], c, true);
 }
 
 // begin_particle() for a packed row (only flying particles have rows).  Returns the particle id.
@@ -289,17 +287,17 @@ __device__ __forceinline__ int begin_from_row(const WalkParams &P, const PackedR
   const uint32_t el = row->elem;
   const double ox = row->ox, oy = row->oy, oz = row->oz;
   if (el >> 31) {  // re-sourced: phase 1 from the stored position (rare)
+    if (!all_finite(ox, oy, oz)) {  // unusable origin: the particle sits this move out
+      c.lost++;
+      return id;
+    }
     const ParticleState s0 = load_state(P.state + id);
     r.e = s0.elem;
     start_reloc(P, r, s0.x, s0.y, s0.z, ox, oy, oz);
     return id;
   }
   r.e = (int32_t)(el & kIdMask);
-  set_ray(r, ox, oy, oz, row->dx, row->dy, row->dz);
-  const double len = sqrt(r.ux * r.ux + r.uy * r.uy + r.uz * r.uz);
-  r.wl = row->w * len;
-  r.stage = kStageTally;
-  c.tracks++;
+  start_tally_to(r, ox, oy, oz, row->dx, row->dy, row->dz, row->w, c, true);
   return id;
 }
 

@@ -220,3 +220,46 @@ def edge_case_scenario(make_engine):
     np.testing.assert_allclose(eng.positions[0], [2.0, 0.2, 0.1], atol=1e-13)
     np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
     return eng
+
+
+def non_finite_input_scenario(make_engine):
+    """NaN / infinity in the caller's arrays must not poison the tally or the stored particle state:
+    such particles sit the move out (counted as lost), everything else is unaffected."""
+    coords, t2v, wl = box_case((6, 6, 5), 4000)
+    n = wl.n
+    eng, orc = make_engine(coords, t2v, n), OraclePumiTally(coords, t2v, n)
+    init = wl.initial_positions()
+    for e in (eng, orc):
+        e.CopyInitialPosition(init.reshape(-1).copy())
+    o, d, f, w = wl.next_step()
+    f[:] = 1
+    bad_dest, bad_w, bad_origin = np.arange(0, 40), np.arange(40, 60), np.arange(60, 90)
+    d_bad, w_bad, o_bad = d.copy(), w.copy(), o.copy()
+    d_bad[bad_dest[:20], 1] = np.nan
+    d_bad[bad_dest[20:], 2] = np.inf
+    w_bad[bad_w[:10]] = np.nan
+    w_bad[bad_w[10:]] = -np.inf
+    o_bad[bad_origin[:15], 0] = np.nan
+    o_bad[bad_origin[15:], 2] = -np.inf
+    skip = np.concatenate([bad_dest, bad_w, bad_origin])
+    f_ref = f.copy()
+    f_ref[skip] = 0
+    eng.MoveToNextLocation(o_bad.reshape(-1).copy(), d_bad.reshape(-1).copy(), f.copy(), w_bad.copy())
+    orc.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f_ref, w.copy())
+    flux = eng.flux
+    assert np.isfinite(flux).all() and np.isfinite(eng.positions).all()
+    assert_flux_close(flux, orc.flux, "non-finite inputs")
+    good = np.ones(n, dtype=bool)
+    good[skip] = False
+    np.testing.assert_array_equal(eng.elem_ids[good], orc.elem_ids[good])
+    np.testing.assert_array_equal(eng.positions[bad_origin], orc.positions[bad_origin])  # untouched
+    assert eng.stats()["lost"] == len(skip)
+    # the next, clean move works for every particle
+    o2, d2, f2, w2 = wl.next_step()
+    f2[:] = 1
+    o2[skip] = d[skip]  # re-source the affected particles at valid points
+    for e in (eng, orc):
+        e.MoveToNextLocation(o2.reshape(-1).copy(), d2.reshape(-1).copy(), f2.copy(), w2.copy())
+    assert_flux_close(eng.flux, orc.flux, "after non-finite inputs")
+    np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+    return eng

@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import (ROOT, assert_flux_close, box_case, edge_case_scenario, run_workload)
+from helpers import (ROOT, assert_flux_close, box_case, edge_case_scenario, non_finite_input_scenario, run_workload)
 from oracle.oracle import OraclePumiTally
 from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, save_raw_mesh, tet_volumes
 from pumiumtally_b200.tally import PumiTally
@@ -672,3 +672,8 @@ def test_degenerate_starts_and_tracks_conserve_length(variant):
     orc = OraclePumiTally(coords, t2v, n)
     orc.CopyInitialPosition(back.reshape(-1).copy())
     np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 8, 16, 20, 24])
+def test_non_finite_inputs_do_not_poison_tally_or_state(variant):
+    non_finite_input_scenario(gpu_engine(variant))

@@ -8,7 +8,8 @@ import os
 import numpy as np
 import pytest
 
-from helpers import HostEmulTally, assert_flux_close, box_case, edge_case_scenario, run_workload
+from helpers import (HostEmulTally, assert_flux_close, box_case, edge_case_scenario, non_finite_input_scenario,
+                     run_workload)
 from oracle.oracle import OraclePumiTally
 from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, tet_volumes
 from pumiumtally_b200.workload import SyntheticWorkload
@@ -270,3 +271,8 @@ def test_degenerate_starts_and_tracks_conserve_length(seed):
     orc = OraclePumiTally(coords, t2v, n)
     orc.CopyInitialPosition(back.reshape(-1).copy())
     np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+
+
+@pytest.mark.parametrize("seed", SEED)
+def test_non_finite_inputs_do_not_poison_tally_or_state(seed):
+    non_finite_input_scenario(lambda c, t, n: HostEmulTally(c, t, n, **seed))

@@ -302,6 +302,19 @@ bool HostMesh::finalize(std::string *err) {
     }
   }
   if (degenerate) { *err = "mesh contains a degenerate (zero-volume) tet"; return false; }
+  // The plane offsets keep 44 mantissa bits: a crossing point is located to ~6e-14 of the largest
+  // coordinate, which has to stay small against a tet.  Far from the origin (|coordinate| beyond ~1e5 mean
+  // tet edges) the tally loses digits: 8e-7 relative at 1e6 (tests/test_host_emul.py::test_far_from_origin...).
+  {
+    double far = 0.0, vol = 0.0;
+    for (int d = 0; d < 3; ++d) far = std::max({far, std::fabs(bbox_lo[d]), std::fabs(bbox_hi[d])});
+    for (int64_t e = 0; e < ntets; ++e) vol += volume[e];
+    const double edge = std::cbrt(6.0 * vol / double(ntets));
+    if (far > 1e5 * edge)
+      fprintf(stderr, "[pumitally] WARNING: mesh coordinates reach %.3g, %.1e mean tet edges from the origin; "
+                      "translate the mesh (and the particle coordinates) towards the origin to keep the tally's precision\n",
+              far, far / edge);
+  }
   return true;
 }
 

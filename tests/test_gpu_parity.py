@@ -677,3 +677,23 @@ def test_degenerate_starts_and_tracks_conserve_length(variant):
 @pytest.mark.parametrize("variant", [0, 1, 2, 8, 16, 20, 24])
 def test_non_finite_inputs_do_not_poison_tally_or_state(variant):
     non_finite_input_scenario(gpu_engine(variant))
+
+
+@pytest.mark.parametrize("variant", [-1, 0, 16, 24])
+def test_zero_and_one_particle(variant):
+    coords, t2v = kuhn_box(2, 2, 2)
+    e = PumiTally.from_arrays(coords, t2v, 0)
+    e.set_option("variant", variant)
+    e.CopyInitialPosition(np.empty(0))
+    for _ in range(3):
+        e.MoveToNextLocation(np.empty(0), np.empty(0), np.empty(0, dtype=np.int8), np.empty(0))
+    assert not e.flux.any() and e.stats()["tracks"] == 0
+    e1, o1 = PumiTally.from_arrays(coords, t2v, 1), OraclePumiTally(coords, t2v, 1)
+    e1.set_option("variant", variant)
+    p0, p1, p2 = np.array([0.3, 0.2, 0.1]), np.array([1.7, 1.2, 0.4]), np.array([0.6, 1.1, 1.9])
+    for x in (e1, o1):
+        x.CopyInitialPosition(p0.copy())
+        x.MoveToNextLocation(p0.copy(), p1.copy(), np.ones(1, dtype=np.int8), np.ones(1))
+        x.MoveToNextLocation(p1.copy(), p2.copy(), np.ones(1, dtype=np.int8), np.full(1, 2.0))
+    assert_flux_close(e1.flux, o1.flux, "one particle")
+    np.testing.assert_array_equal(e1.elem_ids, o1.elem_ids)

@@ -301,3 +301,32 @@ def test_far_from_origin_meshes_lose_digits_gracefully(offset, flux_tol, capfd):
     rel = np.abs(eng.flux - orc.flux) / np.maximum(np.abs(orc.flux), 1e-300)
     assert rel.max() < flux_tol
     assert eng.stats()["lost"] == 0
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_randomised_meshes_and_tracks_parity(block):
+    """Seeded sweep: random Delaunay / jittered / anisotropic Kuhn meshes, random particle counts, track
+    lengths and collimation, both layouts, with and without the seed grid -- five moves each against the oracle."""
+    for seed in range(12 * block, 12 * block + 12):
+        rng = np.random.default_rng(seed)
+        kind = seed % 3
+        if kind == 0:
+            c, t = delaunay_box(int(rng.integers(30, 400)), seed=seed)
+            box = (1.0, 1.0, 1.0)
+        elif kind == 1:
+            dims = tuple(int(x) for x in rng.integers(1, 7, 3))
+            c, t = jitter_interior(*kuhn_box(*dims), amplitude=float(rng.uniform(0, 0.3)), seed=seed)
+            box = tuple(float(d) for d in dims)
+        else:
+            dims = tuple(int(x) for x in rng.integers(1, 9, 3))
+            box = tuple(float(x) for x in rng.uniform(0.3, 5, 3))
+            c, t = kuhn_box(*dims, *box)
+        n = int(rng.integers(1, 3000))
+        mean_length = float(rng.uniform(0.05, 3.0)) * min(box)
+        mu_min = float(rng.choice([-1.0, 0.5, 0.99]))
+        for layout in ("planes", "edge"):
+            for seed_grid in (False, True):
+                wl = SyntheticWorkload(box=box, num_particles=n, mean_length=mean_length, seed=seed, mu_min=mu_min)
+                eng = HostEmulTally(c, t, n, layout=layout, seed_grid=seed_grid)
+                run_workload(eng, OraclePumiTally(c, t, n), wl, steps=5, label=f"seed {seed} {layout} grid={seed_grid}")
+                assert eng.stats()["lost"] == 0

@@ -697,3 +697,30 @@ def test_zero_and_one_particle(variant):
         x.MoveToNextLocation(p1.copy(), p2.copy(), np.ones(1, dtype=np.int8), np.full(1, 2.0))
     assert_flux_close(e1.flux, o1.flux, "one particle")
     np.testing.assert_array_equal(e1.elem_ids, o1.elem_ids)
+
+
+@pytest.mark.parametrize("variant", [-1, 8, 16, 20, 24])
+def test_randomised_meshes_and_tracks_parity(variant):
+    """Seeded sweep through the C ABI: random Delaunay / jittered / anisotropic Kuhn meshes, random particle
+    counts, track lengths and collimation -- five moves each against the oracle."""
+    for seed in range(10):
+        rng = np.random.default_rng(seed)
+        kind = seed % 3
+        if kind == 0:
+            c, t = delaunay_box(int(rng.integers(30, 400)), seed=seed)
+            box = (1.0, 1.0, 1.0)
+        elif kind == 1:
+            dims = tuple(int(x) for x in rng.integers(1, 7, 3))
+            c, t = jitter_interior(*kuhn_box(*dims), amplitude=float(rng.uniform(0, 0.3)), seed=seed)
+            box = tuple(float(d) for d in dims)
+        else:
+            dims = tuple(int(x) for x in rng.integers(1, 9, 3))
+            box = tuple(float(x) for x in rng.uniform(0.3, 5, 3))
+            c, t = kuhn_box(*dims, *box)
+        n = int(rng.integers(1, 3000))
+        wl = SyntheticWorkload(box=box, num_particles=n, mean_length=float(rng.uniform(0.05, 3.0)) * min(box), seed=seed,
+                               mu_min=float(rng.choice([-1.0, 0.5, 0.99])))
+        eng = PumiTally.from_arrays(c, t, n)
+        eng.set_option("variant", variant)
+        run_workload(eng, OraclePumiTally(c, t, n), wl, steps=5, label=f"seed {seed} v{variant}")
+        assert eng.stats()["lost"] == 0

@@ -299,6 +299,26 @@ bool HostMesh::finalize(std::string *err) {
       uint32_t pay = ((uint32_t(e) ^ (nb < 0 ? idmask : uint32_t(nb))) & idmask) | (uint32_t(f ^ back) << 30);
       for (int q = 0; q < 4; ++q)
         r.d[4 * f + q] = bdouble(dbits(p[q]) | uint64_t((pay >> (8 * q)) & 0xffu));
+      if (nb < 0) {
+        // Hull face: truncation and payload move the stored plane by ~1e-13 either way.  Make it err
+        // outwards only: raise the offset, in steps of the 44-bit grid (the payload byte stays), until the
+        // three face vertices satisfy n.x <= c with the normal exactly as stored.  A point exactly on the
+        // hull is then inside (a destination there is reached, a track along the hull surface is walked),
+        // and what leaves the mesh is clipped at most ~1e-13 further out.  Interior faces keep the
+        // symmetric truncation: both tets must see the identical plane.
+        const double nx = r.d[4 * f], ny = r.d[4 * f + 1], nz = r.d[4 * f + 2];
+        const double need = std::max({nx * A[0] + ny * A[1] + nz * A[2], nx * B[0] + ny * B[1] + nz * B[2],
+                                      nx * C[0] + ny * C[1] + nz * C[2]});
+        double c = r.d[4 * f + 3];
+        for (int guard = 0; guard < 64 && !(c >= need); ++guard) {
+          uint64_t u = dbits(c);
+          if (c > 0.0) u += 256;                       // larger magnitude, same low byte
+          else if (c < 0.0 && (u & 0x7fffffffffffff00ull) > 256) u -= 256;  // smaller magnitude
+          else u = dbits(std::ldexp(1.0, -1000)) | (u & 0xffu);             // through zero: a tiny positive offset
+          c = bdouble(u);
+        }
+        r.d[4 * f + 3] = c;
+      }
     }
   }
   if (degenerate) { *err = "mesh contains a degenerate (zero-volume) tet"; return false; }

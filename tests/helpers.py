@@ -263,3 +263,33 @@ def non_finite_input_scenario(make_engine):
     assert_flux_close(eng.flux, orc.flux, "after non-finite inputs")
     np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
     return eng
+
+
+def lattice_track_scenario(make_engine, seeds):
+    """Tracks between points of the quarter-cell lattice of Kuhn boxes: along the hull surface, along
+    edges, inside face planes, through vertices.  Attribution to a particular tet is a tie-break there;
+    what must hold: nothing lost or stopped early, destinations reached exactly, total tally equal to the
+    total track length, final tet containing the final position."""
+    for seed in seeds:
+        rng = np.random.default_rng(seed)
+        dims = tuple(int(x) for x in rng.integers(1, 6, 3))
+        lengths = tuple(float(x) for x in rng.choice([0.5, 1.0, 2.0, 3.0], 3)) if seed % 2 else tuple(float(d) for d in dims)
+        coords, t2v = kuhn_box(*dims, *lengths)
+        h = np.array(lengths) / np.array(dims)
+        a = rng.integers(0, 4 * np.array(dims) + 1, size=(400, 3)) * h / 4.0
+        b = rng.integers(0, 4 * np.array(dims) + 1, size=(400, 3)) * h / 4.0
+        keep = np.abs(a - b).sum(1) > 0
+        a, b = a[keep], b[keep]
+        n = len(a)
+        w = rng.uniform(0.5, 1.0, n)
+        eng = make_engine(coords, t2v, n)
+        eng.CopyInitialPosition(a.reshape(-1).copy())
+        np.testing.assert_array_equal(eng.positions, a, err_msg=f"seed {seed}: localisation")
+        eng.MoveToNextLocation(a.reshape(-1).copy(), b.reshape(-1).copy(), np.ones(n, dtype=np.int8), w.copy())
+        assert eng.stats()["lost"] == 0
+        np.testing.assert_array_equal(eng.positions, b, err_msg=f"seed {seed}: destinations")
+        np.testing.assert_allclose(eng.flux.sum(), (np.linalg.norm(b - a, axis=1) * w).sum(), rtol=1e-12)
+        v = coords[t2v[eng.elem_ids]]
+        T = np.transpose(v[:, 1:] - v[:, :1], (0, 2, 1))
+        lam = np.linalg.solve(T, (eng.positions - v[:, 0])[..., None])[..., 0]
+        assert min(lam.min(), (1.0 - lam.sum(1)).min()) > -1e-11, f"seed {seed}"

@@ -301,21 +301,30 @@ bool HostMesh::finalize(std::string *err) {
         r.d[4 * f + q] = bdouble(dbits(p[q]) | uint64_t((pay >> (8 * q)) & 0xffu));
       if (nb < 0) {
         // Hull face: truncation and payload move the stored plane by ~1e-13 either way.  Make it err
-        // outwards only: raise the offset, in steps of the 44-bit grid (the payload byte stays), until the
-        // three face vertices satisfy n.x <= c with the normal exactly as stored.  A point exactly on the
+        // outwards only: raise the offset on the 44-bit grid (the payload byte stays) until the three face
+        // vertices satisfy n.x <= c, with the normal exactly as stored and a margin for the rounding of n.x.  A point exactly on the
         // hull is then inside (a destination there is reached, a track along the hull surface is walked),
         // and what leaves the mesh is clipped at most ~1e-13 further out.  Interior faces keep the
         // symmetric truncation: both tets must see the identical plane.
         const double nx = r.d[4 * f], ny = r.d[4 * f + 1], nz = r.d[4 * f + 2];
         const double need = std::max({nx * A[0] + ny * A[1] + nz * A[2], nx * B[0] + ny * B[1] + nz * B[2],
                                       nx * C[0] + ny * C[1] + nz * C[2]});
+        // margin for the rounding of n.o in the kernels (fused multiply-adds there, none here; the
+        // numerator and the denominator of the same crossing round differently): a few ulps of the largest
+        // value n.o can take for a ray origin anywhere in the mesh
+        const double mag = std::fabs(nx) * std::max(std::fabs(bbox_lo[0]), std::fabs(bbox_hi[0])) +
+                           std::fabs(ny) * std::max(std::fabs(bbox_lo[1]), std::fabs(bbox_hi[1])) +
+                           std::fabs(nz) * std::max(std::fabs(bbox_lo[2]), std::fabs(bbox_hi[2]));
+        const double target = need + 32.0 * 2.220446049250313e-16 * mag;
         double c = r.d[4 * f + 3];
-        for (int guard = 0; guard < 64 && !(c >= need); ++guard) {
-          uint64_t u = dbits(c);
-          if (c > 0.0) u += 256;                       // larger magnitude, same low byte
-          else if (c < 0.0 && (u & 0x7fffffffffffff00ull) > 256) u -= 256;  // smaller magnitude
-          else u = dbits(std::ldexp(1.0, -1000)) | (u & 0xffu);             // through zero: a tiny positive offset
-          c = bdouble(u);
+        if (!(c >= target)) {
+          const uint64_t low = dbits(c) & 0xffu;  // the payload byte stays
+          if (target > 0.0) {                     // round the magnitude up on the 44-bit grid
+            c = bdouble((((dbits(target) >> 8) + 1) << 8) | low);
+          } else {                                // negative (or zero): round the magnitude down
+            const uint64_t m = dbits(std::fabs(target)) >> 8;
+            c = m > 1 ? -bdouble(((m - 1) << 8) | low) : bdouble(low);
+          }
         }
         r.d[4 * f + 3] = c;
       }

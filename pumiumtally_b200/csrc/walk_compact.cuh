@@ -47,6 +47,11 @@ struct EdgeRay {
   int32_t dv;                                 // vertex id of role 3 in the current tet
 };
 
+// |edge function| <= kEdgeTol * (sum of the magnitudes of its terms) counts as zero.  The terms of q = u x P
+// carry their own rounding, hence the generous factor; a generic ray is 1e-13 away from an edge with
+// probability ~1e-13 per crossing, and then merely finishes on the plane records.
+constexpr double kEdgeTol = 1024.0 * 2.220446049250313e-16;
+
 PTB_HD uint32_t sel4(int k, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   return k == 0 ? a : (k == 1 ? b : (k == 2 ? c : d));
 }
@@ -88,10 +93,16 @@ PTB_HD bool edge_step(const Ray &r, EdgeRay &g, const TetLinks &L, double dx, do
   const double sa = qx * g.ax + qy * g.ay + qz * g.az;
   const double sb = qx * g.bx + qy * g.by + qz * g.bz;
   const double sc = qx * g.cx + qy * g.cy + qz * g.cz;
-  // role whose vertex is left behind (the exit face is the one opposite it).  A zero, or one of
-  // the two sign patterns that cannot occur geometrically (+++ / ---), hands the ray to the planes.
+  // role whose vertex is left behind (the exit face is the one opposite it).  An edge function that is
+  // zero within the rounding of its own terms (the compiler may or may not fuse the multiply-adds, so
+  // "exactly zero" is not a portable test), or one of the two sign patterns that cannot occur
+  // geometrically (+++ / ---), hands the ray to the planes.
+  const double aqx = fabs(qx), aqy = fabs(qy), aqz = fabs(qz);
+  const double ta = kEdgeTol * (aqx * fabs(g.ax) + aqy * fabs(g.ay) + aqz * fabs(g.az));
+  const double tb = kEdgeTol * (aqx * fabs(g.bx) + aqy * fabs(g.by) + aqz * fabs(g.bz));
+  const double tc = kEdgeTol * (aqx * fabs(g.cx) + aqy * fabs(g.cy) + aqz * fabs(g.cz));
   const bool pa = sa > 0.0, pb = sb > 0.0, pc = sc > 0.0;
-  if (sa == 0.0 || sb == 0.0 || sc == 0.0 || (pa == pb && pb == pc)) return false;
+  if (!(fabs(sa) > ta) || !(fabs(sb) > tb) || !(fabs(sc) > tc) || (pa == pb && pb == pc)) return false;
   const int z = pa ? (pb ? 0 : 2) : (pc ? 1 : 0);
   const int e = r.entry;
   int s0 = e & 3, s1 = (e >> 2) & 3, s2 = (e >> 4) & 3;
@@ -138,7 +149,18 @@ PTB_UNROLL
   else if (m01 > 0.0 && m13 > 0.0 && m03 < 0.0) { f = 2; ia = 0; ib = 1; ic = 3; }
   else if (m02 > 0.0 && m12 < 0.0 && m01 < 0.0) { f = 3; ia = 0; ib = 2; ic = 1; }
   else return false;
-  if (m01 == 0.0 || m02 == 0.0 || m03 == 0.0 || m12 == 0.0 || m13 == 0.0 || m23 == 0.0) return false;
+  {  // any edge function within rounding of zero: planes (see edge_step)
+    double t[4];
+PTB_UNROLL
+    for (int i = 0; i < 4; ++i) t[i] = fabs(q[i][0]) + fabs(q[i][1]) + fabs(q[i][2]);
+    double pm[4];
+PTB_UNROLL
+    for (int i = 0; i < 4; ++i) pm[i] = fmax(fabs(p[i][0]), fmax(fabs(p[i][1]), fabs(p[i][2])));
+    if (!(fabs(m01) > kEdgeTol * t[0] * pm[1]) || !(fabs(m02) > kEdgeTol * t[0] * pm[2]) ||
+        !(fabs(m03) > kEdgeTol * t[0] * pm[3]) || !(fabs(m12) > kEdgeTol * t[1] * pm[2]) ||
+        !(fabs(m13) > kEdgeTol * t[1] * pm[3]) || !(fabs(m23) > kEdgeTol * t[2] * pm[3]))
+      return false;
+  }
   auto pick = [&](int i, int d) { return i == 0 ? p[0][d] : (i == 1 ? p[1][d] : (i == 2 ? p[2][d] : p[3][d])); };
   g.ax = pick(ia, 0); g.ay = pick(ia, 1); g.az = pick(ia, 2);
   g.bx = pick(ib, 0); g.by = pick(ib, 1); g.bz = pick(ib, 2);

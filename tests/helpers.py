@@ -68,7 +68,10 @@ _EMUL = None
 def emul_lib():
     global _EMUL
     if _EMUL is None:
-        so = os.path.join(HERE, "host_emul", "libptb_emul.so")
+        # PTB_EMUL_FMA=1: let g++ contract a*b+c into fused multiply-adds, as nvcc does for the device
+        # code, so that rounding-sensitive (degenerate-input) tests see both flavours of the arithmetic
+        fma = os.environ.get("PTB_EMUL_FMA") == "1"
+        so = os.path.join(HERE, "host_emul", "libptb_emul_fma.so" if fma else "libptb_emul.so")
         srcs = [os.path.join(HERE, "host_emul", "emul_walk.cpp"),
                 os.path.join(ROOT, "pumiumtally_b200", "csrc", "tet_mesh.cpp"),
                 os.path.join(ROOT, "pumiumtally_b200", "csrc", "osh_reader.cpp"),
@@ -76,6 +79,7 @@ def emul_lib():
         deps = srcs + [os.path.join(ROOT, "pumiumtally_b200", "csrc", h) for h in ("walk_core.cuh", "walk_compact.cuh", "tet_mesh.hpp", "seed_grid.hpp")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fopenmp",
+                                   *(["-mfma", "-ffp-contract=fast"] if fma else ["-ffp-contract=off"]),
                                    "-I", os.path.join(ROOT, "pumiumtally_b200", "csrc"),
                                    "-I", os.path.join(ROOT, "include"), *srcs, "-o", so, "-lz"])
         L = C.CDLL(so)

@@ -6,6 +6,8 @@
 // It is never linked into libpumitally.so and is not a fallback: the product
 // refuses to construct an engine without a CUDA device.
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -63,6 +65,7 @@ struct Emul {
     if (g) P.grid = *g;
     DeviceStats &stats = *st;
     const int n = count;
+    const bool trace = std::getenv("PTB_EMUL_TRACE") != nullptr;
     for (int i = 0; i < n; ++i) {
       Counters c;
       Ray r;
@@ -103,6 +106,8 @@ struct Emul {
           scan_face(sc, rec[4 * fk], rec[4 * fk + 1], rec[4 * fk + 2], rec[4 * fk + 3], nb, bk, r.ox, r.oy,
                     r.oz, r.ux, r.uy, r.uz);
         }
+        if (trace) fprintf(stderr, "  p%d tet %d entry %d stage %d tcur %.17g texit %.17g (num %.17g den %.17g) next %d\n", i, r.e, en,
+                           r.stage, r.tcur, exit_parameter(sc), sc.bnum, sc.bden, sc.nbr);
         advance(P, i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
         if (r.iters == 0) planes = !edge;  // a new ray (phase 2 after phase 1) starts on the fast path again
       }

@@ -62,15 +62,16 @@ def run_workload(engine, oracle, workload, steps, check_each_step=True, label=""
 # ---------------------------------------------------------------------------
 # test-only host build of the device walk logic (tests/host_emul/emul_walk.cpp)
 # ---------------------------------------------------------------------------
-_EMUL = None
+_EMUL = {}
 
 
-def emul_lib():
-    global _EMUL
-    if _EMUL is None:
-        # PTB_EMUL_FMA=1: let g++ contract a*b+c into fused multiply-adds, as nvcc does for the device
-        # code, so that rounding-sensitive (degenerate-input) tests see both flavours of the arithmetic
+def emul_lib(fma=None):
+    """fma=True: let g++ contract a*b+c into fused multiply-adds, as nvcc does for the device code, so
+    that rounding-sensitive (degenerate-input) tests see both flavours of the arithmetic.  Default:
+    the environment variable PTB_EMUL_FMA=1, else off."""
+    if fma is None:
         fma = os.environ.get("PTB_EMUL_FMA") == "1"
+    if fma not in _EMUL:
         so = os.path.join(HERE, "host_emul", "libptb_emul_fma.so" if fma else "libptb_emul.so")
         srcs = [os.path.join(HERE, "host_emul", "emul_walk.cpp"),
                 os.path.join(ROOT, "pumiumtally_b200", "csrc", "tet_mesh.cpp"),
@@ -98,15 +99,16 @@ def emul_lib():
         L.ptb_emul_degenerate_rays.restype = C.c_ulonglong
         L.ptb_emul_degenerate_rays.argtypes = [C.c_void_p]
         L.ptb_emul_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        _EMUL = L
-    return _EMUL
+        _EMUL[fma] = L
+    return _EMUL[fma]
 
 
 class HostEmulTally:
     """The CUDA kernels' per-ray state machine compiled for the host (tests only)."""
 
-    def __init__(self, coords=None, tet2vert=None, num_particles=0, spec=None, seed_grid=False, layout="planes"):
-        self._L = emul_lib()
+    def __init__(self, coords=None, tet2vert=None, num_particles=0, spec=None, seed_grid=False, layout="planes",
+                 fma=None):
+        self._L = emul_lib(fma)
         self._want_grid = seed_grid
         self.num_particles = int(num_particles)
         if spec is not None:

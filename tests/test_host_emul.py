@@ -331,6 +331,18 @@ def test_randomised_meshes_and_tracks_parity(block):
                 assert eng.stats()["lost"] == 0
 
 
+@pytest.mark.parametrize("fma", [False, True], ids=["plain", "fma"])
 @pytest.mark.parametrize("seed", SEED)
-def test_lattice_tracks_on_hull_faces_edges_and_vertices(seed):
-    lattice_track_scenario(lambda c, t, n: HostEmulTally(c, t, n, **seed), range(30))
+def test_lattice_tracks_on_hull_faces_edges_and_vertices(seed, fma):
+    """Both flavours of the arithmetic: plain, and with fused multiply-adds as the device code has them."""
+    lattice_track_scenario(lambda c, t, n: HostEmulTally(c, t, n, fma=fma, **seed), range(30))
+
+
+@pytest.mark.parametrize("seed", SEED)
+def test_reference_scenarios_with_fused_multiply_adds(seed):
+    """The golden, edge-case and degenerate scenarios once more with the device flavour of rounding."""
+    mk = lambda c, t, n: HostEmulTally(c, t, n, fma=True, **seed)
+    golden_scenario(mk)
+    check_c1_fixture(mk)
+    edge_case_scenario(mk)
+    non_finite_input_scenario(mk)

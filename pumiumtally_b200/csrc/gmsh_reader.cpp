@@ -16,6 +16,8 @@
 namespace ptb {
 namespace {
 
+constexpr long long kMaxCount = 2000000000LL;  // ids are 32-bit in the engine
+
 bool seek_section(std::istream &f, const std::string &name) {
   std::string line;
   while (std::getline(f, line)) {
@@ -49,6 +51,7 @@ bool read_gmsh_mesh(const std::string &path, std::vector<double> *coords, std::v
   if (version < 4.0) {
     long long n = 0;
     f >> n;
+    if (!f || n < 0 || n > kMaxCount) { *err = "implausible node count in $Nodes"; return false; }
     coords->reserve(size_t(3) * n);
     for (long long i = 0; i < n; ++i) {
       long long id; double x, y, z;
@@ -60,9 +63,11 @@ bool read_gmsh_mesh(const std::string &path, std::vector<double> *coords, std::v
     if (!seek_section(f, "$Elements")) { *err = "Gmsh file has no $Elements"; return false; }
     long long ne = 0;
     f >> ne;
+    if (!f || ne < 0 || ne > kMaxCount) { *err = "implausible element count in $Elements"; return false; }
     for (long long e = 0; e < ne; ++e) {
       long long id; int type, ntags;
       f >> id >> type >> ntags;
+      if (!f || ntags < 0 || ntags > 64) { *err = "damaged element record in $Elements"; return false; }
       for (int k = 0; k < ntags; ++k) { long long tag; f >> tag; }
       const int nn = nodes_of_type(type);
       if (nn < 0) { *err = "unsupported Gmsh element type " + std::to_string(type); return false; }
@@ -79,10 +84,12 @@ bool read_gmsh_mesh(const std::string &path, std::vector<double> *coords, std::v
   } else {
     long long nblocks = 0, n = 0, mintag = 0, maxtag = 0;
     f >> nblocks >> n >> mintag >> maxtag;
+    if (!f || nblocks < 0 || n < 0 || nblocks > kMaxCount || n > kMaxCount) { *err = "implausible counts in $Nodes"; return false; }
     coords->reserve(size_t(3) * n);
     for (long long b = 0; b < nblocks; ++b) {
       int edim, etag, parametric; long long nb;
       f >> edim >> etag >> parametric >> nb;
+      if (!f || nb < 0 || nb > n) { *err = "implausible node block in $Nodes"; return false; }
       std::vector<long long> ids(nb);
       for (long long i = 0; i < nb; ++i) f >> ids[i];
       for (long long i = 0; i < nb; ++i) {
@@ -97,9 +104,11 @@ bool read_gmsh_mesh(const std::string &path, std::vector<double> *coords, std::v
     if (!seek_section(f, "$Elements")) { *err = "Gmsh file has no $Elements"; return false; }
     long long ne = 0;
     f >> nblocks >> ne >> mintag >> maxtag;
+    if (!f || nblocks < 0 || ne < 0 || nblocks > kMaxCount || ne > kMaxCount) { *err = "implausible counts in $Elements"; return false; }
     for (long long b = 0; b < nblocks; ++b) {
       int edim, etag, type; long long nb;
       f >> edim >> etag >> type >> nb;
+      if (!f || nb < 0 || nb > ne) { *err = "implausible element block in $Elements"; return false; }
       const int nn = nodes_of_type(type);
       if (nn < 0) { *err = "unsupported Gmsh element type " + std::to_string(type); return false; }
       for (long long i = 0; i < nb; ++i) {

@@ -99,6 +99,15 @@ bool read_raw_mesh(const std::string &path, std::vector<double> *coords,
 }
 
 bool HostMesh::load(const std::string &spec, std::string *err) {
+  try {
+    return load_unguarded(spec, err);
+  } catch (const std::exception &ex) {  // e.g. an absurd element count in a damaged file
+    *err = std::string("cannot load mesh ") + spec + ": " + ex.what();
+    return false;
+  }
+}
+
+bool HostMesh::load_unguarded(const std::string &spec, std::string *err) {
   coords.clear();
   t2v.clear();
   if (spec.empty()) {
@@ -147,6 +156,8 @@ bool HostMesh::finalize(std::string *err) {
   if (ntets >= int64_t(0x3fffffff)) { *err = "too many tets: element ids are 30-bit"; return false; }
   for (size_t i = 0; i < t2v.size(); ++i)
     if (t2v[i] < 0 || t2v[i] >= nverts) { *err = "tet2vert index out of range"; return false; }
+  for (size_t i = 0; i < coords.size(); ++i)
+    if (!(std::fabs(coords[i]) < 1e150)) { *err = "mesh coordinates must be finite (and below 1e150)"; return false; }
 
   for (int d = 0; d < 3; ++d) { bbox_lo[d] = coords[d]; bbox_hi[d] = coords[d]; }
   for (int64_t v = 0; v < nverts; ++v)
@@ -179,7 +190,8 @@ bool HostMesh::finalize(std::string *err) {
       for (int i = 0; i < 4; ++i)
         for (int d = 0; d < 3; ++d) c[d] += 0.25 * coords[3 * size_t(t2v[4 * e + i]) + d];
       auto cell = [&](double x, double lo, int64_t n) {
-        return std::min<int64_t>(std::max<int64_t>(int64_t((x - lo) / h), 0), n - 1);
+        const double q = (x - lo) / h;  // clamped as a double: the cast of a huge or non-finite quotient is undefined
+        return q > 0.0 ? (q < double(n - 1) ? int64_t(q) : n - 1) : int64_t(0);
       };
       const int64_t cx = cell(c[0], bbox_lo[0], gx), cy = cell(c[1], bbox_lo[1], gy), cz = cell(c[2], bbox_lo[2], gz);
       int64_t k = (cz * gy + cy) * gx + cx;

@@ -99,6 +99,7 @@ struct HostMesh {
 
   // "box:nx,ny,nz[,lx,ly,lz]" | raw mesh file | Gmsh .msh (ASCII 2.2 / 4.1) | Omega_h .osh directory.
   bool load(const std::string &spec, std::string *err);
+  bool load_unguarded(const std::string &spec, std::string *err);
   bool from_arrays(const double *coords, int64_t nverts, const int32_t *tet2vert, int64_t ntets,
                    std::string *err);
   // adjacency + volumes + packed records; called by load()/from_arrays().

@@ -89,7 +89,14 @@ bool read_raw_mesh(const std::string &path, std::vector<double> *coords,
   if (!f || std::memcmp(magic, "PUMITB2\0", 8) != 0) { *err = "not a raw mesh file: " + path; return false; }
   int64_t n[2];
   f.read(reinterpret_cast<char *>(n), 16);
-  if (!f || n[0] <= 0 || n[1] <= 0) { *err = "bad raw mesh header"; return false; }
+  if (!f || n[0] <= 0 || n[1] <= 0 || n[0] > 2000000000LL || n[1] > 2000000000LL) { *err = "bad raw mesh header"; return false; }
+  {  // the counts must fit the file before anything is allocated
+    const std::streampos here = f.tellg();
+    f.seekg(0, std::ios::end);
+    const int64_t remaining = int64_t(f.tellg() - here);
+    f.seekg(here);
+    if (remaining < 24 * n[0] + 16 * n[1]) { *err = "truncated raw mesh file"; return false; }
+  }
   coords->resize(size_t(3) * n[0]);
   t2v->resize(size_t(4) * n[1]);
   f.read(reinterpret_cast<char *>(coords->data()), std::streamsize(coords->size() * 8));
@@ -122,8 +129,11 @@ bool HostMesh::load_unguarded(const std::string &spec, std::string *err) {
     std::string tok;
     while (n < 6 && std::getline(ss, tok, ',')) v[n++] = std::atof(tok.c_str());
     if (n != 3 && n != 6) { *err = "box spec is box:nx,ny,nz[,lx,ly,lz]"; return false; }
+    for (int k = 0; k < 3; ++k)
+      if (!(v[k] >= 1.0 && v[k] <= 1e6)) { *err = "box spec needs 1 <= nx,ny,nz <= 1e6"; return false; }
+    for (int k = 3; k < n; ++k)
+      if (!(v[k] > 0.0 && v[k] < 1e150)) { *err = "box spec needs positive, finite lx,ly,lz"; return false; }
     int nx = int(v[0]), ny = int(v[1]), nz = int(v[2]);
-    if (nx < 1 || ny < 1 || nz < 1) { *err = "box spec needs nx,ny,nz >= 1"; return false; }
     if (int64_t(nx) * ny * nz * 6 > int64_t(2000000000)) { *err = "box too large for int32 element ids"; return false; }
     double lx = n == 6 ? v[3] : nx, ly = n == 6 ? v[4] : ny, lz = n == 6 ? v[5] : nz;
     build_kuhn_box(nx, ny, nz, lx, ly, lz, &coords, &t2v);

@@ -85,11 +85,19 @@ pumitally_engine *pumitally_create_from_arrays(const double *coords, int64_t nve
 }
 
 int pumitally_copy_initial_position(pumitally_engine *e, const double *xyz, int32_t size) {
+  if (size > 0 && !xyz) {
+    fprintf(stderr, "[pumitally] ERROR: CopyInitialPosition: null position array\n");
+    return 1;
+  }
   return guarded(e, [&](ptb::Engine &g) { return g.copy_initial_position(xyz, size); });
 }
 
 int pumitally_move_to_next_location(pumitally_engine *e, const double *origin, const double *dest,
                                     int8_t *flying, const double *weights, int32_t size) {
+  if (size > 0 && (!origin || !dest || !flying || !weights)) {
+    fprintf(stderr, "[pumitally] ERROR: MoveToNextLocation: null input array\n");
+    return 1;
+  }
   return guarded(e, [&](ptb::Engine &g) {
     return g.move_to_next_location(origin, dest, flying, weights, size);
   });

@@ -17,7 +17,11 @@
 
 #if defined(__CUDACC__)
 #define PTB_HD __host__ __device__ __forceinline__
+#if defined(__CUDA_ARCH__)
 #define PTB_UNROLL _Pragma("unroll")
+#else
+#define PTB_UNROLL  // nvcc's host pass hands the pragma to g++, which does not know it
+#endif
 #else
 #define PTB_HD inline
 #define PTB_UNROLL

@@ -97,7 +97,7 @@ struct HostMesh {
   }
   double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};
 
-  // "box:nx,ny,nz[,lx,ly,lz]" | raw mesh file | Gmsh .msh (ASCII 2.2 / 4.1) | Omega_h .osh directory.
+  // "box:nx,ny,nz[,lx,ly,lz]" | raw mesh file | Gmsh .msh (2.2 / 4.1, ASCII or binary) | Omega_h .osh directory.
   bool load(const std::string &spec, std::string *err);
   bool load_unguarded(const std::string &spec, std::string *err);
   bool from_arrays(const double *coords, int64_t nverts, const int32_t *tet2vert, int64_t ntets,

@@ -116,12 +116,43 @@ def save_raw_mesh(path: str, coords, tet2vert) -> None:
         f.write(tet2vert.tobytes())
 
 
-def save_gmsh(path: str, coords, tet2vert, version: str = "2.2", node_id_offset: int = 1) -> None:
-    """Write an ASCII Gmsh file (format 2.2 or 4.1) holding the nodes and the tets as element
+def save_gmsh(path: str, coords, tet2vert, version: str = "2.2", node_id_offset: int = 1, binary: bool = False) -> None:
+    """Write a Gmsh file (format 2.2 or 4.1, ASCII or binary) holding the nodes and the tets as element
     type 4, plus one boundary triangle and one point element that readers must skip."""
     coords = np.asarray(coords, dtype=np.float64)
     t2v = np.asarray(tet2vert, dtype=np.int64) + node_id_offset
     nv, nt = len(coords), len(t2v)
+    if binary:
+        import struct
+
+        with open(path, "wb") as f:
+            if version.startswith("2"):
+                f.write(b"$MeshFormat\n2.2 1 8\n" + struct.pack("<i", 1) + b"\n$EndMeshFormat\n$Nodes\n%d\n" % nv)
+                for i, xyz in enumerate(coords):
+                    f.write(struct.pack("<i3d", i + node_id_offset, *xyz))
+                f.write(b"\n$EndNodes\n$Elements\n%d\n" % (nt + 2))
+                f.write(struct.pack("<3i", 15, 1, 2) + struct.pack("<4i", 1, 0, 1, int(t2v[0, 0])))
+                f.write(struct.pack("<3i", 2, 1, 2) + struct.pack("<6i", 2, 0, 1, *(int(v) for v in t2v[0, :3])))
+                f.write(struct.pack("<3i", 4, nt, 2))
+                for e, t in enumerate(t2v):
+                    f.write(struct.pack("<7i", e + 3, 0, 1, *(int(v) for v in t)))
+                f.write(b"\n$EndElements\n")
+            else:
+                f.write(b"$MeshFormat\n4.1 1 8\n" + struct.pack("<i", 1) + b"\n$EndMeshFormat\n$Nodes\n")
+                f.write(struct.pack("<4Q", 1, nv, node_id_offset, nv + node_id_offset - 1))
+                f.write(struct.pack("<3iQ", 3, 1, 0, nv))
+                f.write(np.arange(node_id_offset, nv + node_id_offset, dtype=np.uint64).tobytes())
+                f.write(coords.tobytes())
+                f.write(b"\n$EndNodes\n$Elements\n")
+                f.write(struct.pack("<4Q", 2, nt + 1, 1, nt + 1))
+                f.write(struct.pack("<3iQ", 2, 1, 2, 1) + struct.pack("<4Q", 1, *(int(v) for v in t2v[0, :3])))
+                f.write(struct.pack("<3iQ", 3, 1, 4, nt))
+                rec = np.empty((nt, 5), dtype=np.uint64)
+                rec[:, 0] = np.arange(2, nt + 2)
+                rec[:, 1:] = t2v
+                f.write(rec.tobytes())
+                f.write(b"\n$EndElements\n")
+        return
     with open(path, "w") as f:
         if version.startswith("2"):
             f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % nv)

@@ -41,15 +41,16 @@ def test_box_spec_matches_numpy_generator():
     np.testing.assert_allclose(v, tet_volumes(cn, tn), rtol=1e-13)
 
 
+@pytest.mark.parametrize("binary", [False, True], ids=["ascii", "binary"])
 @pytest.mark.parametrize("version", ["2.2", "4.1"])
-def test_gmsh_ingest(tmp_path, version):
-    """Gmsh .msh (ASCII 2.2 / 4.1) -> same mesh as the arrays it was written from; non-tet
+def test_gmsh_ingest(tmp_path, version, binary):
+    """Gmsh .msh (2.2 / 4.1, ASCII or binary) -> same mesh as the arrays it was written from; non-tet
     elements and 1-based node ids are handled."""
     from pumiumtally_b200.mesh import save_gmsh
 
     c, t = jitter_interior(*kuhn_box(3, 2, 2), amplitude=0.1)
     path = str(tmp_path / "mesh.msh")
-    save_gmsh(path, c, t, version=version)
+    save_gmsh(path, c, t, version=version, binary=binary)
     e = HostEmulTally(spec=path, num_particles=1)
     cm, tm, vm = e.mesh_arrays()
     np.testing.assert_array_equal(tm, t)
@@ -348,7 +349,7 @@ def test_reference_scenarios_with_fused_multiply_adds(seed):
     non_finite_input_scenario(mk)
 
 
-@pytest.mark.parametrize("fmt", ["osh", "osh_raw", "msh4", "msh2"])
+@pytest.mark.parametrize("fmt", ["osh", "osh_raw", "msh4", "msh2", "msh4_binary", "msh2_binary"])
 def test_damaged_mesh_files_are_rejected_or_loaded_never_crash(tmp_path, fmt):
     """Random byte mutations / truncations of valid mesh files: the loader must either load a valid mesh
     or report an error (the same campaign ran clean under ASan/UBSan with 14,000 mutations)."""
@@ -361,7 +362,7 @@ def test_damaged_mesh_files_are_rejected_or_loaded_never_crash(tmp_path, fmt):
         target = os.path.join(path, "0.osh")
     else:
         path = target = str(tmp_path / "m.msh")
-        save_gmsh(path, c, t, version="4.1" if fmt == "msh4" else "2.2")
+        save_gmsh(path, c, t, version="4.1" if fmt.startswith("msh4") else "2.2", binary=fmt.endswith("binary"))
     original = open(target, "rb").read()
     rng = np.random.default_rng(17)
     loaded = rejected = 0

@@ -5,6 +5,7 @@
 // PumiTallyImpl.cpp:384-385, 495-496) and from pumi-pic (face adjacency used by
 // the external tracer).  Nothing here is on the per-step hot path.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <string>
 #include <vector>

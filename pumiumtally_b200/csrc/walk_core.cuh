@@ -85,7 +85,7 @@ PTB_HD void face_payload(double a, double b, double c, double d, int32_t self, i
 // face compute the identical quotient.  The minimum is selected by cross-multiplication
 // (num_a*den_b < num_b*den_a, both den > 0): one fp64 division per crossing instead of one per
 // face; ties within rounding pick either face, which only reorders a zero-length piece.
-constexpr double kDenMin = 1e-280;
+constexpr double kParallelTol = 1e-12;
 
 struct ExitScan {
   double bnum = 1.0, bden = 0.0;  // t = +inf
@@ -97,11 +97,13 @@ PTB_HD void scan_face(ExitScan &s, double nx, double ny, double nz, double c, in
                       double uz) {
   const double den = nx * ux + ny * uy + nz * uz;
   const double num = c - (nx * ox + ny * oy + nz * oz);
-  // den > kDenMin, not den > 0: a plane component that is exactly zero carries the payload byte as a
-  // denormal (~1e-321), so a ray exactly parallel to the face (a track along the hull surface or
-  // inside an axis-aligned face) would see den = +-1e-321*|u| instead of 0 and could "leave"
-  // through it.  No real crossing has |den| anywhere near 1e-280.
-  const bool take = (den > kDenMin) && (num * s.bden < s.bnum * den);
+  // A face counts as an exit candidate only if the ray leaves through it at a real angle:
+  // n.u > kParallelTol*|u|_1, not n.u > 0.  (a) A plane component that is exactly zero carries the
+  // payload byte as a denormal, so a ray exactly parallel to the face would see n.u = +-1e-321*|u|.
+  // (b) A ray that runs inside a face plane or along a mesh edge sees n.u = rounding noise for the faces
+  // that contain it, and num/den of such a face is an arbitrary number that can win the minimum.  No ray
+  // that is not parallel to the face within 1e-12 rad is affected.
+  const bool take = (den > kParallelTol * (fabs(ux) + fabs(uy) + fabs(uz))) && (num * s.bden < s.bnum * den);
   s.bnum = take ? num : s.bnum;
   s.bden = take ? den : s.bden;
   s.nbr = take ? nbr : s.nbr;
@@ -364,6 +366,12 @@ PTB_HD void begin_particle(const WalkParams &P, int i, Ray &r, Counters &c, bool
 template <bool kReloadTarget = false>
 PTB_HD void end_ray(const WalkParams &P, int i, Ray &r, bool reached, double tnew, Counters &c,
                     bool writer) {
+  // crossings of the ray that just ended: tally contributions in the tally phase, relocation crossings
+  // otherwise (counted here, once per ray, instead of once per crossing)
+  if (writer) {
+    if (r.stage == kStageTally) c.segs += (unsigned)r.iters;
+    else c.relocs += (unsigned)r.iters;
+  }
   double x, y, z;
   if (kReloadTarget && (reached || r.stage == kStageSeed)) {
     const double *t = (r.stage == kStageTally ? P.dest : P.origin) + 3 * (size_t)i;
@@ -400,14 +408,8 @@ PTB_HD void advance(const WalkParams &P, int i, Ray &r, double texit, int32_t ne
                     Counters &c, bool writer) {
   const bool reached = !(texit < 1.0);  // last_exit == -1: destination inside this tet
   const double tnew = reached ? 1.0 : fmax(texit, r.tcur);
-  if (r.stage == kStageTally) {  // EvaluateFlux (Impl.cpp:362-379)
-    if (writer) {
-      PTB_TALLY_ADD(P.flux + r.e, (tnew - r.tcur) * r.wl);
-      c.segs++;
-    }
-  } else if (writer) {
-    c.relocs++;
-  }
+  if (r.stage == kStageTally && writer)  // EvaluateFlux (Impl.cpp:362-379)
+    PTB_TALLY_ADD(P.flux + r.e, (tnew - r.tcur) * r.wl);
   const bool hull = !reached && next < 0;  // next_elems == -1 (Impl.cpp:270-271)
   r.iters++;
   const bool over = r.iters >= P.max_iters;

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) walk_quad_kernel(const WalkParams P) {
     const double nx = a, ny = b, nz = cc, pc = d;
     const double den = nx * r.ux + ny * r.uy + nz * r.uz;
     const double num = pc - (nx * r.ox + ny * r.oy + nz * r.oz);
-    const bool out = den > kDenMin;  // see scan_face()
+    const bool out = den > kParallelTol * (fabs(r.ux) + fabs(r.uy) + fabs(r.uz));  // see scan_face()
     double tb = out ? num / den : __builtin_huge_val();
     int32_t nb = out ? nbf : -2;
     int32_t bk = out ? bkf : -1;

@@ -299,3 +299,40 @@ def lattice_track_scenario(make_engine, seeds):
         T = np.transpose(v[:, 1:] - v[:, :1], (0, 2, 1))
         lam = np.linalg.solve(T, (eng.positions - v[:, 0])[..., None])[..., 0]
         assert min(lam.min(), (1.0 - lam.sum(1)).min()) > -1e-11, f"seed {seed}"
+
+
+def unstructured_special_point_scenario(make_engine, seeds):
+    """Tracks between vertices, edge points, face centroids and tet centroids of Delaunay / jittered
+    meshes: rays through vertices, along edges, inside faces.  Nothing may be lost or stopped early,
+    destinations are reached, the total tally equals the total track length."""
+    from pumiumtally_b200.mesh import delaunay_box, jitter_interior
+
+    for seed in seeds:
+        rng = np.random.default_rng(1000 + seed)
+        if seed % 2:
+            coords, t2v = delaunay_box(int(rng.integers(20, 200)), seed=seed)
+        else:
+            dims = tuple(int(x) for x in rng.integers(1, 5, 3))
+            coords, t2v = jitter_interior(*kuhn_box(*dims), amplitude=float(rng.uniform(0.05, 0.3)), seed=seed)
+        tets = t2v[rng.choice(len(t2v), min(len(t2v), 30), replace=False)]
+        pts = []
+        for t in tets:
+            v = coords[t]
+            pts += [v[0], v[3], 0.5 * (v[0] + v[1]), 0.25 * v[1] + 0.75 * v[2], (v[0] + v[1] + v[2]) / 3.0,
+                    (v[1] + v[2] + v[3]) / 3.0, v.mean(0)]
+        pts = np.array(pts)
+        a, b = rng.integers(0, len(pts), 500), rng.integers(0, len(pts), 500)
+        keep = a != b
+        start, dest = pts[a[keep]], pts[b[keep]]
+        n = len(start)
+        w = rng.uniform(0.5, 1.0, n)
+        eng = make_engine(coords, t2v, n)
+        eng.CopyInitialPosition(start.reshape(-1).copy())
+        eng.MoveToNextLocation(start.reshape(-1).copy(), dest.reshape(-1).copy(), np.ones(n, dtype=np.int8), w.copy())
+        assert eng.stats()["lost"] == 0, f"seed {seed}"
+        np.testing.assert_allclose(eng.positions, dest, rtol=0, atol=1e-11, err_msg=f"seed {seed}")
+        np.testing.assert_allclose(eng.flux.sum(), (np.linalg.norm(dest - start, axis=1) * w).sum(), rtol=1e-11)
+        v = coords[t2v[eng.elem_ids]]
+        T = np.transpose(v[:, 1:] - v[:, :1], (0, 2, 1))
+        lam = np.linalg.solve(T, (eng.positions - v[:, 0])[..., None])[..., 0]
+        assert min(lam.min(), (1.0 - lam.sum(1)).min()) > -1e-10, f"seed {seed}"

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from helpers import (ROOT, assert_flux_close, box_case, edge_case_scenario, lattice_track_scenario,
-                     non_finite_input_scenario, run_workload)
+                     non_finite_input_scenario, run_workload, unstructured_special_point_scenario)
 from oracle.oracle import OraclePumiTally
 from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, save_raw_mesh, tet_volumes
 from pumiumtally_b200.tally import PumiTally
@@ -730,3 +730,8 @@ def test_randomised_meshes_and_tracks_parity(variant):
 @pytest.mark.parametrize("variant", [0, 2, 8, 16, 20, 24])
 def test_lattice_tracks_on_hull_faces_edges_and_vertices(variant):
     lattice_track_scenario(gpu_engine(variant), range(8))
+
+
+@pytest.mark.parametrize("variant", [0, 2, 8, 16, 20, 24])
+def test_tracks_through_vertices_and_along_edges_of_unstructured_meshes(variant):
+    unstructured_special_point_scenario(gpu_engine(variant), range(6))

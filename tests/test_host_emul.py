@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from helpers import (HostEmulTally, assert_flux_close, box_case, edge_case_scenario, lattice_track_scenario,
-                     non_finite_input_scenario, run_workload)
+                     non_finite_input_scenario, run_workload, unstructured_special_point_scenario)
 from oracle.oracle import OraclePumiTally
 from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, tet_volumes
 from pumiumtally_b200.workload import SyntheticWorkload
@@ -389,3 +389,9 @@ def test_damaged_mesh_files_are_rejected_or_loaded_never_crash(tmp_path, fmt):
         except RuntimeError:
             rejected += 1
     assert loaded + rejected == 250 and rejected > 50
+
+
+@pytest.mark.parametrize("fma", [False, True], ids=["plain", "fma"])
+@pytest.mark.parametrize("seed", SEED)
+def test_tracks_through_vertices_and_along_edges_of_unstructured_meshes(seed, fma):
+    unstructured_special_point_scenario(lambda c, t, n: HostEmulTally(c, t, n, fma=fma, **seed), range(24))

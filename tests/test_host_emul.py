@@ -395,3 +395,54 @@ def test_damaged_mesh_files_are_rejected_or_loaded_never_crash(tmp_path, fmt):
 @pytest.mark.parametrize("seed", SEED)
 def test_tracks_through_vertices_and_along_edges_of_unstructured_meshes(seed, fma):
     unstructured_special_point_scenario(lambda c, t, n: HostEmulTally(c, t, n, fma=fma, **seed), range(24))
+
+
+@pytest.mark.parametrize("fma", [False, True], ids=["plain", "fma"])
+def test_extreme_meshes_and_batches_parity(fma):
+    """Needle- and plate-shaped cells (aspect ratios 1e-3 .. 1e6), tracks of 1e-9 cell sizes, batches that mostly
+    leave the mesh, batches where every particle is re-sourced: four moves each against the oracle, both layouts."""
+    for seed in range(24):
+        rng = np.random.default_rng(5000 + seed)
+        kind = seed % 4
+        if kind == 0:
+            c, t = delaunay_box(int(rng.integers(50, 300)), seed=seed)
+            hi = np.ones(3)
+        elif kind == 1:
+            dims = (1, 1, int(rng.integers(5, 40)))
+            hi = np.array([0.01, 0.01, float(dims[2])])
+            c, t = kuhn_box(*dims, *hi)
+        elif kind == 2:
+            dims = tuple(int(x) for x in rng.integers(2, 6, 3))
+            c, t = jitter_interior(*kuhn_box(*dims), amplitude=0.25, seed=seed)
+            hi = np.array(dims, dtype=float)
+        else:
+            dims = (int(rng.integers(10, 30)), 1, 1)
+            hi = np.array([float(dims[0]), 1e-3, 1e3])
+            c, t = kuhn_box(*dims, *hi)
+        n = int(rng.integers(50, 1500))
+        pos = rng.uniform(0.01, 0.99, (n, 3)) * hi
+        for layout in ("planes", "edge"):
+            eng, orc = HostEmulTally(c, t, n, layout=layout, seed_grid=bool(seed & 1), fma=fma), OraclePumiTally(c, t, n)
+            for e in (eng, orc):
+                e.CopyInitialPosition(pos.reshape(-1).copy())
+            np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+            cur, r2 = pos.copy(), np.random.default_rng(seed)
+            for step in range(4):
+                mode = int(r2.integers(0, 4))
+                origin = cur.copy()
+                res = r2.random(n) < (1.0 if mode == 3 else 0.1)
+                origin[res] = r2.uniform(0.01, 0.99, (int(res.sum()), 3)) * hi
+                if mode == 0:
+                    dest = origin + r2.normal(0, 1e-9, (n, 3)) * hi
+                elif mode == 1:
+                    dest = r2.uniform(-2, 3, (n, 3)) * hi
+                else:
+                    dest = r2.uniform(0.0, 1.0, (n, 3)) * hi
+                fly, w = (r2.random(n) < 0.9).astype(np.int8), r2.uniform(0, 2, n)
+                for e in (eng, orc):
+                    e.MoveToNextLocation(origin.reshape(-1).copy(), dest.reshape(-1).copy(), fly.copy(), w.copy())
+                cur = orc.positions.copy()
+                assert_flux_close(eng.flux, orc.flux, f"seed {seed} {layout} step {step}")
+                np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+                assert np.abs(eng.positions - orc.positions).max() <= 1e-9 * max(1.0, hi.max())
+                assert eng.stats()["lost"] == 0

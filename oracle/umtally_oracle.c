@@ -125,7 +125,11 @@ static int find_exit_face(const um_oracle *o, int e, int entry, const double *O,
     double n[3], c;
     face_plane(o, e, f, n, &c);
     double den = dot3(n, u);
-    if (den > 0.0) {
+    /* a face the segment is parallel to (within 1e-12 rad) is no exit candidate: for a track that runs
+     * inside a face plane or along an edge, den is rounding noise and num/den an arbitrary number.  The
+     * reference tracer carries a tolerance for the same purpose (constructor argument 1e-8,
+     * PumiTallyImpl.cpp:51); generic tracks are unaffected.  Same rule as scan_face() in the CUDA path. */
+    if (den > 1e-12 * (fabs(u[0]) + fabs(u[1]) + fabs(u[2]))) {
       double t = (c - dot3(n, O)) / den;
       if (t < tbest) { tbest = t; fbest = f; }
     }

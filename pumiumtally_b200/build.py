@@ -17,6 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 OBJDIR = os.path.join(PKG, "build")
 LIB = os.path.join(LIBDIR, "libpumitally.so")
+LIB_EXP = os.path.join(LIBDIR, "libpumitally_exp.so")  # product + measured alternatives (tests/experiments only)
 
 SOURCES = [
     "walk_kernels.cu",
@@ -51,34 +52,42 @@ def _newer(a: str, b: str) -> bool:
     return (not os.path.exists(b)) or os.path.getmtime(a) > os.path.getmtime(b)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile every translation unit that changed and relink. Returns the .so path."""
+def build_library(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+    """Compile every translation unit that changed and relink. Returns the .so path.
+
+    experiments=True builds lib/libpumitally_exp.so instead: the same library plus the measured
+    alternative kernels of csrc/experiments/ (flag PTB_EXPERIMENTS); select it at run time with
+    PUMITALLY_LIB=<path>.  The product library never contains them."""
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
+    objdir = OBJDIR + ("_exp" if experiments else "")
+    os.makedirs(objdir, exist_ok=True)
+    lib = LIB_EXP if experiments else LIB
+    sources = SOURCES + (["experiments/walk_experiments.cu"] if experiments else [])
+    flags = NVCC_FLAGS + (["-DPTB_EXPERIMENTS"] if experiments else [])
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".hpp", ".cuh", ".h"))]
     headers += [os.path.join(ROOT, "include", "pumitally_c.h"),
                 os.path.join(ROOT, "include", "pumitally", "PumiTally.h")]
     newest_header = max(os.path.getmtime(h) for h in headers)
-    objs, relink = [], force or not os.path.exists(LIB)
-    for src in SOURCES:
+    objs, relink = [], force or not os.path.exists(lib)
+    for src in sources:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJDIR, src + ".o")
+        o = os.path.join(objdir, src.replace("/", "_") + ".o")
         objs.append(o)
         if force or _newer(s, o) or newest_header > os.path.getmtime(o):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+            cmd = [nvcc, *flags, "-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             subprocess.check_call(cmd)
             relink = True
     if relink:
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fopenmp", "-lgomp", "-ldl", "-lz",
+        cmd = [nvcc, "-shared", "-o", lib, *objs, "-Xcompiler", "-fopenmp", "-lgomp", "-ldl", "-lz",
                "-gencode", "arch=compute_100a,code=sm_100a"]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_library(force="--force" in sys.argv, verbose=True, experiments="--experiments" in sys.argv))

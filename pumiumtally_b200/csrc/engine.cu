@@ -97,6 +97,9 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
 // reads per crossing; TetStart lines (128 B per tet) are read once per ray.  Built and uploaded the
 // first time one of the edge-walk variants is selected (the default kernels never touch it).
 bool Engine::upload_compact() {
+#ifndef PTB_EXPERIMENTS
+  return false;  // the edge-walk variants are not part of this library
+#endif
   if (d_links_) return true;
   std::string err;
   if (!mesh_.build_compact(&err)) {
@@ -166,7 +169,7 @@ void Engine::build_seed_grid() {
   p.bulk_ok = 1;
   p.work_counter = d_tickets_;
   p.stats = d_stats_;
-  cuda_or_throw(launch_walk(p, kVariantPersist, 128, compute_), "seed walk");
+  cuda_or_throw(launch_walk(p, kVariantPersistRefill8, 128, compute_), "seed walk");
   cuda_or_throw(launch_seed_finalize(xyz, ts, d_grid_, ncell, compute_), "seed finalize");
   cuda_or_throw(cudaStreamSynchronize(compute_), "seed sync");
   cuda_or_throw(cudaMemset(d_stats_, 0, sizeof(DeviceStats)), "memset");
@@ -689,7 +692,7 @@ int Engine::set_option(const std::string &name, int64_t v) {
       auto_variant_ = true;
       return 0;
     }
-    if (v < 0 || v >= kNumVariants) return 1;
+    if (v < 0 || v >= kNumVariants || !walk_variant_available(int(v))) return 1;
     if (v >= kVariantEdge && v <= kVariantEdgeOcc6) {
       if (synchronize()) return 1;
       try {

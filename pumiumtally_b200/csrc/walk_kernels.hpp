@@ -10,6 +10,9 @@ namespace ptb {
 
 // Values are stable (profiles/ refer to them); the gaps are experiments that were measured,
 // lost and removed (9/10 other refill thresholds, 11/12/14 cooperative transposed fetch, 18).
+// libpumitally.so contains the four kernels the engine chooses between -- 0, 8, 16, 24; the other
+// numbers are measured alternatives compiled only into libpumitally_exp.so
+// (experiments/walk_experiments.cu, build flag PTB_EXPERIMENTS).
 enum WalkVariant : int {
   kVariantLdg = 0,    // thread per particle, 4 x 256-bit loads of the tet record (first correct path)
   kVariantBulk = 1,   // thread per particle, record staged in smem by cp.async.bulk + mbarrier
@@ -36,6 +39,7 @@ enum WalkVariant : int {
 
 
 cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_t stream);
+bool walk_variant_available(int variant);  // compiled into this library?
 cudaError_t launch_bin_particles(const SeedGrid &g, const double *origin, const int8_t *flying,
                                  int32_t begin, int32_t end, int32_t *pcell, unsigned int *count,
                                  unsigned int *sums, int32_t *order, unsigned int *work_count,

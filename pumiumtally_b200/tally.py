@@ -15,7 +15,9 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libpumitally.so")
+# PUMITALLY_LIB selects another build of the same library (tests of the measured alternative kernels
+# use lib/libpumitally_exp.so); the default is the product library.
+LIB_PATH = os.environ.get("PUMITALLY_LIB") or os.path.join(_PKG, "lib", "libpumitally.so")
 _lib = None
 
 _dp = C.POINTER(C.c_double)

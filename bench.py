@@ -61,6 +61,25 @@ def recorded_traffic():
         return None
 
 
+def bind_to_gpu_node(torch, index):
+    """Run this rank (and allocate its host arrays) on the CPUs local to its GPU -- what
+    `numactl --cpunodebind` does in an HPC launch line.  Returns the CPU list or None."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        cpus = set()
+        for tok in open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip().split(","):
+            a, _, b = tok.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) * 4 >= len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
 
@@ -185,6 +204,8 @@ def run_gpu(args, rank, local_rank, world):
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    bound = None if args.no_bind else bind_to_gpu_node(torch, local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -294,58 +315,86 @@ def run_gpu(args, rank, local_rank, world):
     del eng
 
     # ---------------- end-to-end arm through the host-pointer C ABI: `e2e` ------
+    # Headline: the call a user of the reference makes (PumiTally.h:87-89) on ordinary pageable host
+    # arrays that the caller reuses for every move, as OpenMC does with its std::vectors, with the
+    # engine's default settings.  Side numbers: the same from pinned buffers, and the direct path
+    # (host_path=0) from pageable memory with and without cudaHostRegister.
     e2e = None
     if not args.no_e2e:
-        if not pregen:  # replay the same counter-based stream from the start
-            wl = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], mu_min=cfg["mu_min"],
+        def replay():
+            w2 = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], mu_min=cfg["mu_min"],
                                    backend="torch", device=dev, id_offset=rank * n)
-            init = wl.initial_positions().contiguous()
+            return w2, w2.initial_positions().contiguous()
 
-        def pinned(t):
-            return tuple(torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x) for x in t)
+        def run_e2e(kind, opts, steps, warmup):
+            """kind: 'pageable' | 'pinned' caller buffers; returns (segments, seconds, h2d bytes per step)."""
+            nonlocal wl, init
+            if not pregen:  # replay the same counter-based stream from the start
+                wl, init = replay()
+            if kind == "pinned":
+                bufs = [torch.empty(s_, dtype=d_, pin_memory=True).numpy() for s_, d_ in
+                        ((3 * n, torch.float64), (3 * n, torch.float64), (n, torch.int8), (n, torch.float64))]
+            else:
+                bufs = [np.empty(3 * n), np.empty(3 * n), np.empty(n, dtype=np.int8), np.empty(n)]
+            O, D, F, W = bufs
+            eng2 = new_engine()
+            for k_, v_ in opts.items():
+                eng2.set_option(k_, v_)
+            eng2.CopyInitialPosition(init.cpu().numpy().reshape(-1))
 
-        host = [pinned(b) for b in batches] if pregen else None
-        one = None if pregen else pinned(batch(0))
-        init_h = init.cpu()
-        eng2 = new_engine()
-        eng2.CopyInitialPosition(init_h.numpy().reshape(-1))
+            def fill(k):  # untimed: the transport code producing its next batch in its own arrays
+                o, d, f, w = batch(k)
+                for dst, src in zip((O, D, F, W), (o, d, f, w)):
+                    dst[:] = src.reshape(-1).cpu().numpy()
 
-        def host_batch(k):
-            if pregen:
-                return host[k]
-            if k > 0:
-                for dst, src in zip(one, batch(k)):
-                    dst.copy_(src)
-                torch.cuda.synchronize()
-            return one
+            for k in range(warmup):
+                fill(k)
+                eng2.MoveToNextLocation(O, D, F, W)
+                eng2.stats()
+            barrier()
+            st_a = eng2.stats()
+            dt = 0.0
+            for k in range(warmup, warmup + steps):
+                fill(k)
+                t0 = time.perf_counter()
+                eng2.MoveToNextLocation(O, D, F, W)
+                st_b = eng2.stats()  # device->host read of the step's result (synchronises)
+                dt += time.perf_counter() - t0
+            e_t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            e_s = torch.tensor([float(st_b["segments"] - st_a["segments"])], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+                dist.all_reduce(e_s, op=dist.ReduceOp.SUM)
+            h2d = (st_b["h2d_bytes"] - st_a["h2d_bytes"]) / steps
+            threads = eng2.get_option("host_threads")
+            del eng2
+            return float(e_s[0]), float(e_t[0]), h2d, threads
 
-        for k in range(args.warmup):
-            o, d, f, w = host_batch(k)
-            eng2.move_host_ptr(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr())
-            eng2.stats()
-        barrier()
-        s0 = eng2.stats()["segments"]
-        dt = 0.0
-        for k in range(args.warmup, nsteps):
-            o, d, f, w = host_batch(k)
-            t0 = time.perf_counter()
-            eng2.move_host_ptr(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr())
-            s1 = eng2.stats()["segments"]  # device->host read of the step's result (synchronises)
-            dt += time.perf_counter() - t0
-        e_t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        e_s = torch.tensor([float(s1 - s0)], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(e_s, op=dist.ReduceOp.SUM)
-        e2e = {"value": float(e_s[0]) / float(e_t[0]), "unit": UNIT,
-               "h2d_bytes_per_step": n * (24 + 24 + 8 + 1), "d2h_bytes_per_step": 56,
-               "ms_per_step": 1e3 * float(e_t[0]) / args.steps,
-               "note": "MoveToNextLocation on pinned host buffers + per-step stats read-back"}
-        del eng2, host, one
+        segs_e, secs_e, h2d_e, threads_e = run_e2e("pageable", {}, args.steps, args.warmup)
+        e2e = {"value": segs_e / secs_e, "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d_e), "d2h_bytes_per_step": 56,
+               "ms_per_step": 1e3 * secs_e / args.steps,
+               "caller_buffers": "pageable numpy arrays, reused for every move",
+               "host_threads": threads_e,
+               "note": "MoveToNextLocation(host pointers) with default options + per-step stats read-back; "
+                       "staged path: pinned per-particle slots refilled by the engine's worker pool, "
+                       "only changed origins travel"}
+        if not args.no_e2e_modes:
+            ks, kw = min(args.steps, 5), min(args.warmup, 2)
+            modes = {}
+            for name, kind, opts in (("pinned_buffers", "pinned", {}),
+                                     ("direct_registered", "pageable", {"host_path": 0, "register_host": 1}),
+                                     ("direct_pageable", "pageable", {"host_path": 0})):
+                if pregen is False and name != "pinned_buffers":
+                    continue
+                sg, sc, hb, _ = run_e2e(kind, opts, ks, kw)
+                modes[name] = {"value": sg / sc, "ms_per_step": 1e3 * sc / ks, "h2d_bytes_per_step": int(hb)}
+            e2e["other_modes"] = modes
 
     # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, all_cpus)  # the CPU arm gets every core of the box
         from oracle.oracle import OraclePumiTally, num_threads
         from pumiumtally_b200.mesh import kuhn_box
 
@@ -379,7 +428,7 @@ def run_gpu(args, rank, local_rank, world):
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_description(args.config, cfg, n), "variant": variant_used,
-                   "block": args.block,
+                   "block": args.block, "cpu_binding": (f"{len(bound)} CPUs local to the GPU" if bound else "none"),
                    "l2": f"inputs larger than L2 ({bytes_per_step / 1e6:.0f} MB of fresh particle data per step)",
                    "timing": "K steps back to back between two CUDA events" if pregen else
                              "per-step CUDA-event times summed (batches generated between steps, untimed)",
@@ -422,7 +471,9 @@ def main():
                     help="on one GPU, run only the per-GPU share of a multi-GPU config")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (repeatable)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-modes", action="store_true", help="skip the e2e side numbers (pinned / direct paths)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

@@ -82,6 +82,16 @@ int pumitally_get_positions(pumitally_engine *e, double *out, int64_t n3);
 int pumitally_get_adjacency(const pumitally_engine *e, int32_t *out, int64_t n4);
 /* zero the flux and the statistics (new batch) */
 int pumitally_reset_tally(pumitally_engine *e);
+/* Per-source-particle normalisation of the NORMALISED flux (pumitally_get_normalized_flux and
+ * WriteTallyResults; the raw flux is unaffected).  The reference divides by tet volume only
+ * (PumiTallyImpl.cpp:402) although PumiTally.h:93 promises "and total number of particles", and
+ * carries an unused total_initial_weight "needed for normalization" (PumiTallyImpl.h:170-171).
+ * mode 0: volume only (default = the reference's behaviour); 1: also by num_particles;
+ * 2: also by `value` (> 0, e.g. the total source weight of the batch); 3: also by the total weight
+ * of the first tracks after CopyInitialPosition / pumitally_reset_tally, summed by the engine. */
+int pumitally_set_source_normalization(pumitally_engine *e, int32_t mode, double value);
+/* the divisor currently in effect (1.0 for mode 0) */
+double pumitally_get_source_normalization(pumitally_engine *e);
 
 typedef struct pumitally_stats {
   uint64_t segments;      /* tally contributions issued in weighted phases (the metric's unit) */
@@ -97,15 +107,20 @@ int pumitally_get_stats(pumitally_engine *e, pumitally_stats *out);
 
 /* Per-call output file name for WriteTallyResults (default "fluxresult.vtk"). */
 int pumitally_set_output_name(pumitally_engine *e, const char *filename);
-/* Options: "variant" (-1 = the engine picks the walk kernel from the mesh size, the default),
- * "block", "chunk", "seed_grid", "morton", "claim_run", and "register_host" (1 = page-lock the
- * caller's pageable buffers with cudaHostRegister the first time they are seen; also enabled by
- * the environment variable PUMITALLY_REGISTER_HOST=1), "delta_upload" (0 = off, the default;
- * 1 = send only the origins that differ from the previous call's destinations, with a self-check
- * that switches it off when the host-side comparison costs more than it saves; 2 = always),
- * "delta_threads", "max_iters" (crossing limit per walk; 0 = number of elements + 16, the
- * default), "l2_fetch", "autotune" (1 = default: while "variant" is automatic the engine times the
- * streaming and the sorted/packed kernel on moves 1-4 of every 64 and keeps the faster one). */
+/* Options: "variant" (-1 = the engine picks the walk kernel from the mesh size, the default; 0, 8,
+ * 16, 24 = the kernels of this library), "block", "chunk" (particles per upload/compute pipeline
+ * stage), "seed_grid", "morton", "claim_run", "host_path" (1 = default: host-pointer moves are
+ * staged through pinned per-particle slots by a small worker pool and only the origins that
+ * differ from the previous call's destinations travel; 0 = direct copies of all four arrays from
+ * the caller's memory), "host_threads" (workers of that pool, before the first host-pointer call;
+ * default: CPU quota / ranks per node - 1; environment: PUMITALLY_HOST_THREADS,
+ * PUMITALLY_HOST_PIN=0 keeps them off the GPU's NUMA node), "register_host" (direct path only:
+ * 1 = page-lock the caller's pageable buffers with cudaHostRegister the first time they are
+ * seen; the caller must then keep them alive; also PUMITALLY_REGISTER_HOST=1), "max_iters"
+ * (crossing limit per walk; 0 = number of elements + 16, the default), "l2_fetch", "autotune"
+ * (1 = default: while "variant" is automatic the engine times the streaming and the sorted/packed
+ * kernel on moves 1-4 of every 64 and keeps the faster one).  Read-only: "launches", "staged",
+ * "stage_host_us", "stage_sent_bytes". */
 int pumitally_set_option(pumitally_engine *e, const char *name, int64_t value);
 int64_t pumitally_get_option(const pumitally_engine *e, const char *name);
 
@@ -138,6 +153,15 @@ int pumitally_allreduce_tally(pumitally_engine *e);
 /* test hook: processing order produced by the last binning pass (ids of flying particles
  * grouped by seed-grid cell); returns the number of entries, copies at most n of them */
 int64_t pumitally_debug_order(pumitally_engine *e, int32_t *out, int64_t n);
+
+/* test hook, needs no GPU: one stage pass of the host-pointer path (csrc/host_stage.hpp) over
+ * particles [0, n) with `threads` workers.  b_dest/b_w/b_fly are the staging slots (b_dest also the
+ * mirror the origins are compared against when compare != 0); out_patches receives 32-byte entries
+ * {x, y, z, int32 index, int32 0}.  Returns the number of entries, or -1 if they exceed cap. */
+int64_t pumitally_debug_stage(const double *origin, const double *dest, int8_t *flying,
+                              const double *weights, double *b_dest, double *b_w, int8_t *b_fly,
+                              int64_t n, int32_t compare, int32_t threads, void *out_patches,
+                              int64_t cap);
 
 const char *pumitally_version(void);
 

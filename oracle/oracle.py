@@ -39,6 +39,7 @@ def lib():
         L.um_oracle_create.argtypes = [dp, C.c_int, ip, C.c_int, C.c_int]
         L.um_oracle_destroy.argtypes = [C.c_void_p]
         L.um_oracle_set_mode.argtypes = [C.c_void_p, C.c_int]
+        L.um_oracle_set_exit_rule.argtypes = [C.c_void_p, C.c_int]
         L.um_oracle_copy_initial_position.argtypes = [C.c_void_p, dp, C.c_int]
         L.um_oracle_move_to_next_location.argtypes = [C.c_void_p, dp, dp, bp, dp, C.c_int]
         L.um_oracle_normalized_flux.argtypes = [C.c_void_p, dp, dp]
@@ -72,9 +73,10 @@ class OraclePumiTally:
 
     ``per_particle=False`` runs the reference-shaped global iterate-until-all-done
     loop; ``True`` walks each particle to completion (same arithmetic, faster).
+    ``strict_exit`` selects the exit-face rule without the parallel-face tolerance.
     """
 
-    def __init__(self, coords, tet2vert, num_particles: int, per_particle: bool = True):
+    def __init__(self, coords, tet2vert, num_particles: int, per_particle: bool = True, strict_exit: bool = False):
         self._L = lib()
         self.coords = np.ascontiguousarray(coords, dtype=np.float64)
         self.tet2vert = np.ascontiguousarray(tet2vert, dtype=np.int32)
@@ -84,6 +86,9 @@ class OraclePumiTally:
             _d(self.coords), self.coords.shape[0], _i(self.tet2vert), self.ntets, self.num_particles
         )
         self._L.um_oracle_set_mode(self._h, 1 if per_particle else 0)
+        # strict_exit=True: the exit rule before the parallel-face tolerance (every face with n.u > 0 is a
+        # candidate); identical results on generic inputs, kept to show exactly that
+        self._L.um_oracle_set_exit_rule(self._h, 1 if strict_exit else 0)
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -65,6 +65,8 @@ typedef struct um_oracle {
   long iter_count;
   int looplimit;
   int per_particle; /* 0 = reference-shaped global loop, 1 = walk each particle to completion */
+  int strict_exit;  /* 1 = every face with n.u > 0 is an exit candidate (the rule before the parallel-face
+                     * tolerance was added); 0 = default, faces parallel to the segment are skipped */
   /* statistics (not in the reference; used for the segments/s metric) */
   long long n_segments;  /* tally contributions with in_flight==1 during weighted phases */
   long long n_crossings; /* all walk iterations of all particles, any phase */
@@ -128,8 +130,11 @@ static int find_exit_face(const um_oracle *o, int e, int entry, const double *O,
     /* a face the segment is parallel to (within 1e-12 rad) is no exit candidate: for a track that runs
      * inside a face plane or along an edge, den is rounding noise and num/den an arbitrary number.  The
      * reference tracer carries a tolerance for the same purpose (constructor argument 1e-8,
-     * PumiTallyImpl.cpp:51); generic tracks are unaffected.  Same rule as scan_face() in the CUDA path. */
-    if (den > 1e-12 * (fabs(u[0]) + fabs(u[1]) + fabs(u[2]))) {
+     * PumiTallyImpl.cpp:51); generic tracks are unaffected.  Same rule as scan_face() in the CUDA path --
+     * which makes the behaviour on such degenerate tracks self-referential: it was chosen, not derived
+     * from the (absent) tracer source.  The rule it replaced (den > 0, um_oracle_set_exit_rule(o, 1)) is
+     * kept so that tests can assert both give identical results on every generic workload. */
+    if (o->strict_exit ? den > 0.0 : den > 1e-12 * (fabs(u[0]) + fabs(u[1]) + fabs(u[2]))) {
       double t = (c - dot3(n, O)) / den;
       if (t < tbest) { tbest = t; fbest = f; }
     }
@@ -247,6 +252,7 @@ void um_oracle_destroy(um_oracle *o) {
 }
 
 void um_oracle_set_mode(um_oracle *o, int per_particle) { o->per_particle = per_particle; }
+void um_oracle_set_exit_rule(um_oracle *o, int strict) { o->strict_exit = strict; }
 
 /* -------------------------------------------------- search, reference-shaped */
 

@@ -23,6 +23,7 @@ SOURCES = [
     "walk_kernels.cu",
     "bin_kernels.cu",
     "engine.cu",
+    "host_stage.cpp",
     "tet_mesh.cpp",
     "osh_reader.cpp",
     "gmsh_reader.cpp",
@@ -35,7 +36,7 @@ SOURCES = [
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-fopenmp,-Wall,-fvisibility=default",
+    "-Xcompiler", "-fPIC,-fopenmp,-pthread,-Wall,-fvisibility=default",
     "-I", os.path.join(ROOT, "include"),
     "-I", CSRC,
 ]
@@ -81,7 +82,7 @@ def build_library(force: bool = False, verbose: bool = False, experiments: bool 
             subprocess.check_call(cmd)
             relink = True
     if relink:
-        cmd = [nvcc, "-shared", "-o", lib, *objs, "-Xcompiler", "-fopenmp", "-lgomp", "-ldl", "-lz",
+        cmd = [nvcc, "-shared", "-o", lib, *objs, "-Xcompiler", "-fopenmp,-pthread", "-lgomp", "-ldl", "-lz",
                "-gencode", "arch=compute_100a,code=sm_100a"]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)

@@ -142,6 +142,13 @@ int pumitally_reset_tally(pumitally_engine *e) {
   return guarded(e, [&](ptb::Engine &g) { return g.reset_tally(); });
 }
 
+int pumitally_set_source_normalization(pumitally_engine *e, int32_t mode, double value) {
+  return guarded(e, [&](ptb::Engine &g) { return g.set_source_normalization(mode, value); });
+}
+double pumitally_get_source_normalization(pumitally_engine *e) {
+  return (e && e->impl) ? e->impl->source_normalization() : 0.0;
+}
+
 int pumitally_get_stats(pumitally_engine *e, pumitally_stats *out) {
   return guarded(e, [&](ptb::Engine &g) {
     ptb::EngineStats s;
@@ -206,6 +213,21 @@ int64_t pumitally_debug_order(pumitally_engine *e, int32_t *out, int64_t n) {
   return e->impl->debug_order(out, n);
 }
 
-const char *pumitally_version(void) { return "pumitally-b200 0.1 (sm_100a)"; }
+int64_t pumitally_debug_stage(const double *origin, const double *dest, int8_t *flying, const double *weights,
+                              double *b_dest, double *b_w, int8_t *b_fly, int64_t n, int32_t compare,
+                              int32_t threads, void *out_patches, int64_t cap) {
+  try {
+    ptb::HostStager st(threads, {});
+    st.set_buffers(b_dest, b_w, b_fly);
+    st.reserve(size_t(cap));
+    st.begin(origin, dest, flying, weights, 0, n, compare != 0, static_cast<ptb::PatchEntry *>(out_patches));
+    return st.end();
+  } catch (const std::exception &ex) {
+    fprintf(stderr, "[pumitally] ERROR: %s\n", ex.what());
+    return -2;
+  }
+}
+
+const char *pumitally_version(void) { return "pumitally-b200 0.2 (sm_100a)"; }
 
 }  // extern "C"

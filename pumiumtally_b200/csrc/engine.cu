@@ -1,9 +1,8 @@
 // Engine: device state + batch orchestration (see engine.hpp).
 #include "engine.hpp"
 
-#include <omp.h>
-
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <climits>
 #include <cstdio>
@@ -11,6 +10,7 @@
 #include <cstring>
 #include <stdexcept>
 
+#include "host_stage.hpp"
 #include "seed_grid.hpp"
 #include "vtk_writer.hpp"
 
@@ -71,6 +71,8 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
   dev_alloc(&d_weights_, N, "weights staging");
   dev_alloc(&d_flying_, N, "flying staging");
   dev_alloc(&d_stats_, 1, "stats");
+  dev_alloc(&d_initial_weight_, 1, "initial weight");
+  cuda_or_throw(cudaMemset(d_initial_weight_, 0, sizeof(double)), "memset");
   dev_alloc(&d_tickets_, kTicketRing, "tickets");
   dev_alloc(&d_pcell_, N, "particle cells");
   dev_alloc(&d_order_, N, "processing order");
@@ -124,10 +126,18 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
   if (nccl_comm_) nccl_comm_destroy(nccl_comm_);
+  cudaFree(d_flux_global_);
+  if (ev_ar0_) cudaEventDestroy(ev_ar0_);
+  if (ev_ar1_) cudaEventDestroy(ev_ar1_);
   for (auto &r : registered_) cudaHostUnregister(const_cast<void *>(r.first));
   for (auto &t : timers_free_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto &t : timers_busy_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto &e : chunk_events_) cudaEventDestroy(e);
+  stager_.reset();
+  if (stage_base_) {
+    if (stage_registered_) { cudaHostUnregister(stage_base_); free(stage_base_); }
+    else cudaFreeHost(stage_base_);
+  }
   cudaFree(d_rows_);
   if (h_patch_) cudaFreeHost(h_patch_);
   cudaFree(d_patch_);
@@ -136,6 +146,7 @@ Engine::~Engine() {
   cudaFree(d_state_);
   cudaFree(d_origin_); cudaFree(d_dest_); cudaFree(d_weights_); cudaFree(d_flying_);
   cudaFree(d_stats_);
+  cudaFree(d_initial_weight_);
   cudaFree(d_tickets_);
   cudaFree(d_grid_);
   cudaFree(d_cell_rank_);
@@ -246,6 +257,9 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
                          const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream,
                          bool timed) {
   if (end <= begin) return 0;
+  if (d_dest) flux_global_valid_ = false;  // the local tally moves on; the last exchange no longer describes it
+  if (d_dest && d_weights && initial_weight_pending_)  // first tracks of the batch: their total weight
+    PTB_CUDA_OK(launch_sum_flying_weights(d_flying, d_weights, begin, end, d_initial_weight_, stream));
   WalkParams p{};
   p.tets = d_tets_;
   p.links = d_links_;
@@ -371,11 +385,29 @@ int Engine::copy_initial_position(const double *xyz, int32_t size) {
     return 1;
   }
   PTB_CUDA_OK(cudaSetDevice(device_));
-  PTB_CUDA_OK(cudaMemcpyAsync(d_origin_, xyz, size_t(size) * sizeof(double), cudaMemcpyHostToDevice, compute_));
+  // Through the staging slots when they can be had: the pool copies xyz into the pinned dest slots
+  // (pageable cudaMemcpy runs at a fifth of the PCIe rate) and the device copy goes to d_dest_, so
+  // that "pinned dest slots == device dest array == where every particle is" already holds for the
+  // first move and its origins need not travel either.
+  const double *src = xyz;
+  double *d_xyz = d_origin_;
+  if (host_path_ == 1 && n_ > 0 && ensure_stage_buffers(xyz, size_t(size) * sizeof(double)) == 0) {
+    HostPool *pool_ = &stager_->pool();
+    const int T = pool_->size();
+    const int64_t total = int64_t(size);
+    pool_->run([&](int t) {
+      const int64_t lo = (total * t / T) & ~int64_t(7), hi = t == T - 1 ? total : (total * (t + 1) / T) & ~int64_t(7);
+      std::memcpy(h_dest_ + lo, xyz + lo, size_t(hi - lo) * sizeof(double));
+    });
+    src = h_dest_;
+    d_xyz = d_dest_;
+    mirror_valid_ = true;
+  }
+  PTB_CUDA_OK(cudaMemcpyAsync(d_xyz, src, size_t(size) * sizeof(double), cudaMemcpyHostToDevice, compute_));
   h2d_bytes_ += double(size) * sizeof(double);
   move_variant_ = variant_;
   move_tag_ = -1;
-  if (launch_range(d_origin_, nullptr, nullptr, nullptr, 0, n_, compute_, true)) return 1;
+  if (launch_range(d_xyz, nullptr, nullptr, nullptr, 0, n_, compute_, true)) return 1;
   PTB_CUDA_OK(cudaStreamSynchronize(compute_));
   initialized_ = true;
   return 0;
@@ -394,11 +426,88 @@ int Engine::copy_initial_position_device(const double *d_xyz, int32_t size, cuda
   return 0;
 }
 
-constexpr int kPatchSlots = 4;          // pinned patch lists in flight
+constexpr int kPatchSlots = 4;             // pinned patch lists in flight
 constexpr double kPatchMaxFraction = 0.4;  // above this share of changed origins a chunk is sent whole
 
+// Pinned staging ("bounce") buffers of the host-pointer path, allocated at the first host call:
+// one slot per particle for dest, weight and flying.  They are the DMA source of every move AND the
+// mirror the next move's origins are compared against (host_stage.hpp).  Ordinary page-aligned
+// memory, first touched by the pool's workers (which run on the GPU's NUMA node) and then
+// page-locked with cudaHostRegister -- an order of magnitude faster than cudaHostAlloc for
+// hundreds of MB; cudaHostAlloc is the fallback.
+// The workers follow the caller's memory: if the arrays of this call live on another NUMA node than
+// the one the pool runs on, the workers move there (a few microseconds, once per change).
+void Engine::follow_caller_memory(const void *p, size_t bytes) {
+  if (!stager_) return;
+  const int node = numa_node_of(p, bytes);
+  if (node < 0 || node == pool_node_) return;
+  const std::vector<int> cpus = numa_node_cpus(node);
+  if (cpus.empty()) return;
+  stager_->pool().repin(cpus);
+  pool_node_ = node;
+}
+
+int Engine::ensure_stage_buffers(const void *caller_mem, size_t caller_bytes) {
+  if (stage_ready_) return 0;
+  if (stage_failed_) return 1;
+  const size_t N = std::max<size_t>(size_t(n_), 1);
+  if (!stager_) {
+    // workers (and, by first touch, the staging slots) on the NUMA node of the caller's arrays; when
+    // that cannot be determined, on the GPU's node
+    std::vector<int> cpus;
+    pool_node_ = numa_node_of(caller_mem, caller_bytes);
+    if (pool_node_ >= 0) cpus = numa_node_cpus(pool_node_);
+    if (cpus.empty()) {
+      char bus[64] = {0};
+      pool_node_ = -1;
+      if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device_) == cudaSuccess) cpus = gpu_local_cpus(bus);
+      else cudaGetLastError();
+    }
+    // one of the CPUs the quota allows is left to the calling thread, which enqueues copies and kernels
+    stager_.reset(new HostStager(host_threads_ > 0 ? host_threads_ : std::max(1, default_host_threads() - 1), cpus));
+  }
+  HostPool *pool_ = &stager_->pool();
+  const size_t bytes_dest = (3 * N * sizeof(double) + 4095) & ~size_t(4095);
+  const size_t bytes_w = (N * sizeof(double) + 4095) & ~size_t(4095);
+  const size_t bytes_fly = (N + 4095) & ~size_t(4095);
+  const size_t total = bytes_dest + bytes_w + bytes_fly;
+  void *base = nullptr;
+  if (posix_memalign(&base, 4096, total) == 0) {
+    const int T = pool_->size();
+    pool_->run([&](int t) {  // first touch on the workers' NUMA node
+      const size_t lo = (total * size_t(t) / size_t(T)) & ~size_t(4095);
+      const size_t hi = t == T - 1 ? total : (total * size_t(t + 1) / size_t(T)) & ~size_t(4095);
+      std::memset(static_cast<char *>(base) + lo, 0, hi - lo);
+    });
+    if (cudaHostRegister(base, total, cudaHostRegisterDefault) == cudaSuccess) {
+      stage_registered_ = true;
+    } else {
+      cudaGetLastError();
+      free(base);
+      base = nullptr;
+    }
+  }
+  if (!base) {
+    if (cudaHostAlloc(&base, total, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      stage_failed_ = true;  // the direct path (plain copies from the caller's memory) still works
+      fprintf(stderr, "[pumitally] WARNING: no pinned host memory for the staging buffers (%zu MB); "
+                      "uploads fall back to direct copies from the caller's arrays\n", total >> 20);
+      return 1;
+    }
+    stage_registered_ = false;
+  }
+  stage_base_ = base;
+  h_dest_ = static_cast<double *>(base);
+  h_w_ = reinterpret_cast<double *>(static_cast<char *>(base) + bytes_dest);
+  h_fly_ = reinterpret_cast<int8_t *>(static_cast<char *>(base) + bytes_dest + bytes_w);
+  stager_->set_buffers(h_dest_, h_w_, h_fly_);
+  stage_ready_ = true;
+  return 0;
+}
+
 int Engine::ensure_patch_buffers(int nchunks) {
-  const size_t cap = size_t(double(std::min<int64_t>(chunk_, n_)) * kPatchMaxFraction) + 1;
+  const size_t cap = size_t(double(std::min<int64_t>(chunk_, n_)) * kPatchMaxFraction) + 64;
   if (h_patch_ && patch_cap_ == cap && patch_chunks_ >= nchunks) return 0;
   PTB_CUDA_OK(cudaDeviceSynchronize());
   if (h_patch_) cudaFreeHost(h_patch_);
@@ -409,49 +518,24 @@ int Engine::ensure_patch_buffers(int nchunks) {
   patch_chunks_ = nchunks;
   PTB_CUDA_OK(cudaHostAlloc(reinterpret_cast<void **>(&h_patch_), cap * kPatchSlots * sizeof(PatchEntry), cudaHostAllocDefault));
   PTB_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&d_patch_), cap * size_t(nchunks) * sizeof(PatchEntry)));
-  if (patch_threads_ <= 0) patch_threads_ = std::max(1, std::min(omp_get_max_threads(), 32));
+  stager_->reserve(cap);
   return 0;
 }
 
-// Particles of [b,e) whose origin differs (bitwise) from the previous move's destination ->
-// patch list; the mirror then takes this move's destinations.  One pass over the three arrays:
-// every thread collects its sub-range's entries privately, then the (short) lists are packed
-// into the pinned slot.  Returns the list length, or -1 when it would exceed the chunk's
-// capacity (the caller then uploads the origin slice whole).
-int Engine::build_patch(const double *origin, const double *dest, int32_t b, int32_t e, PatchEntry *out) {
-  const int nt = patch_threads_;
-  if (int(patch_tls_.size()) != nt) patch_tls_.assign(size_t(nt), std::vector<PatchEntry>());
-  std::vector<int64_t> first(size_t(nt) + 1, 0);
-  double *mir = mirror_.data();
-#pragma omp parallel num_threads(nt)
-  {
-    const int t = omp_get_thread_num();
-    const int64_t len = int64_t(e) - b;
-    const int64_t lo = b + len * t / nt, hi = b + len * (t + 1) / nt;
-    std::vector<PatchEntry> &mine = patch_tls_[size_t(t)];
-    mine.clear();
-    for (int64_t i = lo; i < hi; ++i) {
-      uint64_t a[3], m[3];
-      std::memcpy(a, origin + 3 * i, 24);
-      std::memcpy(m, mir + 3 * i, 24);
-      if (((a[0] ^ m[0]) | (a[1] ^ m[1]) | (a[2] ^ m[2])) != 0)
-        mine.push_back(PatchEntry{origin[3 * i], origin[3 * i + 1], origin[3 * i + 2], int32_t(i), 0});
-      std::memcpy(mir + 3 * i, dest + 3 * i, 24);
-    }
-    first[size_t(t) + 1] = int64_t(mine.size());
-  }
-  for (int k = 0; k < nt; ++k) first[size_t(k) + 1] += first[size_t(k)];
-  if (first[size_t(nt)] > int64_t(patch_cap_)) return -1;
-  for (int k = 0; k < nt; ++k)
-    if (!patch_tls_[size_t(k)].empty())
-      std::memcpy(out + first[size_t(k)], patch_tls_[size_t(k)].data(), patch_tls_[size_t(k)].size() * sizeof(PatchEntry));
-  return int(first[size_t(nt)]);
-}
-
-// MoveToNextLocation (PumiTallyImpl.cpp:66-149), host pointers.  The uploads are cut into
-// particle ranges; range k is walked while range k+1 is still on the wire.  With delta upload the
-// origin array is not sent: the device's copy of the previous destinations becomes the origin
-// array and only the origins that changed are patched in (see engine.hpp).
+// MoveToNextLocation (PumiTallyImpl.cpp:66-149), host pointers.
+//
+// Staged path (default): the particle range is cut into chunks; for each chunk the pool refills the
+// pinned staging slots from the caller's arrays and finds the origins that differ from the previous
+// destinations (stage_chunk), then flying + patch list + dest + weights of the chunk are enqueued on
+// the copy stream and the walk kernel of the chunk behind them on the compute stream -- chunk k is
+// on the wire and chunk k-1 is being walked while the pool stages chunk k+1.  The device's copy of
+// the previous destinations becomes this move's origin array (buffer swap) and only the changed
+// origins are patched in, so 32 B + a few patch bytes per particle cross PCIe instead of 57 B.  The
+// call returns as soon as the caller's arrays have been consumed (they are in the staging buffers
+// by then; reference: blocking deep_copy); copies and kernels may still be in flight.
+//
+// Direct path (option host_path=0, or no pinned memory to be had): plain cudaMemcpyAsync of all
+// four arrays from the caller's memory, optionally page-locked first (option register_host).
 int Engine::move_to_next_location(const double *origin, const double *dest, int8_t *flying,
                                   const double *weights, int32_t size) {
   if (int64_t(size) != 3 * int64_t(n_)) {
@@ -464,95 +548,123 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
   }
   PTB_CUDA_OK(cudaSetDevice(device_));
   begin_move();
-  maybe_register(origin, size_t(size) * sizeof(double));
-  maybe_register(dest, size_t(size) * sizeof(double));
-  maybe_register(weights, size_t(n_) * sizeof(double));
-  maybe_register(flying, size_t(n_));
   const int nchunks = n_ ? (n_ + chunk_ - 1) / chunk_ : 0;
   while (int(chunk_events_.size()) < nchunks + 2) {
     cudaEvent_t e;
     PTB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     chunk_events_.push_back(e);
   }
-  const bool delta = delta_upload_ && mirror_valid_ && n_ > 0;
-  mirror_valid_ = false;  // until this move has gone through completely
-  if (delta_upload_ && n_ > 0) {
-    if (mirror_.size() != 3 * size_t(n_)) mirror_.resize(3 * size_t(n_));
-    if (ensure_patch_buffers(nchunks)) return 1;
+  const bool staged = host_path_ == 1 && n_ > 0 && ensure_stage_buffers(dest, size_t(size) * sizeof(double)) == 0 &&
+                      ensure_patch_buffers(nchunks) == 0;
+  if (!staged) return move_direct(origin, dest, flying, weights, nchunks);
+  follow_caller_memory(dest, size_t(size) * sizeof(double));
+
+  // a chunk's staging slots may be refilled once the previous move's copies out of them are done;
+  // with an unchanged chunking that is chunk_events_[k], otherwise wait for the whole copy stream
+  if (staged_chunk_ != chunk_ || staged_chunks_ != nchunks) {
+    PTB_CUDA_OK(cudaStreamSynchronize(copy_));
+    staged_chunks_ = 0;
   }
-  cudaEvent_t ev_prev_done = chunk_events_[nchunks], ev_fly = chunk_events_[nchunks + 1];
-  // staging buffers are free once the previous move's kernels have finished
+  const bool compare = mirror_valid_;
+  mirror_valid_ = false;  // until this move has gone through completely
+  cudaEvent_t ev_prev_done = chunk_events_[nchunks];
+  // the device staging arrays are free once the previous move's kernels have finished
   PTB_CUDA_OK(cudaEventRecord(ev_prev_done, compute_));
   PTB_CUDA_OK(cudaStreamWaitEvent(copy_, ev_prev_done, 0));
   // the previous destinations, still on the device, are this move's origins before patching
-  if (delta) std::swap(d_origin_, d_dest_);
-  PTB_CUDA_OK(cudaMemcpyAsync(d_flying_, flying, size_t(n_), cudaMemcpyHostToDevice, copy_));
-  PTB_CUDA_OK(cudaEventRecord(ev_fly, copy_));
-  double host_s = 0.0, sent = double(n_);
+  if (compare) std::swap(d_origin_, d_dest_);
+  double sent = 0.0;
+  bool caller_memory_on_the_wire = false;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto range_of = [&](int k, int32_t &b, int32_t &e) {
+    b = int32_t(int64_t(k) * chunk_);
+    e = int32_t(std::min<int64_t>(n_, int64_t(b) + chunk_));
+  };
+  // the staging slots of chunk k may be refilled once the previous move's copies out of them are done,
+  // its pinned patch slot once the copies of chunk k - kPatchSlots of this move are done
+  auto start_stage = [&](int k) -> int {
+    if (k < staged_chunks_) PTB_CUDA_OK(cudaEventSynchronize(chunk_events_[k]));
+    if (k >= kPatchSlots) PTB_CUDA_OK(cudaEventSynchronize(chunk_events_[k - kPatchSlots]));
+    int32_t b, e;
+    range_of(k, b, e);
+    stager_->begin(origin, dest, flying, weights, b, e, compare, h_patch_ + size_t(k % kPatchSlots) * patch_cap_);
+    return 0;
+  };
+  if (nchunks > 0 && start_stage(0)) return 1;
   for (int k = 0; k < nchunks; ++k) {
-    const int32_t b = int32_t(int64_t(k) * chunk_), e = int32_t(std::min<int64_t>(n_, int64_t(b) + chunk_));
+    int32_t b, e;
+    range_of(k, b, e);
     const size_t cnt = size_t(e - b);
-    int npatch = -1;
-    PatchEntry *hp = nullptr, *dp = nullptr;
-    if (delta) {
-      // the pinned slot is free once the copies of chunk k - kPatchSlots have been issued and done
-      if (k >= kPatchSlots) PTB_CUDA_OK(cudaEventSynchronize(chunk_events_[k - kPatchSlots]));
-      hp = h_patch_ + size_t(k % kPatchSlots) * patch_cap_;
-      dp = d_patch_ + size_t(k) * patch_cap_;
-      const auto t0 = std::chrono::steady_clock::now();
-      npatch = build_patch(origin, dest, b, e, hp);
-      host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    }
-    if (npatch < 0) {
+    const int64_t npatch = stager_->end();  // chunk k is staged
+    // the workers stage chunk k+1 while this thread enqueues the copies and kernels of chunk k
+    if (k + 1 < nchunks && start_stage(k + 1)) return 1;
+    PatchEntry *hp = h_patch_ + size_t(k % kPatchSlots) * patch_cap_, *dp = d_patch_ + size_t(k) * patch_cap_;
+    PTB_CUDA_OK(cudaMemcpyAsync(d_flying_ + b, h_fly_ + b, cnt, cudaMemcpyHostToDevice, copy_));
+    if (!compare || npatch < 0) {  // no usable mirror, or too many changed origins: the slice travels whole
       PTB_CUDA_OK(cudaMemcpyAsync(d_origin_ + 3 * size_t(b), origin + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
       sent += 24.0 * double(cnt);
+      caller_memory_on_the_wire = true;
     } else if (npatch > 0) {
       PTB_CUDA_OK(cudaMemcpyAsync(dp, hp, size_t(npatch) * sizeof(PatchEntry), cudaMemcpyHostToDevice, copy_));
       sent += double(npatch) * sizeof(PatchEntry);
     }
-    PTB_CUDA_OK(cudaMemcpyAsync(d_dest_ + 3 * size_t(b), dest + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
-    PTB_CUDA_OK(cudaMemcpyAsync(d_weights_ + b, weights + b, cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
-    sent += 32.0 * double(cnt);
+    PTB_CUDA_OK(cudaMemcpyAsync(d_dest_ + 3 * size_t(b), h_dest_ + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+    PTB_CUDA_OK(cudaMemcpyAsync(d_weights_ + b, h_w_ + b, cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+    sent += 33.0 * double(cnt);
     PTB_CUDA_OK(cudaEventRecord(chunk_events_[k], copy_));
     PTB_CUDA_OK(cudaStreamWaitEvent(compute_, chunk_events_[k], 0));
-    if (npatch > 0) {
-      PTB_CUDA_OK(launch_patch_origins(d_origin_, dp, npatch, compute_));
+    if (compare && npatch > 0) {
+      PTB_CUDA_OK(launch_patch_origins(d_origin_, dp, int32_t(npatch), compute_));
       ++launches_;
     }
     if (launch_range(d_origin_, d_dest_, d_flying_, d_weights_, b, e, compute_, true)) return 1;
   }
+  // origin slices that went whole were read from the caller's own memory (asynchronously, if it is
+  // pinned): they must be on the device before the caller gets its arrays back
+  if (caller_memory_on_the_wire) PTB_CUDA_OK(cudaStreamSynchronize(copy_));
+  stage_host_s_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  stage_sent_bytes_ = sent;
   h2d_bytes_ += sent;
-  if (delta_upload_ && n_ > 0) {
-    if (!delta) {  // first host move (or one after a device move): start the mirror
-      const auto t0 = std::chrono::steady_clock::now();
-      const int64_t total = 3 * int64_t(n_);
-#pragma omp parallel for num_threads(patch_threads_) schedule(static)
-      for (int64_t blk = 0; blk < (total + 65535) / 65536; ++blk) {
-        const int64_t lo = blk * 65536, hi = std::min<int64_t>(total, lo + 65536);
-        std::memcpy(mirror_.data() + lo, dest + lo, size_t(hi - lo) * sizeof(double));
-      }
-      host_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      mirror_valid_ = true;
-    } else {
-      // self-check: if comparing costs the host more than the bytes it saves cost the link
-      // (many ranks sharing one memory system), fall back to plain uploads
-      delta_host_s_ = host_s;
-      delta_saved_bytes_ = double(n_) * 57.0 - sent;
-      const double saved_s = delta_saved_bytes_ / 50e9;
-      delta_strikes_ = (host_s > 1.5 * saved_s) ? delta_strikes_ + 1 : 0;
-      mirror_valid_ = true;
-      if (delta_strikes_ >= 3 && delta_auto_) {
-        delta_upload_ = false;
-        mirror_valid_ = false;
-        std::vector<double>().swap(mirror_);
-      }
-    }
+  staged_chunk_ = chunk_;
+  staged_chunks_ = nchunks;
+  mirror_valid_ = true;
+  initial_weight_pending_ = false;
+  ++moves_;
+  return 0;
+}
+
+// Direct path: every array is copied from the caller's memory as it is.
+int Engine::move_direct(const double *origin, const double *dest, int8_t *flying, const double *weights,
+                        int nchunks) {
+  mirror_valid_ = false;  // the staging slots do not see this move
+  maybe_register(origin, 3 * size_t(n_) * sizeof(double));
+  maybe_register(dest, 3 * size_t(n_) * sizeof(double));
+  maybe_register(weights, size_t(n_) * sizeof(double));
+  maybe_register(flying, size_t(n_));
+  cudaEvent_t ev_prev_done = chunk_events_[nchunks], ev_fly = chunk_events_[nchunks + 1];
+  PTB_CUDA_OK(cudaStreamSynchronize(copy_));  // staged copies of an earlier move
+  staged_chunks_ = 0;
+  PTB_CUDA_OK(cudaEventRecord(ev_prev_done, compute_));
+  PTB_CUDA_OK(cudaStreamWaitEvent(copy_, ev_prev_done, 0));
+  PTB_CUDA_OK(cudaMemcpyAsync(d_flying_, flying, size_t(n_), cudaMemcpyHostToDevice, copy_));
+  PTB_CUDA_OK(cudaEventRecord(ev_fly, copy_));
+  for (int k = 0; k < nchunks; ++k) {
+    const int32_t b = int32_t(int64_t(k) * chunk_), e = int32_t(std::min<int64_t>(n_, int64_t(b) + chunk_));
+    const size_t cnt = size_t(e - b);
+    PTB_CUDA_OK(cudaMemcpyAsync(d_origin_ + 3 * size_t(b), origin + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+    PTB_CUDA_OK(cudaMemcpyAsync(d_dest_ + 3 * size_t(b), dest + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+    PTB_CUDA_OK(cudaMemcpyAsync(d_weights_ + b, weights + b, cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+    PTB_CUDA_OK(cudaEventRecord(chunk_events_[k], copy_));
+    PTB_CUDA_OK(cudaStreamWaitEvent(compute_, chunk_events_[k], 0));
+    if (launch_range(d_origin_, d_dest_, d_flying_, d_weights_, b, e, compute_, true)) return 1;
   }
+  h2d_bytes_ += 57.0 * double(n_);
   // reset the caller's flags once they are on the device (PumiTallyImpl.cpp:169-172)
   PTB_CUDA_OK(cudaEventSynchronize(ev_fly));
   if (n_) std::memset(flying, 0, size_t(n_));
   // caller may reuse its buffers on return (reference: blocking deep_copy)
   PTB_CUDA_OK(cudaStreamSynchronize(copy_));
+  initial_weight_pending_ = false;
   ++moves_;
   return 0;
 }
@@ -566,8 +678,10 @@ int Engine::move_to_next_location_device(const double *d_origin, const double *d
   }
   PTB_CUDA_OK(cudaSetDevice(device_));
   begin_move();
-  mirror_valid_ = false;  // the staging buffers no longer hold the previous host move's destinations
+  // (the staging arrays are not touched: "pinned dest slots == device dest array" keeps holding, and the
+  // next host move's origins are compared against them and patched exactly as after a host move)
   if (launch_range(d_origin, d_dest, d_flying, d_weights, 0, n_, stream, true)) return 1;
+  initial_weight_pending_ = false;
   ++moves_;
   return 0;
 }
@@ -582,7 +696,7 @@ int Engine::get_flux(double *out, int64_t n) {
   if (n != mesh_.ntets) return 1;
   if (synchronize()) return 1;
   std::vector<double> tmp(static_cast<size_t>(n));
-  PTB_CUDA_OK(cudaMemcpy(tmp.data(), d_flux_, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
+  PTB_CUDA_OK(cudaMemcpy(tmp.data(), flux_view(), size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < n; ++i) out[mesh_.orig_of_internal[i]] = tmp[i];  // caller's numbering
   return 0;
 }
@@ -592,7 +706,12 @@ int Engine::get_normalized_flux(double *out_flux, double *out_volume, int64_t n)
   if (n != mesh_.ntets) return 1;
   if (synchronize()) return 1;
   if (out_flux) {
-    PTB_CUDA_OK(launch_normalize(d_flux_, d_volume_, d_scratch_, n, compute_));
+    const double per_source = source_normalization();
+    if (!(per_source > 0.0)) {
+      fprintf(stderr, "[pumitally] ERROR: source normalisation divisor is %g (no source weight seen yet?)\n", per_source);
+      return 1;
+    }
+    PTB_CUDA_OK(launch_normalize(flux_view(), d_volume_, d_scratch_, n, per_source, compute_));
     PTB_CUDA_OK(cudaStreamSynchronize(compute_));
     std::vector<double> tmp(static_cast<size_t>(n));
     PTB_CUDA_OK(cudaMemcpy(tmp.data(), d_scratch_, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
@@ -625,11 +744,35 @@ int Engine::get_positions(double *out, int64_t n3) {
   return 0;
 }
 
+int Engine::set_source_normalization(int mode, double value) {
+  if (mode < 0 || mode > 3 || (mode == 2 && !(value > 0.0))) return 1;
+  norm_mode_ = mode;
+  norm_value_ = value;
+  return 0;
+}
+
+double Engine::source_normalization() {
+  switch (norm_mode_) {
+    case 1: return double(std::max(n_, 1));
+    case 2: return norm_value_;
+    case 3: {
+      double w = 0.0;
+      cudaDeviceSynchronize();
+      if (cudaMemcpy(&w, d_initial_weight_, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return 0.0;
+      return w;
+    }
+    default: return 1.0;
+  }
+}
+
 int Engine::reset_tally() {
   if (synchronize()) return 1;
   collect_timers(true);
+  PTB_CUDA_OK(cudaMemset(d_initial_weight_, 0, sizeof(double)));
+  initial_weight_pending_ = true;
   PTB_CUDA_OK(cudaMemset(d_flux_, 0, size_t(mesh_.ntets) * sizeof(double)));
   PTB_CUDA_OK(cudaMemset(d_stats_, 0, sizeof(DeviceStats)));
+  flux_global_valid_ = false;
   kernel_ms_ = 0.0;
   h2d_bytes_ = 0.0;
   moves_ = 0;
@@ -679,9 +822,13 @@ int64_t Engine::get_option(const std::string &name) const {
     size_t g = 0;
     return cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity) == cudaSuccess ? int64_t(g) : -1;
   }
-  if (name == "delta_upload") return delta_upload_ ? (delta_auto_ ? 1 : 2) : 0;
-  if (name == "delta_host_us") return int64_t(delta_host_s_ * 1e6);       // last move: host time spent comparing
-  if (name == "delta_saved_bytes") return int64_t(delta_saved_bytes_);   // last move: bytes not sent
+  if (name == "allreduce_us") return int64_t(allreduce_ms_ * 1e3);  // device time of the last batch-end exchange
+  if (name == "host_path") return host_path_;
+  if (name == "host_threads") return stager_ ? stager_->threads() : host_threads_;
+  if (name == "stage_host_us") return int64_t(stage_host_s_ * 1e6);   // last staged move: host time from entry to return
+  if (name == "stage_sent_bytes") return int64_t(stage_sent_bytes_);  // last staged move: bytes put on the wire
+  if (name == "staged") return stage_ready_ ? 1 : 0;
+  if (name == "host_node") return pool_node_;  // NUMA node the staging workers run on (-1: not pinned to one)
   return -1;
 }
 
@@ -722,13 +869,13 @@ int Engine::set_option(const std::string &name, int64_t v) {
   } else if (name == "l2_fetch") {  // bytes an L2 miss fetches from DRAM: 32, 64 or 128 (device-wide limit)
     if (v != 32 && v != 64 && v != 128) return 1;
     if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(v)) != cudaSuccess) { cudaGetLastError(); return 1; }
-  } else if (name == "delta_threads") {
-    if (v < 1 || v > 1024) return 1;
-    patch_threads_ = int(v);
-  } else if (name == "delta_upload") {  // 0 off, 1 on unless it stops paying (self-check), 2 always on
-    delta_upload_ = v != 0;
-    delta_auto_ = v != 2;
-    if (!delta_upload_) { mirror_valid_ = false; std::vector<double>().swap(mirror_); }
+  } else if (name == "host_path") {  // 1 = staged through the pinned slots (default), 0 = direct copies
+    if (v != 0 && v != 1) return 1;
+    host_path_ = int(v);
+    if (host_path_ == 0) mirror_valid_ = false;
+  } else if (name == "host_threads") {  // workers of the staging pool; before the first host-pointer call
+    if (v < 1 || v > 256 || stager_) return 1;
+    host_threads_ = int(v);
   } else if (name == "morton") {
     morton_ = v != 0;
   } else if (name == "claim_run") {
@@ -771,21 +918,30 @@ int Engine::comm_init(int rank, int nranks, const uint8_t id[128]) {
   nranks_ = nranks;
   // NCCL sets up its NVLink connections lazily inside the first collective: pay that here,
   // on the scratch array, not in the first batch-end exchange
+  PTB_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&d_flux_global_), std::max<size_t>(size_t(mesh_.ntets), 1) * sizeof(double)));
+  PTB_CUDA_OK(cudaEventCreate(&ev_ar0_));
+  PTB_CUDA_OK(cudaEventCreate(&ev_ar1_));
   PTB_CUDA_OK(cudaMemsetAsync(d_scratch_, 0, size_t(mesh_.ntets) * sizeof(double), compute_));
-  if (nccl_allreduce_sum_f64(nccl_comm_, d_scratch_, size_t(mesh_.ntets), compute_)) return 1;
+  if (nccl_allreduce_sum_f64(nccl_comm_, d_scratch_, d_flux_global_, size_t(mesh_.ntets), compute_)) return 1;
   PTB_CUDA_OK(cudaStreamSynchronize(compute_));
   return 0;
 }
 
 // Batch-end exchange: sum the per-rank tallies.  Every rank holds a full-buffer
 // picpart (all elements are ghosts of every other rank), so the ghost-layer
-// array is the whole flux array.
+// array is the whole flux array.  Out of place: d_flux_ stays this rank's own running tally, the
+// sum over ranks lands in d_flux_global_ -- the call may be repeated after every batch.
 int Engine::allreduce_tally() {
   if (!nccl_comm_) return nranks_ == 1 ? 0 : 1;
   PTB_CUDA_OK(cudaSetDevice(device_));
   PTB_CUDA_OK(cudaDeviceSynchronize());
-  if (nccl_allreduce_sum_f64(nccl_comm_, d_flux_, size_t(mesh_.ntets), compute_)) return 1;
+  PTB_CUDA_OK(cudaEventRecord(ev_ar0_, compute_));
+  if (nccl_allreduce_sum_f64(nccl_comm_, d_flux_, d_flux_global_, size_t(mesh_.ntets), compute_)) return 1;
+  PTB_CUDA_OK(cudaEventRecord(ev_ar1_, compute_));
   PTB_CUDA_OK(cudaStreamSynchronize(compute_));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ev_ar0_, ev_ar1_) == cudaSuccess) allreduce_ms_ = ms;
+  flux_global_valid_ = true;
   return 0;
 }
 

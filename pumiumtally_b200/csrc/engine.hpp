@@ -5,12 +5,15 @@
 // pumi-pic / Omega_h.
 #pragma once
 #include <cstdint>
+#include <functional>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
 
 #include <cuda_runtime.h>
 
+#include "host_stage.hpp"
 #include "tet_mesh.hpp"
 #include "walk_kernels.hpp"
 
@@ -50,9 +53,16 @@ class Engine {
   int get_element_ids(int32_t *out, int64_t n);
   int get_positions(double *out, int64_t n3);
   int reset_tally();
+  // Per-source normalisation of the *normalised* flux (get_normalized_flux, WriteTallyResults); the raw
+  // flux is never touched.  0 = none (reference behaviour: flux / volume, PumiTallyImpl.cpp:402),
+  // 1 = also divide by the number of particles (what PumiTally.h:93 documents), 2 = by `value`
+  // (a total source weight the caller knows), 3 = by the total weight of the first tracks after
+  // CopyInitialPosition / reset_tally (the reference's total_initial_weight, PumiTallyImpl.h:170-171).
+  int set_source_normalization(int mode, double value);
+  double source_normalization();  // the divisor currently in effect (1 for mode 0)
   int get_stats(EngineStats *out);
   int synchronize();
-  double *flux_device_ptr() { return d_flux_; }
+  double *flux_device_ptr() { return flux_view(); }
   int set_option(const std::string &name, int64_t value);
   int64_t get_option(const std::string &name) const;
   void set_output_name(const std::string &s) { output_name_ = s; }
@@ -110,6 +120,10 @@ class Engine {
   VertexRec *d_verts_ = nullptr;
   TetStart *d_starts_ = nullptr;
   double *d_flux_ = nullptr, *d_volume_ = nullptr, *d_scratch_ = nullptr;
+  int norm_mode_ = 0;
+  double norm_value_ = 1.0;
+  double *d_initial_weight_ = nullptr;  // total weight of the first tracks of the batch
+  bool initial_weight_pending_ = true;  // the next move is the batch's first
   ParticleState *d_state_ = nullptr;  // persistent position + parent element, 32 B per particle
   double *d_origin_ = nullptr, *d_dest_ = nullptr, *d_weights_ = nullptr;  // staging
   int8_t *d_flying_ = nullptr;
@@ -134,38 +148,50 @@ class Engine {
   bool register_host_ = false;
   double kernel_ms_ = 0.0, h2d_bytes_ = 0.0;
 
-  // Delta upload (host-pointer path).  A transport code's next origin is, for every particle that
-  // was not re-sourced, bit for bit the destination it passed in the previous call.  The device
-  // still holds those destinations (d_dest_ of the previous move), so only the origins that differ
-  // from the host-side mirror of the previous dest array travel over PCIe, as a patch list.
-  // OFF by default: on the B200 boxes measured, comparing 10 M origins against the mirror costs the
-  // host 11 ms (memory-bound, ~0.96 GB of traffic) to save 4 ms of PCIe time
-  // (profiles/r01/README.md); option "delta_upload" = 1 turns it on with a self-check that
-  // switches it off again when it does not pay, 2 forces it.
-  bool delta_upload_ = false;
-  bool mirror_valid_ = false;         // mirror_ == the dest array of the previous host move == d_dest_
-  std::vector<double> mirror_;        // [3N]
+  // Host-pointer path, staged (host_stage.hpp): pinned per-particle slots for dest / weight / flying
+  // that are both the DMA source of a move and the mirror the next move's origins are compared
+  // against; only origins that changed travel, as a patch list applied to the device's copy of the
+  // previous destinations.  Invariant between moves (mirror_valid_): h_dest_ == the device array
+  // d_dest_, bit for bit.
+  int host_path_ = 1;                 // 1 staged (default), 0 direct copies from the caller's arrays
+  int host_threads_ = 0;              // 0 = default_host_threads() - 1
+  std::unique_ptr<HostStager> stager_;  // worker pool + per-chunk stage pass
+  void *stage_base_ = nullptr;
+  double *h_dest_ = nullptr, *h_w_ = nullptr;
+  int8_t *h_fly_ = nullptr;
+  bool stage_ready_ = false, stage_failed_ = false, stage_registered_ = false;
+  bool mirror_valid_ = false;
+  int32_t staged_chunk_ = 0;          // chunking of the last staged move (its chunk_events_ are still meaningful)
+  int staged_chunks_ = 0;
   PatchEntry *h_patch_ = nullptr;     // pinned ring of kPatchSlots chunk-sized lists
   PatchEntry *d_patch_ = nullptr;     // one list per chunk of a move
   size_t patch_cap_ = 0;              // entries per chunk
   int patch_chunks_ = 0;              // lists d_patch_ has room for
-  int patch_threads_ = 0;  // 0 = pick at first use
-  std::vector<std::vector<PatchEntry>> patch_tls_;
-  bool delta_auto_ = true;
-  double delta_host_s_ = 0.0, delta_saved_bytes_ = 0.0;  // last move: host time spent comparing, bytes not sent
-  int delta_strikes_ = 0;
-  int build_patch(const double *origin, const double *dest, int32_t b, int32_t e, PatchEntry *out);
+  double stage_host_s_ = 0.0, stage_sent_bytes_ = 0.0;
+  int pool_node_ = -1;
+  int ensure_stage_buffers(const void *caller_mem, size_t caller_bytes);
+  void follow_caller_memory(const void *p, size_t bytes);
   int ensure_patch_buffers(int nchunks);
+  int move_direct(const double *origin, const double *dest, int8_t *flying, const double *weights, int nchunks);
 
   // NCCL (resolved with dlopen at comm_init time)
   void *nccl_comm_ = nullptr;
   int rank_ = 0, nranks_ = 1;
+  // Result of the last batch-end exchange.  This rank's own tally keeps accumulating in d_flux_
+  // across moves (reference semantics: raw flux summed over all moves); the exchange writes the
+  // sum over ranks here, so it can be repeated after every batch without counting earlier batches
+  // twice.  The accessors return this array until the next move or reset changes the local tally.
+  double *d_flux_global_ = nullptr;
+  bool flux_global_valid_ = false;
+  double *flux_view() { return flux_global_valid_ ? d_flux_global_ : d_flux_; }
+  double allreduce_ms_ = 0.0;  // device time of the last exchange
+  cudaEvent_t ev_ar0_ = nullptr, ev_ar1_ = nullptr;
 };
 
 // NCCL entry points resolved with dlopen at run time (nccl_dl.cpp)
 int nccl_get_unique_id(uint8_t out[128]);
 int nccl_comm_init_rank(void **comm, int nranks, const uint8_t id[128], int rank);
-int nccl_allreduce_sum_f64(void *comm, double *buf, size_t count, cudaStream_t stream);
+int nccl_allreduce_sum_f64(void *comm, const double *send, double *recv, size_t count, cudaStream_t stream);
 void nccl_comm_destroy(void *comm);
 
 }  // namespace ptb

@@ -80,10 +80,10 @@ int nccl_comm_init_rank(void **comm, int nranks, const uint8_t idb[128], int ran
   return check(a, a->CommInitRank(comm, nranks, id, rank), "ncclCommInitRank");
 }
 
-int nccl_allreduce_sum_f64(void *comm, double *buf, size_t count, cudaStream_t stream) {
+int nccl_allreduce_sum_f64(void *comm, const double *send, double *recv, size_t count, cudaStream_t stream) {
   Api *a = api();
   if (!a) return 1;
-  return check(a, a->AllReduce(buf, buf, count, kNcclFloat64, kNcclSum, comm, stream), "ncclAllReduce");
+  return check(a, a->AllReduce(send, recv, count, kNcclFloat64, kNcclSum, comm, stream), "ncclAllReduce");
 }
 
 void nccl_comm_destroy(void *comm) {

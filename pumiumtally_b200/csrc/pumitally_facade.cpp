@@ -7,7 +7,11 @@
 
 #include <chrono>
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <stdexcept>
 
+#include "pumitally/PumiTallyExtras.h"
 #include "pumitally_c.h"
 
 namespace pumitally {
@@ -33,6 +37,22 @@ struct PumiTallyImpl {
   ~PumiTallyImpl() { pumitally_destroy(engine); }
 };
 
+// The reference header gives no access to what is behind pimpl_ and must stay as it is (it IS the ABI),
+// so the additive calls of PumiTallyExtras.h find the engine of a PumiTally object through this table.
+namespace {
+std::mutex registry_mutex;
+std::map<const PumiTally *, pumitally_engine *> &registry() {
+  static std::map<const PumiTally *, pumitally_engine *> r;
+  return r;
+}
+}  // namespace
+
+pumitally_engine *engine_of(const PumiTally &tally) {
+  std::lock_guard<std::mutex> lk(registry_mutex);
+  auto it = registry().find(&tally);
+  return it == registry().end() ? nullptr : it->second;
+}
+
 namespace {
 struct ScopedTimer {
   double &acc;
@@ -48,22 +68,36 @@ PumiTally::PumiTally(const std::string &mesh_filename, const int32_t num_particl
                      char **&argv)
     : pimpl_(std::make_unique<PumiTallyImpl>()) {
   pimpl_->engine = pumitally_create(mesh_filename.c_str(), num_particles, &argc, &argv);
+  // The reference prints and carries on (PumiTallyImpl.cpp:558-565); a tally object without an
+  // engine would silently turn every later call into a no-op and write an empty result, so this
+  // implementation refuses to exist instead.
   if (!pimpl_->engine)
-    fprintf(stderr, "[ERROR] pumitally: engine construction failed; every later call is a no-op\n");
+    throw std::runtime_error("pumitally::PumiTally: engine construction failed (mesh \"" + mesh_filename +
+                             "\" unreadable, or no usable CUDA device; this library has no CPU fallback)");
+  std::lock_guard<std::mutex> lk(registry_mutex);
+  registry()[this] = pimpl_->engine;
 }
 
-PumiTally::~PumiTally() { pimpl_.reset(nullptr); }
+PumiTally::~PumiTally() {
+  {
+    std::lock_guard<std::mutex> lk(registry_mutex);
+    registry().erase(this);
+  }
+  pimpl_.reset(nullptr);
+}
 
 void PumiTally::CopyInitialPosition(double *init_particle_positions, const std::int32_t size) const {
   ScopedTimer t(pimpl_->tally_times.initialization_time);
-  pumitally_copy_initial_position(pimpl_->engine, init_particle_positions, size);
+  if (pumitally_copy_initial_position(pimpl_->engine, init_particle_positions, size))
+    throw std::runtime_error("pumitally::PumiTally::CopyInitialPosition failed (see the message above)");
 }
 
 void PumiTally::MoveToNextLocation(double *particle_origin, double *particle_destinations,
                                    int8_t *flying, double *weights, const std::int32_t size) const {
   ScopedTimer t(pimpl_->tally_times.total_time_to_tally);
-  pumitally_move_to_next_location(pimpl_->engine, particle_origin, particle_destinations, flying,
-                                  weights, size);
+  if (pumitally_move_to_next_location(pimpl_->engine, particle_origin, particle_destinations, flying,
+                                      weights, size))
+    throw std::runtime_error("pumitally::PumiTally::MoveToNextLocation failed (see the message above)");
   // kernels of the last particle range may still be in flight here; the time
   // they take is charged to the next call that waits on them, as with the
   // reference's un-fenced Kokkos launches (PumiTallyImpl.cpp:146-148).
@@ -72,7 +106,14 @@ void PumiTally::MoveToNextLocation(double *particle_origin, double *particle_des
 void PumiTally::WriteTallyResults() const {
   {
     ScopedTimer t(pimpl_->tally_times.vtk_file_write_time);
-    pumitally_write_tally_results(pimpl_->engine);
+    // lost walks: get_stats prints the reference's "Not all particles are found" line
+    // (PumiTallyImpl.cpp:455-458) -- a result with lost particles must not pass silently
+    pumitally_stats st;
+    if (pumitally_get_stats(pimpl_->engine, &st) == 0 && st.lost)
+      fprintf(stderr, "[pumitally] WARNING: %llu walks were cut short by the crossing limit or had unusable "
+                      "(non-finite) inputs; the tally misses their contributions\n", (unsigned long long)st.lost);
+    if (pumitally_write_tally_results(pimpl_->engine))
+      throw std::runtime_error("pumitally::PumiTally::WriteTallyResults failed (see the message above)");
   }
   pimpl_->tally_times.PrintTimes();
 }

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <utility>
 #include <sys/stat.h>
 
 namespace ptb {
@@ -26,15 +27,31 @@ struct Block {
 bool write_vtk_dataset(const std::string &path, const HostMesh &m, const std::vector<double> &flux,
                        const std::vector<double> &volume, int rank, int nranks, std::string *err) {
   if (!make_dir(path, err) || !make_dir(path + "/pieces", err)) return false;
-  const uint64_t V = uint64_t(m.nverts), E = uint64_t(m.ntets);
+  const uint64_t V = uint64_t(m.nverts), Etot = uint64_t(m.ntets);
+  // One piece per rank.  After the batch-end exchange every rank holds the same global tally, so
+  // rank r writes the r-th contiguous slice of the elements (caller's numbering) and the pieces
+  // tile the mesh; with one rank the piece is the whole mesh, as in the reference.
+  const uint64_t e0 = Etot * uint64_t(rank) / uint64_t(nranks), e1 = Etot * uint64_t(rank + 1) / uint64_t(nranks);
+  const uint64_t E = e1 - e0;
   std::vector<int32_t> offsets(E);
   for (uint64_t e = 0; e < E; ++e) offsets[e] = int32_t(4 * (e + 1));
   std::vector<uint8_t> types(E, 10);  // VTK_TETRA
-  // connectivity in the caller's element order (the cell data arrays already are)
-  const std::vector<int32_t> conn = m.to_original(m.t2v.data(), 4);
-  const Block blocks[6] = {{m.coords.data(), V * 24}, {conn.data(), E * 16},
+  // connectivity in the caller's element order (the cell data arrays already are), every tet
+  // positively oriented as VTK expects: det(v1-v0, v2-v0, v3-v0) > 0
+  std::vector<int32_t> conn = m.to_original(m.t2v.data(), 4);
+  for (uint64_t e = e0; e < e1; ++e) {
+    int32_t *v = conn.data() + 4 * e;
+    const double *a = m.coords.data() + 3 * size_t(v[0]), *b = m.coords.data() + 3 * size_t(v[1]);
+    const double *c = m.coords.data() + 3 * size_t(v[2]), *d = m.coords.data() + 3 * size_t(v[3]);
+    const double ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]},
+                 ad[3] = {d[0] - a[0], d[1] - a[1], d[2] - a[2]};
+    const double det = ab[0] * (ac[1] * ad[2] - ac[2] * ad[1]) - ab[1] * (ac[0] * ad[2] - ac[2] * ad[0]) +
+                       ab[2] * (ac[0] * ad[1] - ac[1] * ad[0]);
+    if (det < 0.0) std::swap(v[2], v[3]);
+  }
+  const Block blocks[6] = {{m.coords.data(), V * 24}, {conn.data() + 4 * e0, E * 16},
                            {offsets.data(), E * 4},   {types.data(), E},
-                           {flux.data(), E * 8},      {volume.data(), E * 8}};
+                           {flux.data() + e0, E * 8}, {volume.data() + e0, E * 8}};
   uint64_t off[6], acc = 0;
   for (int i = 0; i < 6; ++i) { off[i] = acc; acc += 8 + blocks[i].bytes; }
 

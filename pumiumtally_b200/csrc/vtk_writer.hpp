@@ -11,7 +11,9 @@ namespace ptb {
 // Writes the directory layout Omega_h's parallel writer produces --
 // <path>/pieces.pvtu and <path>/pieces/piece_<rank>.vtu -- with cell data
 // "flux" (raw flux / tet volume) and "volume".  Arrays are stored as raw
-// appended binary (little endian, UInt64 block headers).
+// appended binary (little endian, UInt64 block headers).  flux and volume are
+// whole-mesh arrays in the caller's element order; rank r of nranks writes the
+// r-th contiguous slice of the elements as its piece, rank 0 also the .pvtu.
 bool write_vtk_dataset(const std::string &path, const HostMesh &mesh,
                        const std::vector<double> &flux, const std::vector<double> &volume,
                        int rank, int nranks, std::string *err);

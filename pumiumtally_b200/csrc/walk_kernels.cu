@@ -91,9 +91,20 @@ __global__ void patch_origins_kernel(double *origin, const PatchEntry *list, int
 }
 
 // K13 (PumiTallyImpl.cpp:393-405) with volumes precomputed at mesh build.
-__global__ void normalize_kernel(const double *flux, const double *volume, double *out, int64_t n) {
+__global__ void normalize_kernel(const double *flux, const double *volume, double *out, int64_t n, double per_source) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < n) out[e] = flux[e] / volume[e];
+  if (e < n) out[e] = flux[e] / volume[e] / per_source;  // per_source == 1: bit-identical to flux / volume
+}
+
+// Total weight of the particles that fly in this range (the reference's total_initial_weight,
+// PumiTallyImpl.h:170-171: declared "needed for normalization", never filled in).
+__global__ void sum_flying_weights_kernel(const int8_t *flying, const double *weights, int32_t begin, int32_t end,
+                                          double *total) {
+  double s = 0.0;
+  for (int i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x)
+    if ((!flying || flying[i] == 1) && all_finite(weights[i], 0.0, 0.0)) s += weights[i];
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(total, s);
 }
 
 }  // namespace
@@ -167,9 +178,17 @@ cudaError_t launch_patch_origins(double *origin, const PatchEntry *list, int32_t
 }
 
 cudaError_t launch_normalize(const double *flux, const double *volume, double *out, int64_t n,
-                             cudaStream_t stream) {
+                             double per_source, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(flux, volume, out, n);
+  normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(flux, volume, out, n, per_source);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sum_flying_weights(const int8_t *flying, const double *weights, int32_t begin, int32_t end,
+                                      double *total, cudaStream_t stream) {
+  if (end <= begin) return cudaSuccess;
+  const int n = end - begin;
+  sum_flying_weights_kernel<<<std::min((n + 255) / 256, 1184), 256, 0, stream>>>(flying, weights, begin, end, total);
   return cudaGetLastError();
 }
 

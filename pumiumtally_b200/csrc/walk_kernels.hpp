@@ -58,7 +58,11 @@ cudaError_t launch_init_particles(ParticleState *state, int32_t n, double cx, do
                                   int32_t elem, cudaStream_t stream);
 // origin[3*idx..] = (x,y,z) for every entry of the patch list
 cudaError_t launch_patch_origins(double *origin, const PatchEntry *list, int32_t count, cudaStream_t stream);
+// out = flux / volume / per_source (NormalizeFlux, PumiTallyImpl.cpp:393-405; per_source = 1 is the reference)
 cudaError_t launch_normalize(const double *flux, const double *volume, double *out, int64_t n,
-                             cudaStream_t stream);
+                             double per_source, cudaStream_t stream);
+// *total += sum of weights[i] over flying particles of [begin, end)
+cudaError_t launch_sum_flying_weights(const int8_t *flying, const double *weights, int32_t begin, int32_t end,
+                                      double *total, cudaStream_t stream);
 
 }  // namespace ptb

@@ -50,6 +50,8 @@ C_API = {
     "pumitally_get_positions": (C.c_int, [C.c_void_p, _dp, C.c_int64]),
     "pumitally_get_adjacency": (C.c_int, [C.c_void_p, _ip, C.c_int64]),
     "pumitally_reset_tally": (C.c_int, [C.c_void_p]),
+    "pumitally_set_source_normalization": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
+    "pumitally_get_source_normalization": (C.c_double, [C.c_void_p]),
     "pumitally_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "pumitally_set_output_name": (C.c_int, [C.c_void_p, C.c_char_p]),
     "pumitally_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
@@ -63,6 +65,8 @@ C_API = {
     "pumitally_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _u8p]),
     "pumitally_allreduce_tally": (C.c_int, [C.c_void_p]),
     "pumitally_debug_order": (C.c_int64, [C.c_void_p, _ip, C.c_int64]),
+    "pumitally_debug_stage": (C.c_int64, [_dp, _dp, _bp, _dp, _dp, _dp, _bp, C.c_int64, C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_int64]),
     "pumitally_version": (C.c_char_p, []),
 }
 
@@ -241,6 +245,14 @@ class PumiTally:
 
     def reset_tally(self):
         self._L.pumitally_reset_tally(self._h)
+
+    def set_source_normalization(self, mode: int, value: float = 1.0):
+        """0 volume only (reference), 1 /num_particles, 2 /value, 3 /total weight of the batch's first tracks."""
+        if self._L.pumitally_set_source_normalization(self._h, int(mode), float(value)):
+            raise ValueError(f"bad source normalisation mode={mode} value={value}")
+
+    def source_normalization(self) -> float:
+        return float(self._L.pumitally_get_source_normalization(self._h))
 
     def set_option(self, name: str, value: int):
         if self._L.pumitally_set_option(self._h, name.encode(), int(value)):

@@ -204,17 +204,18 @@ def test_chunked_upload_pipeline_equals_single_range(variant):
 
 
 @pytest.mark.parametrize("resample", [0.05, 0.9])
-def test_delta_upload_of_origins_is_exact(resample):
-    """Host-pointer path: origins equal to the previous call's destinations are not sent again
-    (the device still holds them); the changed ones travel as a patch list, or the whole slice when
-    most of a chunk changed.  Results must be identical to plain uploads, bytes must drop."""
+def test_staged_upload_of_origins_is_exact(resample):
+    """Host-pointer path, staged (the default): origins equal to the previous call's destinations are
+    not sent again (the device still holds them); the changed ones travel as a patch list, or the
+    whole slice when most of a chunk changed.  Results must be identical to direct uploads of all
+    four arrays (host_path=0), bytes must drop."""
     coords, t2v = kuhn_box(6, 6, 5)
     n = 40_000
     rng = np.random.default_rng(11)
     engs = []
-    for mode in (0, 2):
+    for mode in (0, 1):
         e = gpu_engine(8, chunk=8192)(coords, t2v, n)
-        e.set_option("delta_upload", mode)
+        e.set_option("host_path", mode)
         engs.append(e)
     orc = OraclePumiTally(coords, t2v, n)
     pos = rng.uniform(0.05, 4.95, size=(n, 3))
@@ -236,25 +237,25 @@ def test_delta_upload_of_origins_is_exact(resample):
     np.testing.assert_array_equal(on.elem_ids, off.elem_ids)
     np.testing.assert_array_equal(on.positions, off.positions)
     np.testing.assert_allclose(on.flux, off.flux, rtol=1e-12)
-    assert_flux_close(on.flux, orc.flux, "delta upload")
+    assert_flux_close(on.flux, orc.flux, "staged upload")
     np.testing.assert_array_equal(on.elem_ids, orc.elem_ids)
     assert on.stats()["h2d_bytes"] < (0.75 if resample < 0.4 else 1.01) * off.stats()["h2d_bytes"]
 
 
-def test_delta_upload_survives_interleaved_device_moves():
+def test_staged_upload_survives_interleaved_device_moves():
     import torch
 
     coords, t2v, wl = box_case((6, 6, 5), 20_000)
     a, b = gpu_engine(8)(coords, t2v, wl.n), gpu_engine(8)(coords, t2v, wl.n)
-    a.set_option("delta_upload", 2)
-    b.set_option("delta_upload", 0)
+    a.set_option("host_path", 1)
+    b.set_option("host_path", 0)
     init = wl.initial_positions().reshape(-1)
     for e in (a, b):
         e.CopyInitialPosition(init.copy())
     for step in range(5):
         o, d, f, w = wl.next_step()
         for e in (a, b):
-            if step == 2:  # a device-pointer move in between invalidates the host-side mirror
+            if step == 2:  # a device-pointer move in between: the particles move, the staging mirror does not
                 t = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (o, d, f, w)]
                 e.move_device(*(x.data_ptr() for x in t), torch.cuda.current_stream().cuda_stream)
                 torch.cuda.synchronize()
@@ -266,9 +267,10 @@ def test_delta_upload_survives_interleaved_device_moves():
 
 
 def test_pageable_buffers_with_host_registration():
-    """register_host=1: the caller's pageable numpy buffers are page-locked once and reused."""
+    """Direct path with register_host=1: the caller's pageable numpy buffers are page-locked once and reused."""
     coords, t2v, wl = box_case((6, 6, 5), 60_000)
     eng = gpu_engine(8)(coords, t2v, wl.n)
+    eng.set_option("host_path", 0)
     eng.set_option("register_host", 1)
     orc = OraclePumiTally(coords, t2v, wl.n)
     init = wl.initial_positions()
@@ -286,6 +288,74 @@ def test_pageable_buffers_with_host_registration():
         assert not F.any()
     assert_flux_close(eng.flux, orc.flux, "registered host buffers")
     np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_staged_path_reused_buffers_ragged_sizes_and_flag_values(threads):
+    """The staged host path with the caller reusing its four buffers (as OpenMC does), a particle
+    count that is not a multiple of anything, flying values other than 0/1 (only 1 flies,
+    PumiTallyImpl.cpp:95), unaligned array addresses and 1..8 staging workers."""
+    coords, t2v, wl = box_case((6, 6, 5), 50_003)
+    n = wl.n
+    e = PumiTally.from_arrays(coords, t2v, n)
+    e.set_option("host_threads", threads)
+    e.set_option("chunk", 4096)
+    orc = OraclePumiTally(coords, t2v, n)
+    init = wl.initial_positions()
+    e.CopyInitialPosition(init.reshape(-1).copy())
+    orc.CopyInitialPosition(init.reshape(-1).copy())
+    assert e.get_option("staged") == 1 and e.get_option("host_threads") == threads
+    # odd offsets: the caller's arrays are only 8-byte (flying: 1-byte) aligned
+    O, D, W = np.empty(3 * n + 1)[1:], np.empty(3 * n + 1)[1:], np.empty(n + 1)[1:]
+    F = np.empty(n + 3, dtype=np.int8)[3:]
+    rng = np.random.default_rng(5)
+    for step in range(4):
+        o, d, f, w = wl.next_step()
+        f = f.copy()
+        odd = rng.random(n) < 0.02
+        f[odd] = rng.choice(np.array([2, -1, 127, -128], dtype=np.int8), int(odd.sum()))
+        O[:], D[:], W[:], F[:] = o.reshape(-1), d.reshape(-1), w, f
+        f_ref = f.copy()
+        e.MoveToNextLocation(O, D, F, W)
+        orc.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f_ref, w.copy())
+        assert not F.any()
+        # (particles with odd flag values did not fly although the generator thinks they did: their
+        # next origin differs from where they are, which both sides handle by relocating them)
+        assert_flux_close(e.flux, orc.flux, f"staged step {step}")
+        np.testing.assert_array_equal(e.elem_ids, orc.elem_ids)
+    st = e.stats()
+    assert st["segments"] == orc.n_segments and st["lost"] == 0
+    # origins travelled only for re-sourced particles: well under the 57 B/particle of a direct upload
+    assert st["h2d_bytes"] < 24 * n + 4 * 0.75 * 57 * n
+
+
+def test_staged_path_every_origin_changed_and_none_changed():
+    """Patch-list overflow (every origin differs from the previous destination -> the slice travels
+    whole) and the opposite extreme (no origin changed -> no origin bytes at all)."""
+    coords, t2v = kuhn_box(6, 6, 5)
+    n = 30_000
+    rng = np.random.default_rng(3)
+    e = gpu_engine(8, chunk=4096)(coords, t2v, n)
+    orc = OraclePumiTally(coords, t2v, n)
+    pos = rng.uniform(0.05, 4.95, size=(n, 3))
+    for x in (e, orc):
+        x.CopyInitialPosition(pos.reshape(-1).copy())
+    sent = [e.stats()["h2d_bytes"]]
+    prev = pos
+    for step in range(4):
+        origin = prev.copy() if step % 2 == 0 else rng.uniform(0.05, 4.95, size=(n, 3))
+        dest = np.clip(origin + rng.normal(0, 0.8, size=(n, 3)), [0.011, 0.013, 0.017], [4.987, 4.983, 4.979])
+        fly, w = np.ones(n, dtype=np.int8), rng.uniform(0.5, 1.0, n)
+        for x in (e, orc):
+            x.MoveToNextLocation(origin.reshape(-1).copy(), dest.reshape(-1).copy(), fly.copy(), w.copy())
+        prev = dest
+        sent.append(e.stats()["h2d_bytes"])
+    per_move = np.diff(sent) / n
+    assert abs(per_move[0] - 33) < 0.01 and abs(per_move[2] - 33) < 0.01   # nothing changed: no origin bytes
+    assert abs(per_move[1] - 57) < 0.01 and abs(per_move[3] - 57) < 0.01   # everything changed: slices sent whole
+    assert_flux_close(e.flux, orc.flux, "overflow / no-change extremes")
+    np.testing.assert_array_equal(e.elem_ids, orc.elem_ids)
+    np.testing.assert_array_equal(e.positions, orc.positions)
 
 
 def test_error_behaviour():
@@ -446,7 +516,9 @@ def _two_gpu_worker(rank, world, port, q):
     for _ in range(3):
         o, d, f, w = wl.next_step()
         eng.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
-    eng.allreduce_tally()
+        # an exchange after every batch: each must give the sum over ranks of everything tallied so
+        # far, never counting an earlier exchange's result again
+        eng.allreduce_tally()
     if rank == 0:
         q.put(eng.flux)
     dist.barrier()
@@ -587,6 +659,66 @@ def test_config_c3_full_size_properties():
     """BASELINE.json configs[2]: 48,000 tets, 100 M particles (about 2,000 particles per tet and move
     hammering the same flux words)."""
     _full_size_properties("c3", -1, cross_check=0, steps=1)
+
+
+def _full_size_oracle_parity(cfg_name, n, steps=2, engine_opts=None):
+    """One BASELINE configuration at its full mesh size and `n` particles through the default engine
+    and through the per-particle oracle (both exit rules): parent elements exact after localisation
+    and after every move, flux 1e-6 element for element, positions, equal segment / track counts."""
+    import torch
+
+    cfg = CONFIGS[cfg_name]
+    cells = cfg["cells"]
+    coords, t2v = kuhn_box(*cells)
+    box = tuple(float(c) for c in cells)
+    wl = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], mu_min=cfg["mu_min"],
+                           backend="torch", device="cuda")
+    eng = PumiTally.from_arrays(coords, t2v, n)
+    for k, v in (engine_opts or {}).items():
+        eng.set_option(k, v)
+    orc = OraclePumiTally(coords, t2v, n, per_particle=True)
+    strict = OraclePumiTally(coords, t2v, n, per_particle=True, strict_exit=True)
+    init = wl.initial_positions().cpu().numpy()
+    for e in (eng, orc, strict):
+        e.CopyInitialPosition(init.reshape(-1).copy())
+    np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids, err_msg=f"{cfg_name}: parent elements after localisation")
+    np.testing.assert_array_equal(strict.elem_ids, orc.elem_ids)
+    for step in range(steps):
+        o, d, f, w = (x.cpu().numpy() for x in wl.next_step())
+        for e in (eng, orc, strict):
+            e.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy())
+        flux = orc.flux
+        assert_flux_close(eng.flux, flux, f"{cfg_name} full size, move {step}")
+        np.testing.assert_allclose(strict.flux, flux, rtol=1e-12)
+        np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids, err_msg=f"{cfg_name}: parent elements after move {step}")
+        np.testing.assert_array_equal(strict.elem_ids, orc.elem_ids)
+        np.testing.assert_allclose(eng.positions, orc.positions, rtol=0, atol=1e-10 * max(box))
+    st = eng.stats()
+    assert st["segments"] == orc.n_segments == strict.n_segments
+    assert st["tracks"] == orc.n_tracks and st["lost"] == 0 and orc.n_lost == 0
+    return eng, orc
+
+
+def test_config_c2_full_size_oracle_parity():
+    """BASELINE configs[1]: 998,250 tets, 10 M particles, element for element against the oracle."""
+    eng, _ = _full_size_oracle_parity("c2", CONFIGS["c2"]["particles"])
+    assert eng.get_option("variant") in (8, 24)
+
+
+def test_config_c4_full_size_oracle_parity():
+    """BASELINE configs[3]: 1 M collimated tracks of ~200 segments on the 1.0 M-tet pin-cell mesh."""
+    _full_size_oracle_parity("c4", CONFIGS["c4"]["particles"])
+
+
+def test_config_c5_per_gpu_share_full_size_oracle_parity():
+    """BASELINE configs[4], one GPU's share: 12.5 M particles on the 9.86 M-tet mesh (binned kernel)."""
+    eng, _ = _full_size_oracle_parity("c5", CONFIGS["c5"]["particles"] // CONFIGS["c5"]["gpus"])
+    assert eng.get_option("variant") == 16
+
+
+def test_config_c3_ten_million_particle_slice_oracle_parity():
+    """BASELINE configs[2] (contention: 48,000 tets), a 10 M-particle slice of its 100 M."""
+    _full_size_oracle_parity("c3", 10_000_000)
 
 
 @pytest.mark.parametrize("variant", [0, 8, 16] + _X)

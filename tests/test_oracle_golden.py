@@ -165,6 +165,29 @@ def test_oracle_modes_agree_and_count_segments():
     assert res[0][3] > res[0][4] > 0
 
 
+@pytest.mark.parametrize("name,coords,t2v,box", list(_meshes()), ids=lambda v: v if isinstance(v, str) else "")
+def test_exit_rule_with_and_without_parallel_face_tolerance_agree_on_generic_tracks(name, coords, t2v, box):
+    """The oracle's exit rule skips faces the segment is parallel to within 1e-12 (added together with
+    the same rule in the CUDA path, so behaviour on degenerate tracks is self-referential); the rule it
+    replaced takes every face with n.u > 0.  On generic tracks the two must give identical results,
+    bit for bit -- the reference known answers (axis-parallel tracks through the 6-tet cube) included."""
+    n = 20_000
+    res = []
+    for strict in (False, True):
+        wl = SyntheticWorkload(box=box, num_particles=n, mean_length=0.6 * min(box), seed=5)
+        o = OraclePumiTally(coords, t2v, n, strict_exit=strict)
+        o.CopyInitialPosition(wl.initial_positions().reshape(-1))
+        for _ in range(3):
+            a, b, f, w = wl.next_step()
+            o.MoveToNextLocation(a.reshape(-1), b.reshape(-1), f.copy(), w)
+        res.append((o.flux, o.elem_ids, o.positions, o.n_segments, o.n_lost))
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-12)  # same contributions, atomics in any order
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    np.testing.assert_array_equal(res[0][2], res[1][2])
+    assert res[0][3] == res[1][3] and res[0][4] == res[1][4] == 0
+    golden_scenario(lambda c, t, m: OraclePumiTally(c, t, m, strict_exit=True))
+
+
 def test_normalized_flux_is_flux_over_volume():
     coords, t2v = kuhn_box(2, 2, 2)
     o = OraclePumiTally(coords, t2v, 10)

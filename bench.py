@@ -10,6 +10,13 @@ Per-GPU work is fixed as N grows (weak scaling); every rank holds the whole
 mesh (full-buffer picpart) and its own particle stripe, and the per-rank
 tallies are summed once at batch end with ncclAllReduce inside the timed
 region.  One JSON line is printed by rank 0.
+
+`value` is device-resident throughput; `e2e` is the same metric through the
+reference-facing call on pageable host arrays (host->device copies inside the
+timed region).  At N = 2, 4, 8 the line also carries `extra` blocks for the
+multi-GPU configurations BASELINE.json names: `c4_x4` (1 M long tracks on 4
+GPUs), `c5_x8` (100 M particles on the 9.86 M-tet mesh, 8 GPUs) and
+`c5_strong_x2/4` (the same 100 M particles on fewer GPUs: strong scaling).
 """
 from __future__ import annotations
 
@@ -21,6 +28,7 @@ import sys
 import threading
 import time
 
+T_START = time.time()
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -54,9 +62,12 @@ def measured_peak():
 
 
 def recorded_traffic():
-    """DRAM bytes per launch of the walk kernel from the committed ncu capture, or None."""
+    """DRAM bytes per launch of the walk kernel from the committed ncu capture (not measured in this
+    run: dram__bytes needs ncu), with the capture it comes from; or None."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["dram_bytes_per_launch"]
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return {"dram_bytes_per_launch": t["dram_bytes_per_launch"],
+                "source": "profiles/traffic.json (%s)" % t.get("source", "ncu capture")}
     except Exception:
         return None
 
@@ -192,145 +203,166 @@ def run_reference(args, rank):
 
 # ------------------------------------------------------------------------- GPU arm
 
-def run_gpu(args, rank, local_rank, world):
-    import numpy as np
-    import torch
+class GpuArm:
+    """One rank of the CUDA arm: measures one configuration at a time (device-resident `value`,
+    end-to-end `e2e`) with every rank taking part; rank 0 assembles the JSON line."""
 
-    from pumiumtally_b200.tally import PumiTally
-    from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
+    def __init__(self, args, rank, local_rank, world):
+        import numpy as np
+        import torch
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the tally engine has no CPU path "
-                         "(use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    all_cpus = os.sched_getaffinity(0)
-    bound = None if args.no_bind else bind_to_gpu_node(torch, local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
-
-    cfg = CONFIGS[args.config]
-    cells = cfg["cells"]
-    # per-GPU particle count: the config's total divided by the GPU count it is quoted on
-    n = args.particles or cfg["particles"] // (cfg.get("gpus", 1) if world > 1 else 1)
-    if world == 1 and cfg.get("gpus", 1) > 1 and not args.particles:
-        n = cfg["particles"] // cfg["gpus"] if args.per_gpu_share else cfg["particles"]
-    box = tuple(float(c) for c in cells)
-    spec = f"box:{cells[0]},{cells[1]},{cells[2]}"
-    nsteps = args.warmup + args.steps
-
-    def new_engine():
-        e = PumiTally.from_spec(spec, n, device=local_rank)
-        e.set_option("variant", args.variant)  # -1 = the engine's own choice for this mesh
-        e.set_option("block", args.block)
-        for kv in args.opt:
-            k, v = kv.split("=")
-            e.set_option(k, int(v))
-        return e
-
-    # identical batches for both arms, generated on the device once
-    wl = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], mu_min=cfg["mu_min"],
-                           backend="torch", device=dev, id_offset=rank * n)
-    init = wl.initial_positions().contiguous()
-    bytes_per_step = n * 57
-    pregen = nsteps * bytes_per_step <= args.pregen_gb * (1 << 30)
-    # default (c2): all batches are generated up front and the K timed steps run back to back.
-    # Configs whose batches do not fit (100M particles) generate each batch just before its step,
-    # outside the timed region, and the per-step device times are summed.
-    batches = [tuple(x.contiguous() for x in wl.next_step()) for _ in range(nsteps)] if pregen else None
-    stream = torch.cuda.current_stream().cuda_stream
-
-    def batch(k):
-        return batches[k] if pregen else tuple(x.contiguous() for x in wl.next_step())
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- device-resident arm: `value` ------------------------------
-    eng = new_engine()
-    if world > 1:
-        from pumiumtally_b200.distributed import broadcast_unique_id
-
-        eng.comm_init(rank, world, broadcast_unique_id(dist, PumiTally.nccl_unique_id, device=dev))
-    eng.copy_initial_position_device(init.data_ptr(), stream)
-    for k in range(args.warmup):
-        o, d, f, w = batch(k)
-        eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
-    barrier()
-    st0 = eng.stats()
-    launches0 = eng.get_option("launches")
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    if pregen:
-        ev0.record()
-        for k in range(args.warmup, nsteps):
-            o, d, f, w = batches[k]
-            eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the tally engine has no CPU path "
+                             "(use --impl reference for the CPU arm)")
+        self.np, self.torch = np, torch
+        self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.all_cpus = os.sched_getaffinity(0)
+        self.bound = None if args.no_bind else bind_to_gpu_node(torch, local_rank)
+        self.dist = None
         if world > 1:
-            torch.cuda.current_stream().synchronize()
-            eng.allreduce_tally()  # batch-end exchange of the ghost tallies over NVLink
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1)
-    else:
-        ms = 0.0
-        for k in range(args.warmup, nsteps):
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.nccl_id = None
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return [float(x) for x in t]
+
+    def measure(self, cfg_name, n, steps, warmup, e2e=True, e2e_modes=False, clocks=False, scaling="weak"):
+        """Device-resident and end-to-end throughput of `cfg_name` with n particles on this rank."""
+        from pumiumtally_b200.tally import PumiTally
+        from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
+
+        np, torch, args, rank, world, dev = self.np, self.torch, self.args, self.rank, self.world, self.dev
+        cfg = CONFIGS[cfg_name]
+        cells = cfg["cells"]
+        box = tuple(float(c) for c in cells)
+        spec = f"box:{cells[0]},{cells[1]},{cells[2]}"
+        nsteps = warmup + steps
+
+        def new_engine():
+            e = PumiTally.from_spec(spec, n, device=self.local_rank)
+            e.set_option("variant", args.variant)  # -1 = the engine's own choice for this mesh
+            e.set_option("block", args.block)
+            for kv in args.opt:
+                k, v = kv.split("=")
+                e.set_option(k, int(v))
+            return e
+
+        def new_workload():
+            w = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], mu_min=cfg["mu_min"],
+                                  backend="torch", device=dev, id_offset=rank * n)
+            return w, w.initial_positions().contiguous()
+
+        # identical batches for both arms, generated on the device
+        wl, init = new_workload()
+        bytes_per_step = n * 57
+        pregen = nsteps * bytes_per_step <= args.pregen_gb * (1 << 30)
+        # default (c2): all batches are generated up front and the K timed steps run back to back.
+        # Configs whose batches do not fit (100M particles) generate each batch just before its step,
+        # outside the timed region, and the per-step device times are summed.
+        batches = [tuple(x.contiguous() for x in wl.next_step()) for _ in range(nsteps)] if pregen else None
+        stream = torch.cuda.current_stream().cuda_stream
+        state = {"wl": wl}
+
+        def batch(k):
+            return batches[k] if pregen else tuple(x.contiguous() for x in state["wl"].next_step())
+
+        # ---------------- device-resident arm: `value` ------------------------------
+        eng = new_engine()
+        if world > 1:
+            from pumiumtally_b200.distributed import broadcast_unique_id
+
+            eng.comm_init(rank, world, broadcast_unique_id(self.dist, PumiTally.nccl_unique_id, device=dev))
+        eng.copy_initial_position_device(init.data_ptr(), stream)
+        for k in range(warmup):
             o, d, f, w = batch(k)
-            barrier()
-            ev0.record()
             eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
-            if world > 1 and k == nsteps - 1:
+        self.barrier()
+        st0 = eng.stats()
+        launches0 = eng.get_option("launches")
+        sampler = ClockSampler(self.local_rank) if (clocks and rank == 0) else None
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        if pregen:
+            ev0.record()
+            for k in range(warmup, nsteps):
+                o, d, f, w = batches[k]
+                eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
+            if world > 1:
                 torch.cuda.current_stream().synchronize()
-                eng.allreduce_tally()
+                eng.allreduce_tally()  # batch-end exchange of the ghost tallies over NVLink
             ev1.record()
-            torch.cuda.synchronize()
-            ms += ev0.elapsed_time(ev1)
-            del o, d, f, w
-        barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    st1 = eng.stats()
-    segs = st1["segments"] - st0["segments"]
-    tracks = st1["tracks"] - st0["tracks"]
-    kernel_ms = st1["kernel_ms"] - st0["kernel_ms"]
-    lost = st1["lost"]
-    t_all = torch.tensor([ms], dtype=torch.float64, device=dev)
-    s_all = torch.tensor([float(segs), float(tracks)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-        dist.all_reduce(s_all, op=dist.ReduceOp.SUM)
-    ms_max = float(t_all[0])
-    total_segs, total_tracks = float(s_all[0]), float(s_all[1])
-    value = total_segs / (ms_max * 1e-3)
-    flux_sum = float(eng.flux.sum())
-    variant_used = eng.get_option("variant")
-    gpu_launches = eng.get_option("launches") - launches0  # kernels the engine launched in the timed region
-    del eng
+            self.barrier()
+            ms = ev0.elapsed_time(ev1)
+        else:
+            ms = 0.0
+            for k in range(warmup, nsteps):
+                o, d, f, w = batch(k)
+                self.barrier()
+                ev0.record()
+                eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
+                if world > 1 and k == nsteps - 1:
+                    torch.cuda.current_stream().synchronize()
+                    eng.allreduce_tally()
+                ev1.record()
+                torch.cuda.synchronize()
+                ms += ev0.elapsed_time(ev1)
+                del o, d, f, w
+            self.barrier()
+        clocks_out = sampler.stop() if sampler else None
+        st1 = eng.stats()
+        segs, tracks = st1["segments"] - st0["segments"], st1["tracks"] - st0["tracks"]
+        kernel_ms = st1["kernel_ms"] - st0["kernel_ms"]
+        ms_max = self.reduce([ms], "MAX")[0]
+        total_segs, total_tracks = self.reduce([float(segs), float(tracks)], "SUM")
+        out = {
+            "config": cfg_name, "particles_per_gpu": n, "n_gpus": world, "scaling": scaling, "steps": steps,
+            "value": total_segs / (ms_max * 1e-3), "ms_per_step": ms_max / steps,
+            "segments_per_track": total_segs / max(total_tracks, 1.0), "lost": int(st1["lost"]),
+            "relocation_crossings_per_step": (st1["relocations"] - st0["relocations"]) / max(steps, 1),
+            "flux_sum": float(eng.flux.sum()), "variant": eng.get_option("variant"),
+            "gpu_launches": eng.get_option("launches") - launches0,  # kernels the engine launched in the timed region
+            "allreduce_ms": (eng.get_option("allreduce_us") / 1e3) if world > 1 else None,
+            "allreduce_bytes": 8 * eng.num_elements if world > 1 else None,
+            "pregen": pregen, "clocks": clocks_out, "bytes_per_step": bytes_per_step,
+        }
+        peak, peak_src = measured_peak()
+        alg_bytes = BYTES_PER_SEGMENT * segs + BYTES_PER_TRACK * tracks  # this rank, whole timed region
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+        out["roofline"] = {
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": (achieved / peak) if achieved else None,
+            "kernel": "walk kernel (variant %d%s), %d launches, %.3f ms each" % (
+                out["variant"], " incl. binning pass" if out["variant"] in (15, 16, 17, 21, 24, 25, 26) else "", steps,
+                kernel_ms / max(steps, 1)),
+            "algorithmic_bytes_per_launch": alg_bytes / max(steps, 1), "peak_source": peak_src}
+        del eng
 
-    # ---------------- end-to-end arm through the host-pointer C ABI: `e2e` ------
-    # Headline: the call a user of the reference makes (PumiTally.h:87-89) on ordinary pageable host
-    # arrays that the caller reuses for every move, as OpenMC does with its std::vectors, with the
-    # engine's default settings.  Side numbers: the same from pinned buffers, and the direct path
-    # (host_path=0) from pageable memory with and without cudaHostRegister.
-    e2e = None
-    if not args.no_e2e:
-        def replay():
-            w2 = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], mu_min=cfg["mu_min"],
-                                   backend="torch", device=dev, id_offset=rank * n)
-            return w2, w2.initial_positions().contiguous()
-
-        def run_e2e(kind, opts, steps, warmup):
-            """kind: 'pageable' | 'pinned' caller buffers; returns (segments, seconds, h2d bytes per step)."""
-            nonlocal wl, init
+        # ---------------- end-to-end arm through the host-pointer C ABI: `e2e` ------
+        # Headline: the call a user of the reference makes (PumiTally.h:87-89) on ordinary pageable host
+        # arrays that the caller reuses for every move, as OpenMC does with its std::vectors, with the
+        # engine's default settings.  Side numbers: the same from pinned buffers, and the direct path
+        # (host_path=0) from pageable memory with and without cudaHostRegister.
+        def run_e2e(kind, opts, ksteps, kwarm):
+            """kind: 'pageable' | 'pinned' caller buffers."""
             if not pregen:  # replay the same counter-based stream from the start
-                wl, init = replay()
+                state["wl"], init2 = new_workload()
+            else:
+                init2 = init
             if kind == "pinned":
                 bufs = [torch.empty(s_, dtype=d_, pin_memory=True).numpy() for s_, d_ in
                         ((3 * n, torch.float64), (3 * n, torch.float64), (n, torch.int8), (n, torch.float64))]
@@ -340,116 +372,150 @@ def run_gpu(args, rank, local_rank, world):
             eng2 = new_engine()
             for k_, v_ in opts.items():
                 eng2.set_option(k_, v_)
-            eng2.CopyInitialPosition(init.cpu().numpy().reshape(-1))
+            eng2.CopyInitialPosition(init2.cpu().numpy().reshape(-1))
 
             def fill(k):  # untimed: the transport code producing its next batch in its own arrays
                 o, d, f, w = batch(k)
                 for dst, src in zip((O, D, F, W), (o, d, f, w)):
                     dst[:] = src.reshape(-1).cpu().numpy()
 
-            for k in range(warmup):
+            for k in range(kwarm):
                 fill(k)
                 eng2.MoveToNextLocation(O, D, F, W)
                 eng2.stats()
-            barrier()
+            self.barrier()
             st_a = eng2.stats()
-            dt = 0.0
-            for k in range(warmup, warmup + steps):
+            dt, ret = 0.0, 0.0
+            for k in range(kwarm, kwarm + ksteps):
                 fill(k)
                 t0 = time.perf_counter()
                 eng2.MoveToNextLocation(O, D, F, W)
+                t1 = time.perf_counter()
                 st_b = eng2.stats()  # device->host read of the step's result (synchronises)
                 dt += time.perf_counter() - t0
-            e_t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            e_s = torch.tensor([float(st_b["segments"] - st_a["segments"])], dtype=torch.float64, device=dev)
-            if dist is not None:
-                dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
-                dist.all_reduce(e_s, op=dist.ReduceOp.SUM)
-            h2d = (st_b["h2d_bytes"] - st_a["h2d_bytes"]) / steps
-            threads = eng2.get_option("host_threads")
+                ret += t1 - t0
+            secs = self.reduce([dt], "MAX")[0]
+            sg = self.reduce([float(st_b["segments"] - st_a["segments"])], "SUM")[0]
+            res = {"value": sg / secs, "ms_per_step": 1e3 * secs / ksteps,
+                   "h2d_bytes_per_step": int((st_b["h2d_bytes"] - st_a["h2d_bytes"]) / ksteps),
+                   "call_return_ms": 1e3 * ret / ksteps, "host_threads": eng2.get_option("host_threads")}
             del eng2
-            return float(e_s[0]), float(e_t[0]), h2d, threads
+            return res
 
-        segs_e, secs_e, h2d_e, threads_e = run_e2e("pageable", {}, args.steps, args.warmup)
-        e2e = {"value": segs_e / secs_e, "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d_e), "d2h_bytes_per_step": 56,
-               "ms_per_step": 1e3 * secs_e / args.steps,
-               "caller_buffers": "pageable numpy arrays, reused for every move",
-               "host_threads": threads_e,
-               "note": "MoveToNextLocation(host pointers) with default options + per-step stats read-back; "
-                       "staged path: pinned per-particle slots refilled by the engine's worker pool, "
-                       "only changed origins travel"}
-        if not args.no_e2e_modes:
-            ks, kw = min(args.steps, 5), min(args.warmup, 2)
-            modes = {}
-            for name, kind, opts in (("pinned_buffers", "pinned", {}),
-                                     ("direct_registered", "pageable", {"host_path": 0, "register_host": 1}),
-                                     ("direct_pageable", "pageable", {"host_path": 0})):
-                if pregen is False and name != "pinned_buffers":
-                    continue
-                sg, sc, hb, _ = run_e2e(kind, opts, ks, kw)
-                modes[name] = {"value": sg / sc, "ms_per_step": 1e3 * sc / ks, "h2d_bytes_per_step": int(hb)}
-            e2e["other_modes"] = modes
+        if e2e:
+            r = run_e2e("pageable", {}, steps, warmup)
+            out["e2e"] = {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                          "d2h_bytes_per_step": 56, "ms_per_step": r["ms_per_step"],
+                          "call_return_ms": r["call_return_ms"],
+                          "caller_buffers": "pageable numpy arrays, reused for every move",
+                          "host_threads": r["host_threads"],
+                          "note": "MoveToNextLocation(host pointers) with default options + per-step stats read-back; "
+                                  "staged path: pinned per-particle slots refilled by the engine's worker pool, "
+                                  "only changed origins travel"}
+            if e2e_modes and pregen:
+                ks, kw = min(steps, 5), min(warmup, 2)
+                out["e2e"]["other_modes"] = {
+                    name: {k: v for k, v in run_e2e(kind, opts, ks, kw).items() if k != "host_threads"}
+                    for name, kind, opts in (("pinned_buffers", "pinned", {}),
+                                             ("direct_registered", "pageable", {"host_path": 0, "register_host": 1}),
+                                             ("direct_pageable", "pageable", {"host_path": 0}))}
+        return out
 
-    # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        os.sched_setaffinity(0, all_cpus)  # the CPU arm gets every core of the box
+    def cpu_baseline(self, cfg_name, n, nsteps):
+        """The oracle (OpenMP) beside it on a bounded sample (rank 0, N=1 only)."""
         from oracle.oracle import OraclePumiTally, num_threads
         from pumiumtally_b200.mesh import kuhn_box
+        from pumiumtally_b200.workload import CONFIGS, SyntheticWorkload
 
+        args = self.args
+        os.sched_setaffinity(0, self.all_cpus)  # the CPU arm gets every core of the box
+        cfg = CONFIGS[cfg_name]
+        cells = cfg["cells"]
         ns = min(args.cpu_sample, n)
         coords, t2v = kuhn_box(*cells)
         orc = OraclePumiTally(coords, t2v, ns, per_particle=True)
         # counter-based generator: the numpy stream of ids [0, ns) is the GPU batch's first ns particles
-        wl_cpu = SyntheticWorkload(box=box, num_particles=ns, mean_length=cfg["mean_length"], mu_min=cfg["mu_min"])
+        wl_cpu = SyntheticWorkload(box=tuple(float(c) for c in cells), num_particles=ns,
+                                   mean_length=cfg["mean_length"], mu_min=cfg["mu_min"])
         orc.CopyInitialPosition(wl_cpu.initial_positions().reshape(-1))
         cpu_steps = min(args.cpu_steps, nsteps)
-        s0, t_cpu = 0, 0.0
-        for k in range(cpu_steps):
+        t_cpu = 0.0
+        for _ in range(cpu_steps):
             o, d, f, w = wl_cpu.next_step()
             t0 = time.perf_counter()
             orc.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
             t_cpu += time.perf_counter() - t0
-        cpu = {"value": orc.n_segments / t_cpu, "unit": UNIT, "cores": num_threads(), "kind": "port",
-               "sample": f"first {ns} particles of the first {cpu_steps} batches ({orc.n_segments} segments, "
-                         f"{t_cpu:.1f} s) on the full mesh; reference-algorithm restatement, OpenMP"}
+        return {"value": orc.n_segments / t_cpu, "unit": UNIT, "cores": num_threads(), "kind": "port",
+                "sample": f"first {ns} particles of the first {cpu_steps} batches ({orc.n_segments} segments, "
+                          f"{t_cpu:.1f} s) on the full mesh; reference-algorithm restatement, OpenMP"}
 
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+
+def run_gpu(args, rank, local_rank, world):
+    from pumiumtally_b200.workload import CONFIGS
+
+    arm = GpuArm(args, rank, local_rank, world)
+    cfg = CONFIGS[args.config]
+    # per-GPU particle count: the config's total divided by the GPU count it is quoted on
+    n = args.particles or cfg["particles"] // (cfg.get("gpus", 1) if world > 1 else 1)
+    if world == 1 and cfg.get("gpus", 1) > 1 and not args.particles:
+        n = cfg["particles"] // cfg["gpus"] if args.per_gpu_share else cfg["particles"]
+    main = arm.measure(args.config, n, args.steps, args.warmup, e2e=not args.no_e2e,
+                       e2e_modes=not args.no_e2e_modes and world == 1, clocks=True)
+
+    # ---- the multi-GPU configurations BASELINE.json names, measured beside the headline ----------
+    # c4 on 4 GPUs (1 M particles / 4), c5 on 8 GPUs (100 M particles / 8), and c5 strong scaling
+    # (100 M particles / N on the 9.86 M-tet mesh) at every N > 1.
+    extra = {}
+    over_budget = arm.reduce([time.time() - T_START], "MAX")[0] > args.extra_after_s
+    if over_budget:
+        extra["skipped"] = f"headline run took more than {args.extra_after_s} s; extras skipped to stay inside the driver's limit"
+    if not args.no_extra and args.config == "c2" and not args.particles and not over_budget:
+        ks, kw = min(args.steps, 10), min(args.warmup, 3)
+        if world == 4:
+            extra["c4_x4"] = arm.measure("c4", CONFIGS["c4"]["particles"] // 4, ks, kw)
+        if world in (2, 4, 8):
+            tag = "c5_x8" if world == 8 else f"c5_strong_x{world}"
+            extra[tag] = arm.measure("c5", CONFIGS["c5"]["particles"] // world, ks, kw, scaling="strong")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = arm.cpu_baseline(args.config, n, args.warmup + args.steps)
+    if arm.dist is not None:
+        arm.dist.barrier()
+        arm.dist.destroy_process_group()
     if rank != 0:
         return
-    peak, peak_src = measured_peak()
-    alg_bytes = BYTES_PER_SEGMENT * segs + BYTES_PER_TRACK * tracks  # this rank, whole timed region
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    traffic = recorded_traffic() if (args.config == "c2" and not args.particles) else None
+    roof = dict(main["roofline"])
+    roof["traffic"] = traffic["dram_bytes_per_launch"] if traffic else None
+    roof["traffic_source"] = traffic["source"] if traffic else None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_description(args.config, cfg, n), "variant": variant_used,
-                   "block": args.block, "cpu_binding": (f"{len(bound)} CPUs local to the GPU" if bound else "none"),
-                   "l2": f"inputs larger than L2 ({bytes_per_step / 1e6:.0f} MB of fresh particle data per step)",
-                   "timing": "K steps back to back between two CUDA events" if pregen else
+        "config": {"workload": workload_description(args.config, cfg, n), "variant": main["variant"],
+                   "block": args.block, "cpu_binding": (f"{len(arm.bound)} CPUs local to the GPU" if arm.bound else "none"),
+                   "l2": f"inputs larger than L2 ({main['bytes_per_step'] / 1e6:.0f} MB of fresh particle data per step)",
+                   "timing": "K steps back to back between two CUDA events" if main["pregen"] else
                              "per-step CUDA-event times summed (batches generated between steps, untimed)",
                    "parallelism": f"particle stripes x{world}, full-buffer picparts, 1 ncclAllReduce(flux) per batch",
-                   "segments_per_track": total_segs / max(total_tracks, 1.0), "lost": int(lost),
-                   "relocation_crossings_per_step": (st1["relocations"] - st0["relocations"]) / max(args.steps, 1),
-                   "flux_sum": flux_sum},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None,
-                     "traffic": recorded_traffic() if (args.config == "c2" and not args.particles) else None,
-                     "kernel": "walk kernel (variant %d%s), %d launches, %.3f ms each" % (
-                         variant_used, " incl. binning pass" if variant_used in (15, 16, 17, 21, 24, 25, 26) else "", args.steps,
-                         kernel_ms / max(args.steps, 1)),
-                     "algorithmic_bytes_per_launch": alg_bytes / max(args.steps, 1), "peak_source": peak_src},
+                   "segments_per_track": main["segments_per_track"], "lost": main["lost"],
+                   "relocation_crossings_per_step": main["relocation_crossings_per_step"],
+                   "flux_sum": main["flux_sum"], "allreduce_ms": main["allreduce_ms"],
+                   "allreduce_bytes": main["allreduce_bytes"]},
+        "roofline": roof,
         "cpu_baseline": cpu,
-        "e2e": e2e,
+        "e2e": main.get("e2e"),
         # kernels of this repo inside the timed region: one fused walk kernel per move, plus the five
         # binning kernels (count, 3-kernel scan, scatter) when the binned variant is in use
-        "gpu_launches": gpu_launches,
-        "clocks": clocks,
+        "gpu_launches": main["gpu_launches"],
+        "clocks": main["clocks"],
     }
+    if extra:
+        for blk in extra.values():
+            blk.pop("clocks", None)
+            blk.pop("pregen", None)
+        line["extra"] = extra
     print(json.dumps(line), flush=True)
 
 
@@ -474,6 +540,10 @@ def main():
     ap.add_argument("--no-e2e-modes", action="store_true", help="skip the e2e side numbers (pinned / direct paths)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node")
+    ap.add_argument("--extra-after-s", type=float, default=360.0,
+                    help="skip the extra blocks when the headline measurement has already taken this long")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="N>1: skip the extra blocks (c4 on 4 GPUs, c5 on 8 GPUs, c5 strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

@@ -28,7 +28,9 @@ __device__ __forceinline__ int32_t cell_of(const SeedGrid &g, double x, double y
 }
 
 // pass 1: cell of every flying particle of [begin,end) + histogram
-__global__ void bin_count_kernel(SeedGrid g, const double *__restrict__ origin,
+// origin == nullptr: every particle starts this move where it is (the host path that patches
+// re-sourced particles beforehand); the key is then the stored position
+__global__ void bin_count_kernel(SeedGrid g, const double *__restrict__ origin, const ParticleState *__restrict__ state,
                                  const int8_t *__restrict__ flying, int32_t begin, int32_t end,
                                  int32_t *__restrict__ pcell, unsigned int *__restrict__ count) {
   const int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,7 +38,12 @@ __global__ void bin_count_kernel(SeedGrid g, const double *__restrict__ origin,
   const bool fly = flying ? (flying[i] == 1) : true;
   int32_t c = -1;
   if (fly) {
-    c = cell_of(g, origin[3 * (size_t)i], origin[3 * (size_t)i + 1], origin[3 * (size_t)i + 2]);
+    if (origin) {
+      c = cell_of(g, origin[3 * (size_t)i], origin[3 * (size_t)i + 1], origin[3 * (size_t)i + 2]);
+    } else {
+      const ParticleState s = load_state(state + i);
+      c = cell_of(g, s.x, s.y, s.z);
+    }
     atomicAdd(count + c, 1u);
   }
   pcell[i] = c;
@@ -122,7 +129,8 @@ __global__ void bin_pack_kernel(const int32_t *__restrict__ pcell, int32_t begin
   const int32_t c = pcell[i];
   if (c < 0) return;
   const ParticleState s = load_state(state + i);
-  const double ox = origin[3 * (size_t)i], oy = origin[3 * (size_t)i + 1], oz = origin[3 * (size_t)i + 2];
+  const double ox = origin ? origin[3 * (size_t)i] : s.x, oy = origin ? origin[3 * (size_t)i + 1] : s.y,
+               oz = origin ? origin[3 * (size_t)i + 2] : s.z;
   const double dx = dest[3 * (size_t)i], dy = dest[3 * (size_t)i + 1], dz = dest[3 * (size_t)i + 2];
   const double w = weights[i];
   const bool moved = ox != s.x || oy != s.y || oz != s.z;  // same test as begin_particle()
@@ -150,7 +158,7 @@ cudaError_t launch_bin_pack_particles(const SeedGrid &g, const double *origin, c
   if (n <= 0) return cudaMemsetAsync(work_count, 0, sizeof(unsigned int), stream);
   cudaError_t e = cudaMemsetAsync(count, 0, size_t(ncell) * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
-  bin_count_kernel<<<(n + 255) / 256, 256, 0, stream>>>(g, origin, flying, begin, end, pcell, count);
+  bin_count_kernel<<<(n + 255) / 256, 256, 0, stream>>>(g, origin, state, flying, begin, end, pcell, count);
   const int nb = (ncell + kScanBlock - 1) / kScanBlock;
   scan_block_kernel<<<nb, 256, 0, stream>>>(count, sums, ncell);
   scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, nb, work_count);
@@ -161,8 +169,8 @@ cudaError_t launch_bin_pack_particles(const SeedGrid &g, const double *origin, c
 
 // count: [ncell] scratch (zeroed here), sums: [ceil(ncell/1024)] scratch, order: [end-begin]
 // compact output, work_count: device scalar receiving the number of flying particles.
-cudaError_t launch_bin_particles(const SeedGrid &g, const double *origin, const int8_t *flying,
-                                 int32_t begin, int32_t end, int32_t *pcell, unsigned int *count,
+cudaError_t launch_bin_particles(const SeedGrid &g, const double *origin, const ParticleState *state,
+                                 const int8_t *flying, int32_t begin, int32_t end, int32_t *pcell, unsigned int *count,
                                  unsigned int *sums, int32_t *order, unsigned int *work_count,
                                  cudaStream_t stream) {
   const int32_t ncell = g.nx * g.ny * g.nz;
@@ -170,7 +178,7 @@ cudaError_t launch_bin_particles(const SeedGrid &g, const double *origin, const 
   if (n <= 0) return cudaMemsetAsync(work_count, 0, sizeof(unsigned int), stream);
   cudaError_t e = cudaMemsetAsync(count, 0, size_t(ncell) * sizeof(unsigned int), stream);
   if (e != cudaSuccess) return e;
-  bin_count_kernel<<<(n + 255) / 256, 256, 0, stream>>>(g, origin, flying, begin, end, pcell, count);
+  bin_count_kernel<<<(n + 255) / 256, 256, 0, stream>>>(g, origin, state, flying, begin, end, pcell, count);
   const int nb = (ncell + kScanBlock - 1) / kScanBlock;
   scan_block_kernel<<<nb, 256, 0, stream>>>(count, sums, ncell);
   scan_sums_kernel<<<1, 1024, 0, stream>>>(sums, nb, work_count);

@@ -127,6 +127,8 @@ Engine::~Engine() {
   cudaDeviceSynchronize();
   if (nccl_comm_) nccl_comm_destroy(nccl_comm_);
   cudaFree(d_flux_global_);
+  if (ev_copy0_) cudaEventDestroy(ev_copy0_);
+  if (ev_copy1_) cudaEventDestroy(ev_copy1_);
   if (ev_ar0_) cudaEventDestroy(ev_ar0_);
   if (ev_ar1_) cudaEventDestroy(ev_ar1_);
   for (auto &r : registered_) cudaHostUnregister(const_cast<void *>(r.first));
@@ -134,6 +136,10 @@ Engine::~Engine() {
   for (auto &t : timers_busy_) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (auto &e : chunk_events_) cudaEventDestroy(e);
   stager_.reset();
+  if (h_pos_) { cudaHostUnregister(h_pos_); free(h_pos_); }
+  if (d2h_) cudaStreamDestroy(d2h_);
+  for (auto &e : pos_events_) cudaEventDestroy(e);
+  for (auto &e : walk_events_) cudaEventDestroy(e);
   if (stage_base_) {
     if (stage_registered_) { cudaHostUnregister(stage_base_); free(stage_base_); }
     else cudaFreeHost(stage_base_);
@@ -180,6 +186,7 @@ void Engine::build_seed_grid() {
   p.bulk_ok = 1;
   p.work_counter = d_tickets_;
   p.stats = d_stats_;
+  p.cx = mesh_.center[0]; p.cy = mesh_.center[1]; p.cz = mesh_.center[2];
   cuda_or_throw(launch_walk(p, kVariantPersistRefill8, 128, compute_), "seed walk");
   cuda_or_throw(launch_seed_finalize(xyz, ts, d_grid_, ncell, compute_), "seed finalize");
   cuda_or_throw(cudaStreamSynchronize(compute_), "seed sync");
@@ -253,6 +260,25 @@ void Engine::begin_move() {
   }
 }
 
+// Re-sourced particles of the pinned-caller host path: phase 1 for the listed particles only.
+int Engine::relocate_patches(const PatchEntry *d_list, int32_t count, cudaStream_t stream) {
+  if (count <= 0) return 0;
+  WalkParams p{};
+  p.tets = d_tets_;
+  p.flux = d_flux_;
+  p.state = d_state_;
+  p.begin = 0;
+  p.end = n_;
+  p.max_iters = max_iters_ > 0 ? max_iters_ : int32_t(std::min<int64_t>(mesh_.ntets + 16, INT_MAX));
+  p.stats = d_stats_;
+  p.grid = grid_;
+  p.cx = mesh_.center[0]; p.cy = mesh_.center[1]; p.cz = mesh_.center[2];
+  if (!use_seed_grid_) p.grid.cell_tet = nullptr;
+  PTB_CUDA_OK(launch_relocate_patches(p, d_list, count, d_flying_, stream));
+  ++launches_;
+  return 0;
+}
+
 int Engine::launch_range(const double *d_origin, const double *d_dest, const int8_t *d_flying,
                          const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream,
                          bool timed) {
@@ -276,6 +302,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   p.max_iters = max_iters_ > 0 ? max_iters_ : int32_t(std::min<int64_t>(mesh_.ntets + 16, INT_MAX));
   p.stats = d_stats_;
   p.grid = grid_;
+  p.cx = mesh_.center[0]; p.cy = mesh_.center[1]; p.cz = mesh_.center[2];
   if (!use_seed_grid_) p.grid.cell_tet = nullptr;
   p.work_counter = d_tickets_ + (ticket_next_++ % kTicketRing);
   auto aligned16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
@@ -297,7 +324,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   }
   int variant = move_variant_;
   const bool packed = variant == kVariantPacked || variant == kVariantPackedL1 || variant == kVariantPackedL1Occ6;
-  if (packed && !(d_origin && d_dest && d_weights)) variant = kVariantPersistRefill8;  // localisation
+  if (packed && !(d_dest && d_weights)) variant = kVariantPersistRefill8;  // localisation
   bool use_packed = packed && variant == move_variant_;
   if (use_packed && !d_rows_ &&
       cudaMalloc(reinterpret_cast<void **>(&d_rows_), std::max<size_t>(size_t(n_), 1) * sizeof(PackedRow)) != cudaSuccess) {
@@ -329,11 +356,11 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
       variant == kVariantPersistGatherPlain || variant == kVariantEdgeGather) {
     // counting sort of the range's flying particles by seed-grid cell of their origin
     unsigned int *wc = d_work_count_ + (ticket_next_ % kTicketRing);
-    const double *key = d_origin ? d_origin : d_dest;
+    const double *key = d_origin;  // no origin array (pinned-caller host path): the stored position
     SeedGrid bin_grid = grid_;
     if (!morton_) bin_grid.cell_rank = nullptr;
     p.claim_run = claim_run_;
-    PTB_CUDA_OK(launch_bin_particles(bin_grid, key, d_flying, begin, end, d_pcell_, d_cell_count_,
+    PTB_CUDA_OK(launch_bin_particles(bin_grid, key, d_state_, d_flying, begin, end, d_pcell_, d_cell_count_,
                                      d_cell_sums_, d_order_ + begin, wc, stream));
     p.order = d_order_ + begin;
     p.work_count = wc;
@@ -558,6 +585,18 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
                       ensure_patch_buffers(nchunks) == 0;
   if (!staged) return move_direct(origin, dest, flying, weights, nchunks);
   follow_caller_memory(dest, size_t(size) * sizeof(double));
+  if (register_host_) {  // opt-in: page-lock the caller's arrays the first time they are seen
+    maybe_register(origin, 3 * size_t(n_) * sizeof(double));
+    maybe_register(dest, 3 * size_t(n_) * sizeof(double));
+    maybe_register(weights, size_t(n_) * sizeof(double));
+  }
+  // Caller arrays that are page-locked (by the caller, or just above) need no copy into the staging
+  // slots: dest and weights go to the device straight from them, and the origins are compared with
+  // the device's own particle positions, which each move sends back (move_pinned).
+  if (pinned_path_ && host_is_pinned(origin) && host_is_pinned(dest) && host_is_pinned(weights) &&
+      ensure_position_mirror(nchunks) == 0)
+    return move_pinned(origin, dest, flying, weights, nchunks);
+  pos_mirror_valid_ = false;  // the move below does not send positions back
 
   // a chunk's staging slots may be refilled once the previous move's copies out of them are done;
   // with an unchanged chunking that is chunk_events_[k], otherwise wait for the whole copy stream
@@ -567,6 +606,7 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
   }
   const bool compare = mirror_valid_;
   mirror_valid_ = false;  // until this move has gone through completely
+  stager_->set_buffers(h_dest_, h_w_, h_fly_);
   cudaEvent_t ev_prev_done = chunk_events_[nchunks];
   // the device staging arrays are free once the previous move's kernels have finished
   PTB_CUDA_OK(cudaEventRecord(ev_prev_done, compute_));
@@ -590,6 +630,11 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
     stager_->begin(origin, dest, flying, weights, b, e, compare, h_patch_ + size_t(k % kPatchSlots) * patch_cap_);
     return 0;
   };
+  if (!ev_copy0_) {
+    PTB_CUDA_OK(cudaEventCreate(&ev_copy0_));
+    PTB_CUDA_OK(cudaEventCreate(&ev_copy1_));
+  }
+  PTB_CUDA_OK(cudaEventRecord(ev_copy0_, copy_));
   if (nchunks > 0 && start_stage(0)) return 1;
   for (int k = 0; k < nchunks; ++k) {
     int32_t b, e;
@@ -619,6 +664,7 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
     }
     if (launch_range(d_origin_, d_dest_, d_flying_, d_weights_, b, e, compute_, true)) return 1;
   }
+  PTB_CUDA_OK(cudaEventRecord(ev_copy1_, copy_));
   // origin slices that went whole were read from the caller's own memory (asynchronously, if it is
   // pinned): they must be on the device before the caller gets its arrays back
   if (caller_memory_on_the_wire) PTB_CUDA_OK(cudaStreamSynchronize(copy_));
@@ -633,10 +679,151 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
   return 0;
 }
 
+// Pinned mirror of the particle positions as the device holds them (x,y,z per particle, the layout of
+// the caller's origin array), refreshed by every move of the pinned-caller path.
+int Engine::ensure_position_mirror(int nchunks) {
+  if (!h_pos_) {
+    const size_t bytes = (3 * std::max<size_t>(size_t(n_), 1) * sizeof(double) + 4095) & ~size_t(4095);
+    void *base = nullptr;
+    if (posix_memalign(&base, 4096, bytes) == 0) {
+      HostPool &pool = stager_->pool();
+      const int T = pool.size();
+      pool.run([&](int t) {
+        const size_t lo = (bytes * size_t(t) / size_t(T)) & ~size_t(4095);
+        const size_t hi = t == T - 1 ? bytes : (bytes * size_t(t + 1) / size_t(T)) & ~size_t(4095);
+        std::memset(static_cast<char *>(base) + lo, 0, hi - lo);
+      });
+      if (cudaHostRegister(base, bytes, cudaHostRegisterDefault) != cudaSuccess) {
+        cudaGetLastError();
+        free(base);
+        base = nullptr;
+      }
+    }
+    if (!base) {
+      pinned_path_ = false;  // no pinned memory for the mirror: the staged path serves pinned callers too
+      return 1;
+    }
+    h_pos_ = static_cast<double *>(base);
+    PTB_CUDA_OK(cudaStreamCreateWithFlags(&d2h_, cudaStreamNonBlocking));
+  }
+  while (int(pos_events_.size()) < nchunks) {
+    cudaEvent_t a, b;
+    PTB_CUDA_OK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    PTB_CUDA_OK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    pos_events_.push_back(a);
+    walk_events_.push_back(b);
+  }
+  return 0;
+}
+
+// Host-pointer move when the caller's origin / dest / weights arrays are page-locked.
+//
+// Nothing is copied on the host except flying[] (1 byte per particle, so that it can be zeroed at
+// once): dest and weights are DMA'd from the caller's arrays, chunk by chunk.  The origins are not
+// sent at all; the pool compares them with h_pos_, the device's own particle positions as of the end
+// of the previous move (exact bit patterns, hull clip points included), and only particles that fly
+// from somewhere else are listed.  On the device the listed particles are relocated first (phase 1,
+// tally off: relocate_patches), then the walk kernel runs with "origin == stored position" for every
+// particle, then the chunk's new positions are exported and sent back on the otherwise idle
+// device->host direction of the link.  Host memory traffic per particle: 24 B origin + 24 B mirror
+// read by the pool, 33 B read and 24 B written by the DMA engines -- half of the staged path's.
+int Engine::move_pinned(const double *origin, const double *dest, int8_t *flying, const double *weights,
+                        int nchunks) {
+  mirror_valid_ = false;  // the staged path's mirror does not see this move
+  if (!ev_copy0_) {
+    PTB_CUDA_OK(cudaEventCreate(&ev_copy0_));
+    PTB_CUDA_OK(cudaEventCreate(&ev_copy1_));
+  }
+  if (staged_chunk_ != chunk_ || staged_chunks_ != nchunks || !pos_mirror_valid_) {
+    PTB_CUDA_OK(cudaStreamSynchronize(copy_));
+    PTB_CUDA_OK(cudaStreamSynchronize(d2h_));
+    staged_chunks_ = 0;
+  }
+  if (!pos_mirror_valid_) {  // first move on this path, or moves in between that sent nothing back
+    PTB_CUDA_OK(launch_export_positions(d_state_, d_origin_, 0, n_, compute_));
+    PTB_CUDA_OK(cudaMemcpyAsync(h_pos_, d_origin_, 3 * size_t(n_) * sizeof(double), cudaMemcpyDeviceToHost, compute_));
+    PTB_CUDA_OK(cudaStreamSynchronize(compute_));
+    ++launches_;
+  }
+  pos_mirror_valid_ = false;  // until this move has gone through completely
+  stager_->set_buffers(nullptr, nullptr, h_fly_, h_pos_);
+  cudaEvent_t ev_prev_done = chunk_events_[nchunks];
+  PTB_CUDA_OK(cudaEventRecord(ev_prev_done, compute_));
+  PTB_CUDA_OK(cudaStreamWaitEvent(copy_, ev_prev_done, 0));
+  double sent = 0.0;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto range_of = [&](int k, int32_t &b, int32_t &e) {
+    b = int32_t(int64_t(k) * chunk_);
+    e = int32_t(std::min<int64_t>(n_, int64_t(b) + chunk_));
+  };
+  auto start_stage = [&](int k) -> int {
+    if (k < staged_chunks_) {
+      PTB_CUDA_OK(cudaEventSynchronize(chunk_events_[k]));  // previous move's upload of the chunk's flying slots
+      PTB_CUDA_OK(cudaEventSynchronize(pos_events_[k]));    // its positions are back
+    }
+    if (k >= kPatchSlots) PTB_CUDA_OK(cudaEventSynchronize(chunk_events_[k - kPatchSlots]));
+    int32_t b, e;
+    range_of(k, b, e);
+    stager_->begin(origin, dest, flying, weights, b, e, true, h_patch_ + size_t(k % kPatchSlots) * patch_cap_);
+    return 0;
+  };
+  PTB_CUDA_OK(cudaEventRecord(ev_copy0_, copy_));
+  if (nchunks > 0 && start_stage(0)) return 1;
+  for (int k = 0; k < nchunks; ++k) {
+    int32_t b, e;
+    range_of(k, b, e);
+    const size_t cnt = size_t(e - b);
+    const int64_t npatch = stager_->end();
+    if (k + 1 < nchunks && start_stage(k + 1)) return 1;
+    PatchEntry *hp = h_patch_ + size_t(k % kPatchSlots) * patch_cap_, *dp = d_patch_ + size_t(k) * patch_cap_;
+    PTB_CUDA_OK(cudaMemcpyAsync(d_flying_ + b, h_fly_ + b, cnt, cudaMemcpyHostToDevice, copy_));
+    if (npatch < 0) {  // most of the chunk was re-sourced: its origins travel whole, the kernel sorts them out
+      PTB_CUDA_OK(cudaStreamWaitEvent(copy_, walk_events_[k], 0));  // d_origin_ doubles as the export buffer
+      PTB_CUDA_OK(cudaMemcpyAsync(d_origin_ + 3 * size_t(b), origin + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+      sent += 24.0 * double(cnt);
+    } else if (npatch > 0) {
+      PTB_CUDA_OK(cudaMemcpyAsync(dp, hp, size_t(npatch) * sizeof(PatchEntry), cudaMemcpyHostToDevice, copy_));
+      sent += double(npatch) * sizeof(PatchEntry);
+    }
+    PTB_CUDA_OK(cudaMemcpyAsync(d_dest_ + 3 * size_t(b), dest + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+    PTB_CUDA_OK(cudaMemcpyAsync(d_weights_ + b, weights + b, cnt * sizeof(double), cudaMemcpyHostToDevice, copy_));
+    sent += 33.0 * double(cnt);
+    PTB_CUDA_OK(cudaEventRecord(chunk_events_[k], copy_));
+    PTB_CUDA_OK(cudaStreamWaitEvent(compute_, chunk_events_[k], 0));
+    // the export below reuses d_origin_: the previous move's device->host copy out of it must be done
+    PTB_CUDA_OK(cudaStreamWaitEvent(compute_, pos_events_[k], 0));
+    if (npatch > 0 && relocate_patches(dp, int32_t(npatch), compute_)) return 1;
+    if (launch_range(npatch < 0 ? d_origin_ : nullptr, d_dest_, d_flying_, d_weights_, b, e, compute_, true)) return 1;
+    PTB_CUDA_OK(launch_export_positions(d_state_, d_origin_, b, e, compute_));
+    ++launches_;
+    PTB_CUDA_OK(cudaEventRecord(walk_events_[k], compute_));
+    PTB_CUDA_OK(cudaStreamWaitEvent(d2h_, walk_events_[k], 0));
+    static const bool debug_no_d2h = std::getenv("PUMITALLY_DEBUG_NO_D2H") != nullptr;  // timing experiments only: wrong results
+    if (!debug_no_d2h)
+    PTB_CUDA_OK(cudaMemcpyAsync(h_pos_ + 3 * size_t(b), d_origin_ + 3 * size_t(b), 3 * cnt * sizeof(double), cudaMemcpyDeviceToHost, d2h_));
+    PTB_CUDA_OK(cudaEventRecord(pos_events_[k], d2h_));
+  }
+  PTB_CUDA_OK(cudaEventRecord(ev_copy1_, copy_));
+  // dest and weights are read from the caller's own arrays: they must be on the device before the
+  // caller gets them back (reference: blocking deep_copy)
+  PTB_CUDA_OK(cudaStreamSynchronize(copy_));
+  stage_host_s_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  stage_sent_bytes_ = sent;
+  h2d_bytes_ += sent;
+  d2h_bytes_ += 24.0 * double(n_);
+  staged_chunk_ = chunk_;
+  staged_chunks_ = nchunks;
+  pos_mirror_valid_ = true;
+  initial_weight_pending_ = false;
+  ++moves_;
+  return 0;
+}
+
 // Direct path: every array is copied from the caller's memory as it is.
 int Engine::move_direct(const double *origin, const double *dest, int8_t *flying, const double *weights,
                         int nchunks) {
   mirror_valid_ = false;  // the staging slots do not see this move
+  pos_mirror_valid_ = false;
   maybe_register(origin, 3 * size_t(n_) * sizeof(double));
   maybe_register(dest, 3 * size_t(n_) * sizeof(double));
   maybe_register(weights, size_t(n_) * sizeof(double));
@@ -679,7 +866,9 @@ int Engine::move_to_next_location_device(const double *d_origin, const double *d
   PTB_CUDA_OK(cudaSetDevice(device_));
   begin_move();
   // (the staging arrays are not touched: "pinned dest slots == device dest array" keeps holding, and the
-  // next host move's origins are compared against them and patched exactly as after a host move)
+  // next host move's origins are compared against them and patched exactly as after a host move;
+  // the position mirror of the pinned-caller path, however, is out of date after this move)
+  pos_mirror_valid_ = false;
   if (launch_range(d_origin, d_dest, d_flying, d_weights, 0, n_, stream, true)) return 1;
   initial_weight_pending_ = false;
   ++moves_;
@@ -823,11 +1012,22 @@ int64_t Engine::get_option(const std::string &name) const {
     return cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity) == cudaSuccess ? int64_t(g) : -1;
   }
   if (name == "allreduce_us") return int64_t(allreduce_ms_ * 1e3);  // device time of the last batch-end exchange
+  if (name == "d2h_bytes") return int64_t(d2h_bytes_);  // particle positions sent back by the pinned-caller path, cumulative
   if (name == "host_path") return host_path_;
+  if (name == "pinned_path") return pinned_path_ ? 1 : 0;
+  if (name == "position_mirror") return pos_mirror_valid_ ? 1 : 0;  // the last host move took the pinned-caller path
   if (name == "host_threads") return stager_ ? stager_->threads() : host_threads_;
   if (name == "stage_host_us") return int64_t(stage_host_s_ * 1e6);   // last staged move: host time from entry to return
   if (name == "stage_sent_bytes") return int64_t(stage_sent_bytes_);  // last staged move: bytes put on the wire
   if (name == "staged") return stage_ready_ ? 1 : 0;
+  if (name == "stage_copy_us") {  // last staged move: device time from "copy stream free" to the last upload's end
+    float ms = 0.f;
+    if (!ev_copy0_ || cudaEventSynchronize(ev_copy1_) != cudaSuccess || cudaEventElapsedTime(&ms, ev_copy0_, ev_copy1_) != cudaSuccess) {
+      cudaGetLastError();
+      return -1;
+    }
+    return int64_t(ms * 1e3);
+  }
   if (name == "host_node") return pool_node_;  // NUMA node the staging workers run on (-1: not pinned to one)
   return -1;
 }
@@ -873,6 +1073,8 @@ int Engine::set_option(const std::string &name, int64_t v) {
     if (v != 0 && v != 1) return 1;
     host_path_ = int(v);
     if (host_path_ == 0) mirror_valid_ = false;
+  } else if (name == "pinned_path") {  // 0 = page-locked caller arrays also go through the staging slots
+    pinned_path_ = v != 0;
   } else if (name == "host_threads") {  // workers of the staging pool; before the first host-pointer call
     if (v < 1 || v > 256 || stager_) return 1;
     host_threads_ = int(v);

@@ -168,11 +168,22 @@ class Engine {
   size_t patch_cap_ = 0;              // entries per chunk
   int patch_chunks_ = 0;              // lists d_patch_ has room for
   double stage_host_s_ = 0.0, stage_sent_bytes_ = 0.0;
+  cudaEvent_t ev_copy0_ = nullptr, ev_copy1_ = nullptr;  // span of the last staged move's uploads
   int pool_node_ = -1;
   int ensure_stage_buffers(const void *caller_mem, size_t caller_bytes);
   void follow_caller_memory(const void *p, size_t bytes);
   int ensure_patch_buffers(int nchunks);
   int move_direct(const double *origin, const double *dest, int8_t *flying, const double *weights, int nchunks);
+  // Page-locked caller arrays (pinned by the caller, or by option register_host): see move_pinned().
+  bool pinned_path_ = true;
+  double *h_pos_ = nullptr;            // pinned mirror of the device's particle positions [3N]
+  bool pos_mirror_valid_ = false;
+  cudaStream_t d2h_ = nullptr;
+  std::vector<cudaEvent_t> pos_events_, walk_events_;  // per chunk: positions back on the host / walk + export done
+  double d2h_bytes_ = 0.0;
+  int ensure_position_mirror(int nchunks);
+  int move_pinned(const double *origin, const double *dest, int8_t *flying, const double *weights, int nchunks);
+  int relocate_patches(const PatchEntry *d_list, int32_t count, cudaStream_t stream);
 
   // NCCL (resolved with dlopen at comm_init time)
   void *nccl_comm_ = nullptr;

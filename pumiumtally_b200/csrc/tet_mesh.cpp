@@ -263,6 +263,13 @@ bool HostMesh::finalize(std::string *err) {
     }
   }
 
+  // ---- mesh-centred coordinates (tet_mesh.hpp) ---------------------------------
+  for (int d = 0; d < 3; ++d) center[d] = 0.5 * bbox_lo[d] + 0.5 * bbox_hi[d];
+  ccoords.resize(coords.size());
+#pragma omp parallel for schedule(static)
+  for (int64_t v = 0; v < nverts; ++v)
+    for (int d = 0; d < 3; ++d) ccoords[3 * v + d] = coords[3 * v + d] - center[d];
+
   // ---- volumes + packed records ----------------------------------------------
   volume.resize(ntets);
   records.resize(ntets);
@@ -270,7 +277,7 @@ bool HostMesh::finalize(std::string *err) {
 #pragma omp parallel for schedule(static) reduction(|| : degenerate)
   for (int64_t e = 0; e < ntets; ++e) {
     const double *V[4];
-    for (int i = 0; i < 4; ++i) V[i] = &coords[3 * size_t(t2v[4 * e + i])];
+    for (int i = 0; i < 4; ++i) V[i] = &ccoords[3 * size_t(t2v[4 * e + i])];
     {
       double a[3], b[3], c[3];
       for (int d = 0; d < 3; ++d) { a[d] = V[1][d] - V[0][d]; b[d] = V[2][d] - V[0][d]; c[d] = V[3][d] - V[0][d]; }
@@ -286,8 +293,8 @@ bool HostMesh::finalize(std::string *err) {
       for (int i = 0; i < 4; ++i)
         if (i != f) v[k++] = t2v[4 * e + i];
       sort3(v[0], v[1], v[2]);
-      const double *A = &coords[3 * size_t(v[0])], *B = &coords[3 * size_t(v[1])],
-                   *C = &coords[3 * size_t(v[2])];
+      const double *A = &ccoords[3 * size_t(v[0])], *B = &ccoords[3 * size_t(v[1])],
+                   *C = &ccoords[3 * size_t(v[2])];
       double ab[3], ac[3], n[3];
       for (int d = 0; d < 3; ++d) { ab[d] = B[d] - A[d]; ac[d] = C[d] - A[d]; }
       n[0] = ab[1] * ac[2] - ab[2] * ac[1];
@@ -334,10 +341,12 @@ bool HostMesh::finalize(std::string *err) {
         // margin for the rounding of n.o in the kernels (fused multiply-adds there, none here; the
         // numerator and the denominator of the same crossing round differently): a few ulps of the largest
         // value n.o can take for a ray origin anywhere in the mesh
-        const double mag = std::fabs(nx) * std::max(std::fabs(bbox_lo[0]), std::fabs(bbox_hi[0])) +
-                           std::fabs(ny) * std::max(std::fabs(bbox_lo[1]), std::fabs(bbox_hi[1])) +
-                           std::fabs(nz) * std::max(std::fabs(bbox_lo[2]), std::fabs(bbox_hi[2]));
-        const double target = need + 32.0 * 2.220446049250313e-16 * mag;
+        // (centred coordinates: n.o is at most |n|.half-extent; the translation x - center is itself
+        // correctly rounded, i.e. off by at most half an ulp of a number of that size, and exact far
+        // from the origin)
+        const double mag = std::fabs(nx) * 0.5 * (bbox_hi[0] - bbox_lo[0]) + std::fabs(ny) * 0.5 * (bbox_hi[1] - bbox_lo[1]) +
+                           std::fabs(nz) * 0.5 * (bbox_hi[2] - bbox_lo[2]);
+        const double target = need + 34.0 * 2.220446049250313e-16 * mag;
         double c = r.d[4 * f + 3];
         if (!(c >= target)) {
           const uint64_t low = dbits(c) & 0xffu;  // the payload byte stays
@@ -353,18 +362,19 @@ bool HostMesh::finalize(std::string *err) {
     }
   }
   if (degenerate) { *err = "mesh contains a degenerate (zero-volume) tet"; return false; }
-  // The plane offsets keep 44 mantissa bits: a crossing point is located to ~6e-14 of the largest
-  // coordinate, which has to stay small against a tet.  Far from the origin (|coordinate| beyond ~1e5 mean
-  // tet edges) the tally loses digits: 8e-7 relative at 1e6 (tests/test_host_emul.py::test_far_from_origin...).
+  // The plane offsets keep 44 mantissa bits of mesh-centred numbers: a crossing point is located to
+  // ~6e-14 of the mesh extent.  What remains far from the origin is the granularity of the caller's own
+  // coordinates (ulp of the absolute position against the size of a tet): worth a warning only when
+  // it reaches 1e-9 of a tet edge.
   {
     double far = 0.0, vol = 0.0;
     for (int d = 0; d < 3; ++d) far = std::max({far, std::fabs(bbox_lo[d]), std::fabs(bbox_hi[d])});
     for (int64_t e = 0; e < ntets; ++e) vol += volume[e];
     const double edge = std::cbrt(6.0 * vol / double(ntets));
-    if (far > 1e5 * edge)
-      fprintf(stderr, "[pumitally] WARNING: mesh coordinates reach %.3g, %.1e mean tet edges from the origin; "
-                      "translate the mesh (and the particle coordinates) towards the origin to keep the tally's precision\n",
-              far, far / edge);
+    if (far * 2.220446049250313e-16 > 1e-9 * edge)
+      fprintf(stderr, "[pumitally] WARNING: mesh coordinates reach %.3g, %.1e mean tet edges from the origin: double "
+                      "precision positions there resolve only %.1e of a tet edge; translate the mesh (and the "
+                      "particle coordinates) towards the origin\n", far, far / edge, far * 2.220446049250313e-16 / edge);
   }
   return true;
 }
@@ -381,14 +391,14 @@ bool HostMesh::build_compact(std::string *err) {
     if (vnew[v] < 0) vnew[v] = next++;
   cverts.assign(static_cast<size_t>(nverts), VertexRec{0, 0, 0, 0});
   for (int64_t v = 0; v < nverts; ++v)
-    cverts[vnew[v]] = VertexRec{coords[3 * v], coords[3 * v + 1], coords[3 * v + 2], 0.0};
+    cverts[vnew[v]] = VertexRec{ccoords[3 * v], ccoords[3 * v + 1], ccoords[3 * v + 2], 0.0};
 
   // slot s of tet e = local vertex (s ^ flip) for s >= 2: swapping the last two makes det > 0
   std::vector<uint8_t> flip(static_cast<size_t>(ntets));
 #pragma omp parallel for schedule(static)
   for (int64_t e = 0; e < ntets; ++e) {
     const double *V[4];
-    for (int i = 0; i < 4; ++i) V[i] = &coords[3 * size_t(t2v[4 * e + i])];
+    for (int i = 0; i < 4; ++i) V[i] = &ccoords[3 * size_t(t2v[4 * e + i])];
     double a[3], b[3], c[3];
     for (int d = 0; d < 3; ++d) { a[d] = V[1][d] - V[0][d]; b[d] = V[2][d] - V[0][d]; c[d] = V[3][d] - V[0][d]; }
     const double det = a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) +
@@ -404,7 +414,7 @@ bool HostMesh::build_compact(std::string *err) {
     TetStart &S = starts[e];
     for (int s = 0; s < 4; ++s) {
       const int32_t v = t2v[4 * e + local_of_slot(e, s)];
-      for (int d = 0; d < 3; ++d) S.v[3 * s + d] = coords[3 * size_t(v) + d];
+      for (int d = 0; d < 3; ++d) S.v[3 * s + d] = ccoords[3 * size_t(v) + d];
     }
     for (int k = 0; k < 4; ++k) {
       const int32_t nb = t2t[4 * e + local_of_slot(e, k)];

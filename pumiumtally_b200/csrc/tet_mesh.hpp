@@ -97,6 +97,13 @@ struct HostMesh {
     return out;
   }
   double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};
+  // MESH-CENTRED COORDINATES.  Face planes (and the compact layout's vertices) are stored relative to
+  // `center`, the middle of the bounding box, and the kernels translate every ray origin once
+  // (x - center) before walking.  The 44-bit plane offsets then locate a crossing to ~6e-14 of the
+  // mesh EXTENT instead of the largest absolute coordinate, so the tally keeps its digits however far
+  // from the origin the mesh sits (only the granularity of the caller's own doubles remains).
+  double center[3] = {0, 0, 0};
+  std::vector<double> ccoords;  // [3*nverts] coords - center, as the kernels compute it (fl(x - c))
 
   // "box:nx,ny,nz[,lx,ly,lz]" | raw mesh file | Gmsh .msh (2.2 / 4.1, ASCII or binary) | Omega_h .osh directory.
   bool load(const std::string &spec, std::string *err);

@@ -251,6 +251,7 @@ struct WalkParams {
   const PackedRow *rows;       // packed mode: work_count rows in processing order
   DeviceStats *stats;
   SeedGrid grid;
+  double cx, cy, cz;           // mesh centre: the planes are stored relative to it (tet_mesh.hpp)
 };
 
 constexpr int kStageReloc = 0;  // phase 1: move to caller's origin, tally off
@@ -259,7 +260,7 @@ constexpr int kStageDone = 2;
 constexpr int kStageSeed = 3;   // phase 1 started from a seed-grid cell centre
 
 struct Ray {
-  double ox, oy, oz;  // ray origin (fixed for the whole walk)
+  double ox, oy, oz;  // ray origin (fixed for the whole walk), in mesh-centred coordinates
   double ux, uy, uz;  // target - origin
   double tx, ty, tz;  // target (stored exactly as given: it becomes the position when reached)
   double tcur;        // parameter of the last crossing (the reference's prev_xpoint)
@@ -275,8 +276,10 @@ struct Counters {
   unsigned segs = 0, tracks = 0, relocs = 0, lost = 0, fallbacks = 0;
 };
 
-PTB_HD void set_ray(Ray &r, double x, double y, double z, double tx, double ty, double tz) {
-  r.ox = x; r.oy = y; r.oz = z;
+// (x,y,z) and the target are the caller's (absolute) coordinates; only the ray origin is translated,
+// once: the direction is a difference and the target is kept as given (it becomes the stored position)
+PTB_HD void set_ray(const WalkParams &P, Ray &r, double x, double y, double z, double tx, double ty, double tz) {
+  r.ox = x - P.cx; r.oy = y - P.cy; r.oz = z - P.cz;
   r.ux = tx - x; r.uy = ty - y; r.uz = tz - z;
   r.tx = tx; r.ty = ty; r.tz = tz;
   r.tcur = 0.0;
@@ -290,14 +293,14 @@ PTB_HD bool all_finite(double a, double b, double c) { return (a * 0.0 + b * 0.0
 
 // Tally phase towards (tx,ty,tz) with weight w.  A non-finite destination or weight turns the flight
 // into a zero-length one (the particle stays where it is, nothing is tallied) and counts as lost.
-PTB_HD void start_tally_to(Ray &r, double x, double y, double z, double tx, double ty, double tz, double w,
-                           Counters &c, bool writer) {
+PTB_HD void start_tally_to(const WalkParams &P, Ray &r, double x, double y, double z, double tx, double ty,
+                           double tz, double w, Counters &c, bool writer) {
   if (!all_finite(tx, ty, tz) || !all_finite(w, 0.0, 0.0)) {
     tx = x; ty = y; tz = z;
     w = 0.0;
     if (writer) c.lost++;
   }
-  set_ray(r, x, y, z, tx, ty, tz);
+  set_ray(P, r, x, y, z, tx, ty, tz);
   const double len = sqrt(r.ux * r.ux + r.uy * r.uy + r.uz * r.uz);
   r.wl = w * len;
   r.stage = kStageTally;
@@ -306,7 +309,7 @@ PTB_HD void start_tally_to(Ray &r, double x, double y, double z, double tx, doub
 
 PTB_HD void start_tally(const WalkParams &P, int i, Ray &r, double x, double y, double z,
                         Counters &c, bool writer) {
-  start_tally_to(r, x, y, z, PTB_LDG(P.dest + 3 * (size_t)i), PTB_LDG(P.dest + 3 * (size_t)i + 1),
+  start_tally_to(P, r, x, y, z, PTB_LDG(P.dest + 3 * (size_t)i), PTB_LDG(P.dest + 3 * (size_t)i + 1),
                  PTB_LDG(P.dest + 3 * (size_t)i + 2), PTB_LDG(P.weights + i), c, writer);
 }
 
@@ -325,14 +328,14 @@ PTB_HD void start_reloc(const WalkParams &P, Ray &r, double x, double y, double 
       if (seed >= 0) {
         double sx, sy, sz;
         seed_point(g, cx, cy, cz, sx, sy, sz);
-        set_ray(r, sx, sy, sz, tx, ty, tz);
+        set_ray(P, r, sx, sy, sz, tx, ty, tz);
         r.e = seed;
         r.stage = kStageSeed;
         return;
       }
     }
   }
-  set_ray(r, x, y, z, tx, ty, tz);
+  set_ray(P, r, x, y, z, tx, ty, tz);
   r.stage = kStageReloc;
 }
 
@@ -383,14 +386,14 @@ PTB_HD void end_ray(const WalkParams &P, int i, Ray &r, bool reached, double tne
     const ParticleState s0 = load_state(P.state + i);
     x = s0.x; y = s0.y; z = s0.z;
     r.e = s0.elem;
-    set_ray(r, x, y, z, r.tx, r.ty, r.tz);
+    set_ray(P, r, x, y, z, r.tx, r.ty, r.tz);
     r.stage = kStageReloc;
     return;
   }
   if (reached) {  // tracer commit: origin <- dest, exactly (test lines 323-346)
     x = r.tx; y = r.ty; z = r.tz;
   } else {  // vacuum BC: dest <- intersection point (Impl.cpp:275-281)
-    x = fma(tnew, r.ux, r.ox); y = fma(tnew, r.uy, r.oy); z = fma(tnew, r.uz, r.oz);
+    x = fma(tnew, r.ux, r.ox) + P.cx; y = fma(tnew, r.uy, r.oy) + P.cy; z = fma(tnew, r.uz, r.oz) + P.cz;
   }
   if (r.stage != kStageTally && P.dest) {
     start_tally(P, i, r, x, y, z, c, writer);  // phase 2 starts where phase 1 ended

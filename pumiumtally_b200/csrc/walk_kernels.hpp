@@ -40,8 +40,9 @@ enum WalkVariant : int {
 
 cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_t stream);
 bool walk_variant_available(int variant);  // compiled into this library?
-cudaError_t launch_bin_particles(const SeedGrid &g, const double *origin, const int8_t *flying,
-                                 int32_t begin, int32_t end, int32_t *pcell, unsigned int *count,
+// origin == nullptr: the binning key is the stored position (state)
+cudaError_t launch_bin_particles(const SeedGrid &g, const double *origin, const ParticleState *state,
+                                 const int8_t *flying, int32_t begin, int32_t end, int32_t *pcell, unsigned int *count,
                                  unsigned int *sums, int32_t *order, unsigned int *work_count,
                                  cudaStream_t stream);
 // Like launch_bin_particles, but instead of the id list the scatter pass writes one PackedRow per
@@ -58,6 +59,16 @@ cudaError_t launch_init_particles(ParticleState *state, int32_t n, double cx, do
                                   int32_t elem, cudaStream_t stream);
 // origin[3*idx..] = (x,y,z) for every entry of the patch list
 cudaError_t launch_patch_origins(double *origin, const PatchEntry *list, int32_t count, cudaStream_t stream);
+// Phase 1 of MoveToNextLocation (PumiTallyImpl.cpp:71-112) for the listed particles only: each is
+// walked, tally off, from its stored position to (x,y,z) of its entry and its state is updated; an
+// entry with a non-finite position makes the particle sit the move out (flying[idx] <- 0, counted as
+// lost).  p.origin / p.dest / p.weights are ignored.  For the host path whose mirror is the device's
+// own particle positions: every particle not listed is already where its origin says.
+cudaError_t launch_relocate_patches(const WalkParams &p, const PatchEntry *list, int32_t count, int8_t *flying,
+                                    cudaStream_t stream);
+// xyz[3i..3i+2] = position of particle i for i in [begin, end)
+cudaError_t launch_export_positions(const ParticleState *state, double *xyz, int32_t begin, int32_t end,
+                                    cudaStream_t stream);
 // out = flux / volume / per_source (NormalizeFlux, PumiTallyImpl.cpp:393-405; per_source = 1 is the reference)
 cudaError_t launch_normalize(const double *flux, const double *volume, double *out, int64_t n,
                              double per_source, cudaStream_t stream);

@@ -150,7 +150,7 @@ __device__ __forceinline__ void begin_from_stage(const WalkParams &P, const Part
       return;
     }
   }
-  if (P.dest) start_tally_to(r, x, y, z, st->dest[3 * s], st->dest[3 * s + 1], st->dest[3 * s + 2], st->w[s], c, true);
+  if (P.dest) start_tally_to(P, r, x, y, z, st->dest[3 * s], st->dest[3 * s + 1], st->dest[3 * s + 2], st->w[s], c, true);
 }
 
 // begin_particle() for a packed row (only flying particles have rows).  Returns the particle id.
@@ -169,7 +169,7 @@ __device__ __forceinline__ int begin_from_row(const WalkParams &P, const PackedR
     return id;
   }
   r.e = (int32_t)(el & kIdMask);
-  start_tally_to(r, ox, oy, oz, row->dx, row->dy, row->dz, row->w, c, true);
+  start_tally_to(P, r, ox, oy, oz, row->dx, row->dy, row->dz, row->w, c, true);
   return id;
 }
 

@@ -271,7 +271,7 @@ def non_finite_input_scenario(make_engine):
     return eng
 
 
-def lattice_track_scenario(make_engine, seeds):
+def lattice_track_scenario(make_engine, seeds, exact_destinations=True):
     """Tracks between points of the quarter-cell lattice of Kuhn boxes: along the hull surface, along
     edges, inside face planes, through vertices.  Attribution to a particular tet is a tie-break there;
     what must hold: nothing lost or stopped early, destinations reached exactly, total tally equal to the
@@ -290,10 +290,17 @@ def lattice_track_scenario(make_engine, seeds):
         w = rng.uniform(0.5, 1.0, n)
         eng = make_engine(coords, t2v, n)
         eng.CopyInitialPosition(a.reshape(-1).copy())
-        np.testing.assert_array_equal(eng.positions, a, err_msg=f"seed {seed}: localisation")
+        if exact_destinations:
+            np.testing.assert_array_equal(eng.positions, a, err_msg=f"seed {seed}: localisation")
+        else:
+            np.testing.assert_allclose(eng.positions, a, rtol=0, atol=4e-16 * max(lengths), err_msg=f"seed {seed}: localisation")
         eng.MoveToNextLocation(a.reshape(-1).copy(), b.reshape(-1).copy(), np.ones(n, dtype=np.int8), w.copy())
         assert eng.stats()["lost"] == 0
-        np.testing.assert_array_equal(eng.positions, b, err_msg=f"seed {seed}: destinations")
+        if exact_destinations:
+            np.testing.assert_array_equal(eng.positions, b, err_msg=f"seed {seed}: destinations")
+        else:  # the experimental edge-function walk has no outward-erring hull: a destination exactly on
+            # the hull may count as a clip point there, which is the same point to within an ulp
+            np.testing.assert_allclose(eng.positions, b, rtol=0, atol=4e-16 * max(lengths), err_msg=f"seed {seed}: destinations")
         np.testing.assert_allclose(eng.flux.sum(), (np.linalg.norm(b - a, axis=1) * w).sum(), rtol=1e-12)
         v = coords[t2v[eng.elem_ids]]
         T = np.transpose(v[:, 1:] - v[:, :1], (0, 2, 1))

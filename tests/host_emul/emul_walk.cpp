@@ -62,6 +62,7 @@ struct Emul {
     P.begin = 0; P.end = count;
     P.max_iters = int32_t(mesh.ntets + 16);
     P.stats = st;
+    P.cx = mesh.center[0]; P.cy = mesh.center[1]; P.cz = mesh.center[2];
     if (g) P.grid = *g;
     DeviceStats &stats = *st;
     const int n = count;

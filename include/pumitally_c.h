@@ -135,6 +135,17 @@ int pumitally_copy_initial_position_device(pumitally_engine *e, const double *d_
 int pumitally_move_to_next_location_device(pumitally_engine *e, const double *d_origin,
                                            const double *d_destinations, const int8_t *d_flying,
                                            const double *d_weights, int32_t size, void *stream);
+/* Particle slots [first, first+count) <- positions d_xyz[3*count] in elements d_elem[count] (the
+ * caller's element numbering), without walking there; and the reverse.  For drivers that place
+ * particles themselves, e.g. the spatially partitioned multi-GPU driver
+ * (pumiumtally_b200/partition.py), which hands particles from one picpart's engine to the next.
+ * The elements are trusted to contain the positions.  Enqueued on `stream`, no synchronisation. */
+int pumitally_set_state_device(pumitally_engine *e, const double *d_xyz, const int32_t *d_elem,
+                               int32_t first, int32_t count, void *stream);
+int pumitally_get_state_device(pumitally_engine *e, double *d_xyz, int32_t *d_elem, int32_t first,
+                               int32_t count, void *stream);
+/* raw flux in the caller's element numbering into device memory d_out[num_elements] */
+int pumitally_get_flux_device(pumitally_engine *e, double *d_out, void *stream);
 /* device address of the raw flux array (double[num_elements]); NOTE: in the engine's internal
  * (spatially sorted) element order -- use pumitally_get_flux for the caller's numbering */
 double *pumitally_flux_device_ptr(pumitally_engine *e);

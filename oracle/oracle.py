@@ -40,6 +40,7 @@ def lib():
         L.um_oracle_destroy.argtypes = [C.c_void_p]
         L.um_oracle_set_mode.argtypes = [C.c_void_p, C.c_int]
         L.um_oracle_set_exit_rule.argtypes = [C.c_void_p, C.c_int]
+        L.um_oracle_set_state.argtypes = [C.c_void_p, dp, ip, C.c_int]
         L.um_oracle_copy_initial_position.argtypes = [C.c_void_p, dp, C.c_int]
         L.um_oracle_move_to_next_location.argtypes = [C.c_void_p, dp, dp, bp, dp, C.c_int]
         L.um_oracle_normalized_flux.argtypes = [C.c_void_p, dp, dp]
@@ -110,6 +111,12 @@ class OraclePumiTally:
         self._L.um_oracle_move_to_next_location(
             self._h, _d(o), _d(d), flying.ctypes.data_as(C.POINTER(C.c_byte)), _d(w), int(size)
         )
+
+    def set_state(self, xyz, elems):
+        """Particles [0, len(elems)) placed at xyz in tets elems without walking (driver tests)."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1)
+        elems = np.ascontiguousarray(elems, dtype=np.int32)
+        self._L.um_oracle_set_state(self._h, _d(xyz), _i(elems), len(elems))
 
     def normalized_flux(self):
         f = np.empty(self.ntets)

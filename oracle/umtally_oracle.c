@@ -420,6 +420,16 @@ void um_oracle_normalized_flux(const um_oracle *o, double *out_flux, double *out
   }
 }
 
+/* Places particles [0, count) at given positions in given tets without walking there (test support
+ * for drivers that hand particles between picparts; not part of the reference interface). */
+void um_oracle_set_state(um_oracle *o, const double *xyz, const int *elems, int count) {
+  for (int p = 0; p < count && p < o->nptcls; ++p) {
+    for (int d = 0; d < 3; ++d) o->orig[3 * p + d] = xyz[3 * p + d];
+    o->elem_ids[p] = elems[p];
+  }
+  o->initialized = 1;
+}
+
 int um_oracle_ntets(const um_oracle *o) { return o->ntets; }
 int um_oracle_nptcls(const um_oracle *o) { return o->nptcls; }
 const double *um_oracle_flux(const um_oracle *o) { return o->flux; }

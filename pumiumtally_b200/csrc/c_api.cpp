@@ -193,6 +193,21 @@ int pumitally_move_to_next_location_device(pumitally_engine *e, const double *d_
                                           static_cast<cudaStream_t>(stream));
   });
 }
+int pumitally_set_state_device(pumitally_engine *e, const double *d_xyz, const int32_t *d_elem, int32_t first,
+                               int32_t count, void *stream) {
+  return guarded(e, [&](ptb::Engine &g) {
+    return g.set_state_device(d_xyz, d_elem, first, count, static_cast<cudaStream_t>(stream));
+  });
+}
+int pumitally_get_state_device(pumitally_engine *e, double *d_xyz, int32_t *d_elem, int32_t first, int32_t count,
+                               void *stream) {
+  return guarded(e, [&](ptb::Engine &g) {
+    return g.get_state_device(d_xyz, d_elem, first, count, static_cast<cudaStream_t>(stream));
+  });
+}
+int pumitally_get_flux_device(pumitally_engine *e, double *d_out, void *stream) {
+  return guarded(e, [&](ptb::Engine &g) { return g.get_flux_device(d_out, static_cast<cudaStream_t>(stream)); });
+}
 double *pumitally_flux_device_ptr(pumitally_engine *e) {
   return (e && e->impl) ? e->impl->flux_device_ptr() : nullptr;
 }

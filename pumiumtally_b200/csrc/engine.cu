@@ -155,6 +155,7 @@ Engine::~Engine() {
   cudaFree(d_initial_weight_);
   cudaFree(d_tickets_);
   cudaFree(d_grid_);
+  cudaFree(d_orig_of_internal_); cudaFree(d_internal_of_orig_);
   cudaFree(d_cell_rank_);
   cudaFree(d_pcell_); cudaFree(d_order_); cudaFree(d_cell_count_); cudaFree(d_cell_sums_);
   cudaFree(d_work_count_);
@@ -501,11 +502,18 @@ int Engine::ensure_stage_buffers(const void *caller_mem, size_t caller_bytes) {
   void *base = nullptr;
   if (posix_memalign(&base, 4096, total) == 0) {
     const int T = pool_->size();
+    // Where the staging slots live.  Default: on the workers' node (= the caller's arrays' node).
+    // PUMITALLY_STAGE_NODE=<n> puts them on another node: on a two-socket host the pass then draws on
+    // both sockets' memory controllers (caller arrays on one, slots + DMA reads on the other).
+    const char *env_node = std::getenv("PUMITALLY_STAGE_NODE");
+    const std::vector<int> there = env_node ? numa_node_cpus(std::atoi(env_node)) : std::vector<int>();
+    if (!there.empty()) pool_->repin(there);
     pool_->run([&](int t) {  // first touch on the workers' NUMA node
       const size_t lo = (total * size_t(t) / size_t(T)) & ~size_t(4095);
       const size_t hi = t == T - 1 ? total : (total * size_t(t + 1) / size_t(T)) & ~size_t(4095);
       std::memset(static_cast<char *>(base) + lo, 0, hi - lo);
     });
+    if (!there.empty() && pool_node_ >= 0) pool_->repin(numa_node_cpus(pool_node_));
     if (cudaHostRegister(base, total, cudaHostRegisterDefault) == cudaSuccess) {
       stage_registered_ = true;
     } else {
@@ -878,6 +886,45 @@ int Engine::move_to_next_location_device(const double *d_origin, const double *d
 int Engine::synchronize() {
   PTB_CUDA_OK(cudaSetDevice(device_));
   PTB_CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int Engine::ensure_element_maps() {
+  if (d_orig_of_internal_) return 0;
+  const size_t E = std::max<size_t>(size_t(mesh_.ntets), 1);
+  PTB_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&d_orig_of_internal_), E * sizeof(int32_t)));
+  PTB_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&d_internal_of_orig_), E * sizeof(int32_t)));
+  PTB_CUDA_OK(cudaMemcpy(d_orig_of_internal_, mesh_.orig_of_internal.data(), size_t(mesh_.ntets) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  PTB_CUDA_OK(cudaMemcpy(d_internal_of_orig_, mesh_.internal_of_orig.data(), size_t(mesh_.ntets) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// Places particles [first, first + count) at given positions in given elements (caller's numbering)
+// without walking there: for drivers that hand particles between engines (spatial partition).  The
+// elements are trusted to contain the positions.
+int Engine::set_state_device(const double *d_xyz, const int32_t *d_elem, int32_t first, int32_t count, cudaStream_t stream) {
+  if (first < 0 || count < 0 || int64_t(first) + count > n_) return 1;
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  if (ensure_element_maps()) return 1;
+  PTB_CUDA_OK(launch_set_state(d_state_, d_xyz, d_elem, d_internal_of_orig_, first, first + count, stream));
+  initialized_ = true;
+  mirror_valid_ = false;
+  pos_mirror_valid_ = false;
+  return 0;
+}
+
+int Engine::get_state_device(double *d_xyz, int32_t *d_elem, int32_t first, int32_t count, cudaStream_t stream) {
+  if (first < 0 || count < 0 || int64_t(first) + count > n_) return 1;
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  if (ensure_element_maps()) return 1;
+  PTB_CUDA_OK(launch_get_state(d_state_, d_xyz, d_elem, d_orig_of_internal_, first, first + count, stream));
+  return 0;
+}
+
+int Engine::get_flux_device(double *d_out, cudaStream_t stream) {
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  if (ensure_element_maps()) return 1;
+  PTB_CUDA_OK(launch_flux_to_caller_order(flux_view(), d_orig_of_internal_, d_out, mesh_.ntets, stream));
   return 0;
 }
 

@@ -49,6 +49,10 @@ class Engine {
                                    cudaStream_t stream);
 
   int get_flux(double *out, int64_t n);
+  // Device-side accessors, caller's element numbering, enqueued on `stream` (no synchronisation).
+  int set_state_device(const double *d_xyz, const int32_t *d_elem, int32_t first, int32_t count, cudaStream_t stream);
+  int get_state_device(double *d_xyz, int32_t *d_elem, int32_t first, int32_t count, cudaStream_t stream);
+  int get_flux_device(double *d_out, cudaStream_t stream);
   int get_normalized_flux(double *out_flux, double *out_volume, int64_t n);
   int get_element_ids(int32_t *out, int64_t n);
   int get_positions(double *out, int64_t n3);
@@ -132,6 +136,8 @@ class Engine {
   unsigned ticket_next_ = 0;
   SeedGrid grid_{};              // relocation seed grid (grid_.cell_tet lives in d_grid_)
   int32_t *d_grid_ = nullptr;
+  int32_t *d_orig_of_internal_ = nullptr, *d_internal_of_orig_ = nullptr;  // element renumbering maps (device accessors)
+  int ensure_element_maps();
   int32_t *d_cell_rank_ = nullptr;
   // spatial binning of the flying particles (gather-mode kernels)
   int32_t *d_pcell_ = nullptr, *d_order_ = nullptr;

@@ -125,6 +125,36 @@ __global__ void __launch_bounds__(128) relocate_patches_kernel(WalkParams P, con
   flush_counters(P, c);
 }
 
+// Particle slots [begin, end) <- (xyz, element in the caller's numbering): for callers that manage
+// particle placement themselves (the spatially partitioned multi-GPU driver hands particles from one
+// picpart to the next).  elem_map: caller's element id -> internal id.
+__global__ void set_state_kernel(ParticleState *state, const double *xyz, const int32_t *elem, const int32_t *elem_map,
+                                 int32_t begin, int32_t end) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = begin + k;
+  if (i >= end) return;
+  store_state(state + i, xyz[3 * (size_t)k], xyz[3 * (size_t)k + 1], xyz[3 * (size_t)k + 2], elem_map[elem[k]]);
+}
+
+// (xyz, element in the caller's numbering) <- particle slots [begin, end).  elem_map: internal id -> caller's.
+__global__ void get_state_kernel(const ParticleState *state, double *xyz, int32_t *elem, const int32_t *elem_map,
+                                 int32_t begin, int32_t end) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = begin + k;
+  if (i >= end) return;
+  const ParticleState s = load_state(state + i);
+  xyz[3 * (size_t)k] = s.x;
+  xyz[3 * (size_t)k + 1] = s.y;
+  xyz[3 * (size_t)k + 2] = s.z;
+  elem[k] = elem_map[s.elem];
+}
+
+// out[caller's element id] = flux[internal id]
+__global__ void flux_to_caller_order_kernel(const double *flux, const int32_t *orig_of_internal, double *out, int64_t n) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) out[orig_of_internal[e]] = flux[e];
+}
+
 __global__ void export_positions_kernel(const ParticleState *state, double *xyz, int32_t begin, int32_t end) {
   const int i = begin + blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= end) return;
@@ -230,6 +260,27 @@ cudaError_t launch_relocate_patches(const WalkParams &p, const PatchEntry *list,
   q.weights = nullptr;
   q.flying = nullptr;
   relocate_patches_kernel<<<(count + 127) / 128, 128, 0, stream>>>(q, list, count, flying);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_set_state(ParticleState *state, const double *xyz, const int32_t *elem, const int32_t *elem_map,
+                             int32_t begin, int32_t end, cudaStream_t stream) {
+  if (end <= begin) return cudaSuccess;
+  set_state_kernel<<<(end - begin + 255) / 256, 256, 0, stream>>>(state, xyz, elem, elem_map, begin, end);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_get_state(const ParticleState *state, double *xyz, int32_t *elem, const int32_t *elem_map,
+                             int32_t begin, int32_t end, cudaStream_t stream) {
+  if (end <= begin) return cudaSuccess;
+  get_state_kernel<<<(end - begin + 255) / 256, 256, 0, stream>>>(state, xyz, elem, elem_map, begin, end);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_flux_to_caller_order(const double *flux, const int32_t *orig_of_internal, double *out, int64_t n,
+                                        cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  flux_to_caller_order_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(flux, orig_of_internal, out, n);
   return cudaGetLastError();
 }
 

@@ -66,6 +66,13 @@ cudaError_t launch_patch_origins(double *origin, const PatchEntry *list, int32_t
 // own particle positions: every particle not listed is already where its origin says.
 cudaError_t launch_relocate_patches(const WalkParams &p, const PatchEntry *list, int32_t count, int8_t *flying,
                                     cudaStream_t stream);
+// particle slots [begin, end) <-> (xyz[3k..], elem[k]) with k = slot - begin; elem in the caller's numbering
+cudaError_t launch_set_state(ParticleState *state, const double *xyz, const int32_t *elem, const int32_t *elem_map,
+                             int32_t begin, int32_t end, cudaStream_t stream);
+cudaError_t launch_get_state(const ParticleState *state, double *xyz, int32_t *elem, const int32_t *elem_map,
+                             int32_t begin, int32_t end, cudaStream_t stream);
+cudaError_t launch_flux_to_caller_order(const double *flux, const int32_t *orig_of_internal, double *out, int64_t n,
+                                        cudaStream_t stream);
 // xyz[3i..3i+2] = position of particle i for i in [begin, end)
 cudaError_t launch_export_positions(const ParticleState *state, double *xyz, int32_t begin, int32_t end,
                                     cudaStream_t stream);

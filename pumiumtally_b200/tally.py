@@ -59,6 +59,9 @@ C_API = {
     "pumitally_copy_initial_position_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "pumitally_move_to_next_location_device": (
         C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pumitally_set_state_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "pumitally_get_state_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "pumitally_get_flux_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pumitally_flux_device_ptr": (C.c_void_p, [C.c_void_p]),
     "pumitally_synchronize": (C.c_int, [C.c_void_p]),
     "pumitally_nccl_unique_id": (C.c_int, [_u8p]),
@@ -193,6 +196,18 @@ class PumiTally:
         if self._L.pumitally_move_to_next_location_device(self._h, d_origin, d_dest, d_flying, d_weights,
                                                           3 * self.num_particles, stream):
             raise RuntimeError("MoveToNextLocation(device) failed")
+
+    def set_state_device(self, d_xyz, d_elem, first, count, stream=None):
+        if self._L.pumitally_set_state_device(self._h, d_xyz, d_elem, int(first), int(count), stream):
+            raise RuntimeError("set_state_device failed")
+
+    def get_state_device(self, d_xyz, d_elem, first, count, stream=None):
+        if self._L.pumitally_get_state_device(self._h, d_xyz, d_elem, int(first), int(count), stream):
+            raise RuntimeError("get_state_device failed")
+
+    def get_flux_device(self, d_out, stream=None):
+        if self._L.pumitally_get_flux_device(self._h, d_out, stream):
+            raise RuntimeError("get_flux_device failed")
 
     def synchronize(self):
         self._L.pumitally_synchronize(self._h)

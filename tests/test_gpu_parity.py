@@ -648,6 +648,25 @@ def test_two_gpu_stripes_allreduce_equals_single_gpu():
     assert_flux_close(flux2, one.flux, "2-GPU allreduce vs 1 GPU")
 
 
+def test_two_gpu_spatial_partition_equals_replicas():
+    """pumiumtally_b200/partition.py on two GPUs (RCB picparts, routing, hand-off, ghost exchange)
+    against the replica scheme on the same particles: scripts/exp_partition.py reports the parity."""
+    import json
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.check_output(
+        ["python", "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+         "--master-port", str(29900 + os.getpid() % 90), os.path.join(ROOT, "scripts", "exp_partition.py"),
+         "c2", "400000", "2", "4"], text=True, cwd=ROOT, timeout=600)
+    res = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert res["parity"]["flux_elements_outside_1e-6"] == 0
+    assert res["parity"]["parent_element_mismatches"] == 0 and res["parity"]["max_position_error"] < 1e-9
+    assert res["partition"]["handoffs_per_move"] > 0
+    assert res["partition"]["local_tets"] < 0.7 * res["tets"]
+
+
 # ---------------------------------------------------------------- full sizes
 
 def _box_clip_length(o, d, box):

@@ -127,6 +127,7 @@ Engine::~Engine() {
   cudaDeviceSynchronize();
   if (nccl_comm_) nccl_comm_destroy(nccl_comm_);
   cudaFree(d_flux_global_);
+  if (ev_order_) cudaEventDestroy(ev_order_);
   if (ev_copy0_) cudaEventDestroy(ev_copy0_);
   if (ev_copy1_) cudaEventDestroy(ev_copy1_);
   if (ev_ar0_) cudaEventDestroy(ev_ar0_);
@@ -284,6 +285,16 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
                          const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream,
                          bool timed) {
   if (end <= begin) return 0;
+  // Particle state, binning scratch and the ticket ring are shared by every launch: work enqueued on
+  // another stream than the previous launch's (a device-pointer move on the caller's stream after a
+  // host-pointer move on the engine's own, or the other way round) is ordered behind it by an event.
+  if (last_stream_set_ && stream != last_stream_) {
+    if (!ev_order_) PTB_CUDA_OK(cudaEventCreateWithFlags(&ev_order_, cudaEventDisableTiming));
+    PTB_CUDA_OK(cudaEventRecord(ev_order_, last_stream_));
+    PTB_CUDA_OK(cudaStreamWaitEvent(stream, ev_order_, 0));
+  }
+  last_stream_ = stream;
+  last_stream_set_ = true;
   if (d_dest) flux_global_valid_ = false;  // the local tally moves on; the last exchange no longer describes it
   if (d_dest && d_weights && initial_weight_pending_)  // first tracks of the batch: their total weight
     PTB_CUDA_OK(launch_sum_flying_weights(d_flying, d_weights, begin, end, d_initial_weight_, stream));
@@ -354,7 +365,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
     launches_ += 5;  // count, 3-kernel scan, pack
   }
   if (variant == kVariantPersistGather || variant == kVariantPersistGatherL1 ||
-      variant == kVariantPersistGatherPlain || variant == kVariantEdgeGather) {
+      variant == kVariantPersistGatherPlain || variant == kVariantEdgeGather || variant == kVariantGatherAggTally) {
     // counting sort of the range's flying particles by seed-grid cell of their origin
     unsigned int *wc = d_work_count_ + (ticket_next_ % kTicketRing);
     const double *key = d_origin;  // no origin array (pinned-caller host path): the stored position

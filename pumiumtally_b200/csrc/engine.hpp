@@ -146,6 +146,9 @@ class Engine {
   unsigned int *d_cell_count_ = nullptr, *d_cell_sums_ = nullptr, *d_work_count_ = nullptr;
 
   cudaStream_t compute_ = nullptr, copy_ = nullptr;
+  cudaStream_t last_stream_ = nullptr;  // stream of the previous kernel launch that touched the particle state
+  bool last_stream_set_ = false;
+  cudaEvent_t ev_order_ = nullptr;
   struct TimerPair { cudaEvent_t a, b; int tag; };  // tag: auto-tuner slot the time belongs to, -1 = none
   std::vector<TimerPair> timers_free_, timers_busy_;
   std::vector<cudaEvent_t> chunk_events_;

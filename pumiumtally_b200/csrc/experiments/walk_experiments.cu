@@ -109,6 +109,148 @@ __global__ void __launch_bounds__(256) walk_quad_kernel(const WalkParams P) {
   flush_counters(P, c);
 }
 
+
+// ---------------------------------------------------------------- variant 27
+// Two rays per lane ("settle the latency-vs-L2 question with measurements").
+// The streaming kernel (variant 8) keeps 28 warps x 1 ray per SM in flight and stalls ~10 warps per
+// issue slot on the long scoreboard.  Here every lane owns two independent rays; each iteration
+// issues the record loads of both before either is used, so a warp has twice the loads in flight
+// at the same occupancy -- if the kernel were latency-bound this would pay, if it is bound by L2
+// request throughput it cannot.  Same staging (TMA bulk copies of 16-particle chunks, two stages per
+// warp), same per-ray state machine, same results.
+__device__ __forceinline__ void plane_load(const WalkParams &P, const Ray &r, uint64_t pol, double (&q)[3][4],
+                                           double (&q3)[4]) {
+  const double *rec = P.tets[r.e].d;
+  const int en = r.entry;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int fk = k + ((en >= 0 && k >= en) ? 1 : 0);
+    load_face<kFetchPolicy>(rec + 4 * fk, pol, q[k][0], q[k][1], q[k][2], q[k][3]);
+  }
+  if (en < 0) load_face<kFetchPolicy>(rec + 12, pol, q3[0], q3[1], q3[2], q3[3]);
+}
+__device__ __forceinline__ void plane_compute(const WalkParams &P, int my_i, Ray &r, Counters &c, const double (&q)[3][4],
+                                              const double (&q3)[4]) {
+  ExitScan sc;
+  const int en = r.entry;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int fk = k + ((en >= 0 && k >= en) ? 1 : 0);
+    int32_t nb, bk;
+    face_payload(q[k][0], q[k][1], q[k][2], q[k][3], r.e, fk, nb, bk);
+    scan_face(sc, q[k][0], q[k][1], q[k][2], q[k][3], nb, bk, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
+  }
+  if (en < 0) {
+    int32_t nb, bk;
+    face_payload(q3[0], q3[1], q3[2], q3[3], r.e, 3, nb, bk);
+    scan_face(sc, q3[0], q3[1], q3[2], q3[3], nb, bk, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
+  }
+  advance(P, my_i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
+}
+
+template <int BLOCK, int MINB, int REFILL_T>
+__global__ void __launch_bounds__(BLOCK, MINB) walk_tworays_kernel(const WalkParams P) {
+  constexpr int WARPS = BLOCK / 32;
+  __shared__ ParticleStage stages[WARPS][2];
+  __shared__ __align__(8) unsigned long long bars[WARPS][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t bar0 = smem_u32(&bars[warp][0]);
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  const uint64_t keep = l2_policy_keep(), strm = l2_policy_stream();
+  const int total = P.end - P.begin;
+  const int nchunks = (total + kChunk - 1) / kChunk;
+  auto claim = [&]() -> int {
+    int c = 0;
+    if (lane == 0) c = (int)atomicAdd(P.work_counter, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    return c < nchunks ? c : -1;
+  };
+  int cur = 0, cursor = 0, cur_count = 0;
+  uint32_t parity = 0;
+  int chunk_cur = claim();
+  if (chunk_cur >= 0) stage_load_hint(P, chunk_cur, &stages[warp][0], bar0, lane, strm);
+  int chunk_next = chunk_cur >= 0 ? claim() : -1;
+  if (chunk_next >= 0) stage_load_hint(P, chunk_next, &stages[warp][1], bar0 + 8, lane, strm);
+  if (chunk_cur >= 0) {
+    mbar_wait(bar0, 0);
+    parity ^= 1u;
+    cur_count = min(kChunk, total - chunk_cur * kChunk);
+  }
+  Counters c;
+  Ray r[2];
+  int my_i[2] = {0, 0};
+  r[0].stage = r[1].stage = kStageDone;
+  for (;;) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      unsigned idle = __ballot_sync(0xffffffffu, r[k].stage == kStageDone);
+      while (cur_count > 0 && (int)__popc(idle) >= REFILL_T) {
+        const int slot = cursor + __popc(idle & ((1u << lane) - 1u));
+        if (r[k].stage == kStageDone && slot < cur_count) {
+          my_i[k] = P.begin + chunk_cur * kChunk + slot;
+          begin_from_stage(P, &stages[warp][cur], slot, r[k], c);
+        }
+        __syncwarp();
+        cursor += __popc(idle);
+        if (cursor >= cur_count) {
+          const int recycled = cur;
+          chunk_cur = chunk_next;
+          cur ^= 1;
+          cursor = 0;
+          cur_count = 0;
+          chunk_next = -1;
+          if (chunk_cur >= 0) {
+            mbar_wait(bar0 + 8 * cur, (parity >> cur) & 1u);
+            parity ^= 1u << cur;
+            cur_count = min(kChunk, total - chunk_cur * kChunk);
+            chunk_next = claim();
+            if (chunk_next >= 0) {
+              if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              stage_load_hint(P, chunk_next, &stages[warp][recycled], bar0 + 8 * recycled, lane, strm);
+            }
+          }
+        }
+        idle = __ballot_sync(0xffffffffu, r[k].stage == kStageDone);
+      }
+    }
+    const bool a0 = r[0].stage != kStageDone, a1 = r[1].stage != kStageDone;
+    if (!__any_sync(0xffffffffu, a0 || a1)) break;  // nothing in flight and nothing left to hand out
+    double qa[3][4], qa3[4], qb[3][4], qb3[4];
+    if (a0) plane_load(P, r[0], keep, qa, qa3);  // both rays' records are requested ...
+    if (a1) plane_load(P, r[1], keep, qb, qb3);
+    if (a0) plane_compute(P, my_i[0], r[0], c, qa, qa3);  // ... before either is used
+    if (a1) plane_compute(P, my_i[1], r[1], c, qb, qb3);
+  }
+  flush_counters(P, c);
+}
+
+template <int BLOCK, int MINB, int REFILL_T>
+cudaError_t launch_tworays(const WalkParams &p, long long n, cudaStream_t stream) {
+  static int sms = 0, occ = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(walk_tworays_kernel<BLOCK, MINB, REFILL_T>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         (int)cudaSharedmemCarveoutMaxShared);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, walk_tworays_kernel<BLOCK, MINB, REFILL_T>, BLOCK, 0);
+    if (occ < 1) occ = 1;
+  }
+  const long long nchunks = (n + kChunk - 1) / kChunk;
+  const long long want = (nchunks + BLOCK / 32 - 1) / (BLOCK / 32);
+  const unsigned grid = (unsigned)std::min<long long>(want, (long long)sms * occ);
+  cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) return e;
+  walk_tworays_kernel<BLOCK, MINB, REFILL_T><<<grid, BLOCK, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t launch_walk_experiment(const WalkParams &p, int variant, int block, cudaStream_t stream) {
@@ -142,6 +284,17 @@ cudaError_t launch_walk_experiment(const WalkParams &p, int variant, int block, 
       return launch_persist<128, kFetchPolicy, 7, 8, true>(p, n, stream);
     case kVariantPersistGatherPlain:
       return launch_persist<128, kFetchPlain, 7, 1, true, 40>(p, n, stream);
+    case kVariantPersistRefill8Occ8:
+      return launch_persist<128, kFetchPolicy, 8, 8>(p, n, stream);
+    case kVariantTwoRays:
+      if (p.order || p.rows) return cudaErrorInvalidValue;
+      if (block == 64) return launch_tworays<128, 3, 8>(p, n, stream);   // block=64 selects 3 resident blocks
+      if (block == 256) return launch_tworays<128, 5, 8>(p, n, stream);  // block=256 selects 5
+      return launch_tworays<128, 4, 8>(p, n, stream);
+    case kVariantPersistAggTally:
+      return launch_persist<128, kFetchPolicyAgg, 7, 8>(p, n, stream);
+    case kVariantGatherAggTally:
+      return launch_persist<128, kFetchPolicyL1Agg, 6, 8, true, 40>(p, n, stream);
     case kVariantPersistBulkOcc7:
       return launch_persist<128, kFetchBulk, 7>(p, n, stream);
     case kVariantPackedL1:

@@ -40,6 +40,24 @@ __device__ __forceinline__ void tally_add(double *ptr, double v) {
   asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(ptr), "d"(v), "l"(pol) : "memory");
 }
 #define PTB_TALLY_ADD(ptr, v) tally_add((ptr), (v))
+// Experiment (north_star: "warp-aggregated atomicAdd to cut contention"): lanes of the warp that tally
+// into the same tet in this step are found with match.any, their contributions are summed with
+// shuffles and one lane issues the reduction.  Called by every converged lane; `on` = this lane has
+// something to add.  Measured in profiles/r02 (variants 28, 29); not used by the product kernels.
+__device__ __forceinline__ void tally_add_aggregated(double *flux, int32_t e, double v, bool on) {
+  const unsigned act = __activemask();
+  const int lane = threadIdx.x & 31;
+  unsigned peers = __match_any_sync(act, on ? e : -1 - lane);  // lanes with nothing to add match only themselves
+  const int leader = __ffs(peers) - 1;
+  double sum = 0.0;
+  unsigned m = peers;
+  while (__any_sync(act, m != 0)) {
+    const int src = m ? __ffs(m) - 1 : lane;
+    const double x = __shfl_sync(act, v, src);
+    if (m) { sum += x; m &= m - 1; }
+  }
+  if (on && lane == leader) tally_add(flux + e, sum);
+}
 #else
 #define PTB_LDG(p) (*(p))
 #define PTB_TALLY_ADD(ptr, v) (*(ptr) += (v))  // test-only host build is single threaded
@@ -406,11 +424,16 @@ PTB_HD void end_ray(const WalkParams &P, int i, Ray &r, bool reached, double tne
 }
 
 // Functor body for one crossing, given the tracer's answer (texit, next).
-template <bool kReloadTarget = false>
+template <bool kReloadTarget = false, bool kAggregateTally = false>
 PTB_HD void advance(const WalkParams &P, int i, Ray &r, double texit, int32_t next, int32_t back,
                     Counters &c, bool writer) {
   const bool reached = !(texit < 1.0);  // last_exit == -1: destination inside this tet
   const double tnew = reached ? 1.0 : fmax(texit, r.tcur);
+#if defined(__CUDA_ARCH__)
+  if constexpr (kAggregateTally) {
+    tally_add_aggregated(P.flux, r.e, (tnew - r.tcur) * r.wl, r.stage == kStageTally && writer);
+  } else
+#endif
   if (r.stage == kStageTally && writer)  // EvaluateFlux (Impl.cpp:362-379)
     PTB_TALLY_ADD(P.flux + r.e, (tnew - r.tcur) * r.wl);
   const bool hull = !reached && next < 0;  // next_elems == -1 (Impl.cpp:270-271)

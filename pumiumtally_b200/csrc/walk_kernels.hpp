@@ -23,6 +23,7 @@ enum WalkVariant : int {
   kVariantPersistBulk = 6,           // 4 with tet records fetched by cp.async.bulk into smem rows
   kVariantPersistPolicy128Occ8 = 7,  // 5 compiled for 8 resident blocks (64 registers)
   kVariantPersistRefill8 = 8,        // 4, refilling only when >= 8 lanes are idle (default, mesh <~ 2x L2)
+  kVariantPersistRefill8Occ8 = 9,    // 8 compiled for 8 resident blocks (64 registers) -- re-test after entry-face elision
   kVariantPersistBulkOcc7 = 13,      // 6 compiled for 7 resident blocks
   kVariantPersistGather = 15,        // 8 on spatially binned particles (order[] from launch_bin_particles)
   kVariantPersistGatherL1 = 16,      // 15 with L1-allocating tet loads (default, mesh >> L2)
@@ -34,7 +35,10 @@ enum WalkVariant : int {
   kVariantPacked = 24,      // 8 on a packed, spatially sorted copy of the flying particles' inputs (bin + pack pass)
   kVariantPackedL1 = 25,    // 24 with L1-allocating tet loads (neighbouring lanes share records once particles are sorted)
   kVariantPackedL1Occ6 = 26,
-  kNumVariants = 27
+  kVariantTwoRays = 27,        // 8 with two rays per lane in flight (software-pipelined walk)
+  kVariantPersistAggTally = 28,  // 8 with the warp-aggregated tally (match.any + shuffles)
+  kVariantGatherAggTally = 29,   // 16 with the warp-aggregated tally
+  kNumVariants = 30
 };
 
 

@@ -185,7 +185,9 @@ __device__ __forceinline__ int begin_from_row(const WalkParams &P, const PackedR
 //      spatial order and neighbouring lanes/warps revisit the same records)
 //   6  compact layout + edge-function exit test (walk_compact.cuh): one 32-byte TetLinks sector and
 //      one 32-byte vertex per crossing, both L2-resident; degenerate rays finish on the plane records
-enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3, kFetchPolicyL1 = 5, kFetchEdge = 6 };
+//   7, 8  as 1 and 5 with the warp-aggregated tally of walk_core.cuh (experiment)
+enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3, kFetchPolicyL1 = 5, kFetchEdge = 6,
+             kFetchPolicyAgg = 7, kFetchPolicyL1Agg = 8 };
 
 __device__ __forceinline__ uint64_t l2_policy_keep() {
   uint64_t p;
@@ -215,10 +217,10 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void *src, uin
 template <int FETCH>
 __device__ __forceinline__ void load_face(const double *p, uint64_t pol, double &a, double &b,
                                           double &c, double &d) {
-  if constexpr (FETCH == kFetchPolicy)
+  if constexpr (FETCH == kFetchPolicy || FETCH == kFetchPolicyAgg)
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
         : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
-  else if constexpr (FETCH == kFetchPolicyL1)
+  else if constexpr (FETCH == kFetchPolicyL1 || FETCH == kFetchPolicyL1Agg)
     asm volatile("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
         : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p), "l"(pol));
   else if constexpr (FETCH == kFetchPolicy128)
@@ -316,7 +318,7 @@ __device__ __forceinline__ void plane_step(const WalkParams &P, int my_i, Ray &r
     face_payload(q3[0], q3[1], q3[2], q3[3], r.e, 3, nb, bk);
     scan_face(sc, q3[0], q3[1], q3[2], q3[3], nb, bk, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
   }
-  advance(P, my_i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
+  advance<false, FETCH == kFetchPolicyAgg || FETCH == kFetchPolicyL1Agg>(P, my_i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
 }
 
 // ---- compact layout (kFetchEdge) ----------------------------------------------------------

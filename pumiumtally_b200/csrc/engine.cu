@@ -87,6 +87,10 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
                                       mesh_.centroid0[2], mesh_.start_elem, compute_), "init particles");
   cuda_or_throw(cudaStreamSynchronize(compute_), "init sync");
   build_seed_grid();
+  use_seed_grid_ = mesh_.hull_convex;  // seed_grid_mode_ 1: only where it is equivalent to the reference's walk
+  if (!mesh_.hull_convex)
+    printf("[INFO] pumitally-b200: the mesh hull is not convex: relocation walks go the reference's way (no seed-grid "
+           "shortcut; option seed_grid=2 forces it)\n");
   variant_ = choose_variant();
   if (const char *env = std::getenv("PUMITALLY_REGISTER_HOST")) register_host_ = std::atoi(env) != 0;
   // the packed records are only needed on the device from here on
@@ -357,7 +361,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
     SeedGrid bin_grid = grid_;
     if (!morton_) bin_grid.cell_rank = nullptr;
     PTB_CUDA_OK(launch_bin_pack_particles(bin_grid, d_origin, d_dest, d_weights, d_flying, d_state_, begin, end,
-                                          d_pcell_, d_cell_count_, d_cell_sums_, d_rows_ + begin, wc, stream));
+                                          d_pcell_, d_cell_count_, d_cell_sums_, d_rows_ + begin, wc, bin_midpoint_, stream));
     p.rows = d_rows_ + begin;
     p.work_count = wc;
     last_work_count_ = wc;
@@ -372,7 +376,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
     SeedGrid bin_grid = grid_;
     if (!morton_) bin_grid.cell_rank = nullptr;
     p.claim_run = claim_run_;
-    PTB_CUDA_OK(launch_bin_particles(bin_grid, key, d_state_, d_flying, begin, end, d_pcell_, d_cell_count_,
+    PTB_CUDA_OK(launch_bin_particles(bin_grid, key, d_state_, (bin_midpoint_ && d_dest) ? d_dest : nullptr, d_flying, begin, end, d_pcell_, d_cell_count_,
                                      d_cell_sums_, d_order_ + begin, wc, stream));
     p.order = d_order_ + begin;
     p.work_count = wc;
@@ -1063,7 +1067,10 @@ int64_t Engine::get_option(const std::string &name) const {
   if (name == "autotune") return autotune_ ? 1 : 0;
   if (name == "block") return block_;
   if (name == "chunk") return chunk_;
-  if (name == "seed_grid") return use_seed_grid_ ? 1 : 0;
+  if (name == "seed_grid") return seed_grid_mode_;
+  if (name == "seed_grid_active") return use_seed_grid_ ? 1 : 0;
+  if (name == "hull_convex") return mesh_.hull_convex ? 1 : 0;
+  if (name == "bin_midpoint") return bin_midpoint_ ? 1 : 0;
   if (name == "max_iters") return max_iters_;
   if (name == "l2_fetch") {
     size_t g = 0;
@@ -1118,7 +1125,9 @@ int Engine::set_option(const std::string &name, int64_t v) {
     if (v < 1024) return 1;
     chunk_ = int32_t(std::min<int64_t>(v, INT_MAX)) & ~1023;  // keeps every range 16-byte aligned
   } else if (name == "seed_grid") {
-    use_seed_grid_ = v != 0;
+    if (v < 0 || v > 2) return 1;
+    seed_grid_mode_ = int(v);
+    use_seed_grid_ = v == 2 || (v == 1 && mesh_.hull_convex);
   } else if (name == "register_host") {
     register_host_ = v != 0;
   } else if (name == "max_iters") {  // crossing limit per walk (the tracer's loop limit); 0 = number of tets + 16
@@ -1136,6 +1145,8 @@ int Engine::set_option(const std::string &name, int64_t v) {
   } else if (name == "host_threads") {  // workers of the staging pool; before the first host-pointer call
     if (v < 1 || v > 256 || stager_) return 1;
     host_threads_ = int(v);
+  } else if (name == "bin_midpoint") {  // binning key: cell of the track's midpoint instead of its start
+    bin_midpoint_ = v != 0;
   } else if (name == "morton") {
     morton_ = v != 0;
   } else if (name == "claim_run") {

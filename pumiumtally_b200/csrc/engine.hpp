@@ -113,10 +113,17 @@ class Engine {
   void begin_move();
   int block_ = 128;
   int32_t chunk_ = 1 << 20;  // particles per H2D/compute pipeline stage
+  // Seed grid for relocation / localisation.  The reference walks straight from the particle's old
+  // position to the new one and stops at the hull if that segment leaves the mesh -- on a mesh with
+  // concavities or voids even when the new position is inside.  Starting from a seed cell instead
+  // reaches it, which is a different (better, but different) answer, so by default the shortcut is
+  // used only when the hull is convex (seed_grid_mode_ 1); 0 = never, 2 = always.
   bool use_seed_grid_ = true;
+  int seed_grid_mode_ = 1;
   int32_t max_iters_ = 0;  // crossing limit per walk; 0 = ntets + 16
   bool morton_ = true;    // binning key: Morton rank of the cell (matches the tet storage order) instead of its z-major index
   int claim_run_ = 4;     // chunks per ticket in gather mode
+  bool bin_midpoint_ = false;  // binning key: cell of the track's midpoint instead of its start (experiment, c5)
 
   // device memory
   TetRecord *d_tets_ = nullptr;
@@ -184,7 +191,9 @@ class Engine {
   int ensure_patch_buffers(int nchunks);
   int move_direct(const double *origin, const double *dest, int8_t *flying, const double *weights, int nchunks);
   // Page-locked caller arrays (pinned by the caller, or by option register_host): see move_pinned().
-  bool pinned_path_ = true;
+  // Off by default: on the measured box the positions travelling back (24 B per particle, device->host)
+  // slow the uploads down more than the saved host work buys (profiles/r02/README.md).
+  bool pinned_path_ = false;
   double *h_pos_ = nullptr;            // pinned mirror of the device's particle positions [3N]
   bool pos_mirror_valid_ = false;
   cudaStream_t d2h_ = nullptr;

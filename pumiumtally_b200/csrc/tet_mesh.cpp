@@ -3,6 +3,7 @@
 #include "tet_mesh.hpp"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -261,6 +262,72 @@ bool HostMesh::finalize(std::string *err) {
       }
       i = j;
     }
+  }
+
+  // ---- is the hull convex? (tet_mesh.hpp) --------------------------------------
+  {
+    struct HullEdge { int32_t a, b, opp; int64_t face; };  // edge (a<b) of a hull face, its third vertex, the face
+    std::vector<HullEdge> edges;
+    std::vector<std::array<int32_t, 3>> hull_faces;
+    for (int64_t e = 0; e < ntets; ++e)
+      for (int f = 0; f < 4; ++f)
+        if (t2t[4 * e + f] < 0) {
+          int32_t v[3];
+          int k = 0;
+          for (int i = 0; i < 4; ++i)
+            if (i != f) v[k++] = t2v[4 * e + i];
+          const int64_t id = int64_t(hull_faces.size());
+          hull_faces.push_back({v[0], v[1], v[2]});
+          for (int q = 0; q < 3; ++q) {
+            const int32_t a = v[q], b = v[(q + 1) % 3], o = v[(q + 2) % 3];
+            edges.push_back(HullEdge{std::min(a, b), std::max(a, b), o, id});
+          }
+        }
+    std::sort(edges.begin(), edges.end(), [](const HullEdge &x, const HullEdge &y) {
+      return x.a != y.a ? x.a < y.a : (x.b != y.b ? x.b < y.b : x.face < y.face);
+    });
+    // outward normal of a hull face = away from the tet's fourth vertex; found again from the face id
+    std::vector<double> normal(3 * hull_faces.size());
+    {
+      size_t id = 0;
+      for (int64_t e = 0; e < ntets; ++e)
+        for (int f = 0; f < 4; ++f)
+          if (t2t[4 * e + f] < 0) {
+            const auto &hf = hull_faces[id];
+            const double *A = &coords[3 * size_t(hf[0])], *B = &coords[3 * size_t(hf[1])], *C = &coords[3 * size_t(hf[2])];
+            const double *P = &coords[3 * size_t(t2v[4 * e + f])];
+            double ab[3], ac[3], n[3];
+            for (int d = 0; d < 3; ++d) { ab[d] = B[d] - A[d]; ac[d] = C[d] - A[d]; }
+            n[0] = ab[1] * ac[2] - ab[2] * ac[1]; n[1] = ab[2] * ac[0] - ab[0] * ac[2]; n[2] = ab[0] * ac[1] - ab[1] * ac[0];
+            const double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            const double side = n[0] * (P[0] - A[0]) + n[1] * (P[1] - A[1]) + n[2] * (P[2] - A[2]);
+            for (int d = 0; d < 3; ++d) normal[3 * id + d] = (side > 0 ? -n[d] : n[d]) / (len > 0 ? len : 1.0);
+            ++id;
+          }
+    }
+    bool convex = true;
+    double diag = 0.0;
+    for (int d = 0; d < 3; ++d) diag += (bbox_hi[d] - bbox_lo[d]) * (bbox_hi[d] - bbox_lo[d]);
+    const double tol = 1e-9 * std::sqrt(diag);
+    for (size_t i = 0; i < edges.size() && convex;) {
+      size_t j = i + 1;
+      while (j < edges.size() && edges[j].a == edges[i].a && edges[j].b == edges[i].b) ++j;
+      if (j - i != 2) {
+        convex = false;  // an edge where more than two hull faces meet: hull components touching
+      } else {
+        // the third vertex of each face must not lie outside the other face's plane
+        const double *A = &coords[3 * size_t(edges[i].a)];
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const HullEdge &mine = edges[i + s2], &other = edges[i + 1 - s2];
+          const double *O = &coords[3 * size_t(other.opp)];
+          const double *n = &normal[3 * size_t(mine.face)];
+          if (n[0] * (O[0] - A[0]) + n[1] * (O[1] - A[1]) + n[2] * (O[2] - A[2]) > tol) convex = false;
+        }
+      }
+      i = j;
+    }
+    // one component: a second closed surface (a void) is concave all over, so it fails the test above
+    hull_convex = convex;
   }
 
   // ---- mesh-centred coordinates (tet_mesh.hpp) ---------------------------------

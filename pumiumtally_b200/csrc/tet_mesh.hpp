@@ -102,6 +102,11 @@ struct HostMesh {
   // (x - center) before walking.  The 44-bit plane offsets then locate a crossing to ~6e-14 of the
   // mesh EXTENT instead of the largest absolute coordinate, so the tally keeps its digits however far
   // from the origin the mesh sits (only the granularity of the caller's own doubles remains).
+  // Is the hull one closed, everywhere locally convex surface?  (Every hull edge is shared by two hull
+  // faces whose dihedral angle, seen from inside, is <= 180 degrees, and there is one hull component.)
+  // Only then does "walk straight from A to B inside the mesh" reach every B in the mesh, which is what
+  // the seed-grid shortcut of the relocation walk relies on to be equivalent to the reference.
+  bool hull_convex = true;
   double center[3] = {0, 0, 0};
   std::vector<double> ccoords;  // [3*nverts] coords - center, as the kernels compute it (fl(x - c))
 

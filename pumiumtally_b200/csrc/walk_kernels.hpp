@@ -45,8 +45,9 @@ enum WalkVariant : int {
 cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_t stream);
 bool walk_variant_available(int variant);  // compiled into this library?
 // origin == nullptr: the binning key is the stored position (state)
+// mid != nullptr: the key is the midpoint of (start, mid[i]) -- pass the dest array
 cudaError_t launch_bin_particles(const SeedGrid &g, const double *origin, const ParticleState *state,
-                                 const int8_t *flying, int32_t begin, int32_t end, int32_t *pcell, unsigned int *count,
+                                 const double *mid, const int8_t *flying, int32_t begin, int32_t end, int32_t *pcell, unsigned int *count,
                                  unsigned int *sums, int32_t *order, unsigned int *work_count,
                                  cudaStream_t stream);
 // Like launch_bin_particles, but instead of the id list the scatter pass writes one PackedRow per
@@ -55,7 +56,7 @@ cudaError_t launch_bin_pack_particles(const SeedGrid &g, const double *origin, c
                                       const double *weights, const int8_t *flying, const ParticleState *state,
                                       int32_t begin, int32_t end, int32_t *pcell, unsigned int *count,
                                       unsigned int *sums, PackedRow *rows, unsigned int *work_count,
-                                      cudaStream_t stream);
+                                      bool midpoint_key, cudaStream_t stream);
 cudaError_t launch_seed_points(const SeedGrid &g, double *xyz, cudaStream_t stream);
 cudaError_t launch_seed_finalize(const double *xyz, const ParticleState *state, int32_t *cell_tet,
                                  int32_t ncell, cudaStream_t stream);

@@ -28,7 +28,8 @@ for mode in modes:
         if len(parts) > 1 and int(parts[1]) > 0: eng.set_option("host_threads", int(parts[1]))
         if len(parts) > 2 and int(parts[2]) > 0: eng.set_option("chunk", int(parts[2]))
         if kind == "registered": eng.set_option("register_host", 1)   # pageable arrays, page-locked by the engine
-        if kind == "pinned_staged": eng.set_option("pinned_path", 0)  # pinned arrays through the staging slots
+        if kind in ("registered", "pinned"): eng.set_option("pinned_path", 1)  # DMA from the caller's arrays, positions mirrored back
+        if kind == "pinned_staged": eng.set_option("pinned_path", 0)  # pinned arrays through the staging slots (the default)
     else:
         eng.set_option("host_path", 0)
         eng.set_option("register_host", 1 if kind == "direct_registered" else 0)

@@ -1,5 +1,5 @@
 """Kernel-variant sweep on device-resident batches: ms per move and segments/s per variant.
-Usage: [PUMITALLY_LIB=pumiumtally_b200/lib/libpumitally_exp.so] python scripts/exp_variants.py <config> <particles|0> v[:block] ..."""
+Usage: [PUMITALLY_LIB=pumiumtally_b200/lib/libpumitally_exp.so] python scripts/exp_variants.py <config> <particles|0> v[:block[:opt=val,opt=val]] ..."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -13,7 +13,8 @@ box = tuple(float(c) for c in cells)
 dev = torch.device("cuda", 0)
 steps, warm = int(os.environ.get("EXP_STEPS", 8)), 3
 for spec in sys.argv[3:]:
-    v, _, b = spec.partition(":")
+    parts = spec.split(":")
+    v, b, opts = parts[0], (parts[1] if len(parts) > 1 else ""), (parts[2] if len(parts) > 2 else "")
     wl = SyntheticWorkload(box=box, num_particles=n, mean_length=cfg["mean_length"], mu_min=cfg["mu_min"], backend="torch", device=dev)
     init = wl.initial_positions().contiguous()
     eng = PumiTally.from_spec(f"box:{cells[0]},{cells[1]},{cells[2]}", n, device=0)
@@ -23,6 +24,8 @@ for spec in sys.argv[3:]:
         print(json.dumps({"variant": spec, "error": "not in this library"})); continue
     eng.set_option("autotune", 0)
     if b: eng.set_option("block", int(b))
+    for kv in filter(None, opts.split(",")):
+        k_, v_ = kv.split("="); eng.set_option(k_, int(v_))
     stream = torch.cuda.current_stream().cuda_stream
     eng.copy_initial_position_device(init.data_ptr(), stream)
     ms = []

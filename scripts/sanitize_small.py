@@ -7,7 +7,7 @@ from helpers import box_case, run_workload
 from oracle.oracle import OraclePumiTally
 from pumiumtally_b200.tally import PumiTally
 
-variants = [int(v) for v in sys.argv[1:]] or [8, 16, 6, 0]
+variants = [int(v) for v in sys.argv[1:]] or [8, 16, 24, 0]
 for v in variants:
     coords, t2v, wl = box_case((6, 6, 5), 6000)
     e = PumiTally.from_arrays(coords, t2v, wl.n)

@@ -99,6 +99,7 @@ def emul_lib(fma=None):
         L.ptb_emul_degenerate_rays.restype = C.c_ulonglong
         L.ptb_emul_degenerate_rays.argtypes = [C.c_void_p]
         L.ptb_emul_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ptb_emul_hull_convex.argtypes = [C.c_void_p]
         _EMUL[fma] = L
     return _EMUL[fma]
 
@@ -126,6 +127,10 @@ class HostEmulTally:
         if layout == "edge" and self._L.ptb_emul_set_layout(self._h, 1) != 0:
             raise RuntimeError("compact layout rejected")
         self.grid_valid_cells = self._L.ptb_emul_build_grid(self._h) if seed_grid else 0
+
+    @property
+    def hull_convex(self):
+        return bool(self._L.ptb_emul_hull_convex(self._h))
 
     def grid_dims(self):
         d = np.zeros(3, dtype=np.int32)
@@ -174,6 +179,49 @@ class HostEmulTally:
         v = np.empty(self.num_elements)
         self._L.ptb_emul_mesh(self._h, c.ctypes.data, t.ctypes.data, v.ctypes.data)
         return c, t, v
+
+
+def carve(coords, t2v, keep):
+    """Sub-mesh of the tets selected by the boolean mask `keep`, vertices renumbered."""
+    t = t2v[keep]
+    verts, inv = np.unique(t.ravel(), return_inverse=True)
+    return np.ascontiguousarray(coords[verts]), inv.reshape(-1, 4).astype(np.int32)
+
+
+def l_shaped_mesh(nx=4, ny=4, nz=2):
+    """Kuhn box with one quadrant (x > nx/2 and y > ny/2) removed: an L-shaped prism, hull not convex."""
+    coords, t2v = kuhn_box(nx, ny, nz)
+    c = coords[t2v].mean(1)
+    return carve(coords, t2v, ~((c[:, 0] > nx / 2) & (c[:, 1] > ny / 2)))
+
+
+def non_convex_relocation_scenario(make_engine, expect_reference=True):
+    """Particles re-sourced across the notch of an L-shaped mesh.  The reference walks straight from the
+    old position to the new one and stops at the hull when that segment leaves the mesh, the flight then
+    starts from where the relocation stopped (PumiTallyImpl.cpp:71-145) -- so must this engine, unless the
+    seed-grid shortcut is forced on, in which case the new position is reached."""
+    coords, t2v = l_shaped_mesh()
+    n = 400
+    rng = np.random.default_rng(2)
+    a = np.column_stack([rng.uniform(2.2, 3.8, n), rng.uniform(0.2, 1.8, n), rng.uniform(0.2, 1.8, n)])  # one arm
+    b = np.column_stack([rng.uniform(0.2, 1.8, n), rng.uniform(2.2, 3.8, n), rng.uniform(0.2, 1.8, n)])  # the other arm
+    d = b + rng.normal(0, 0.2, (n, 3))
+    d[:, 2] = np.clip(d[:, 2], 0.05, 1.95)
+    w = rng.uniform(0.5, 1.0, n)
+    eng, orc = make_engine(coords, t2v, n), OraclePumiTally(coords, t2v, n)
+    for e in (eng, orc):
+        e.CopyInitialPosition(a.reshape(-1).copy())
+        e.MoveToNextLocation(b.reshape(-1).copy(), d.reshape(-1).copy(), np.ones(n, dtype=np.int8), w.copy())
+    crosses_notch = (orc.positions != d).any(1)  # the oracle (= the reference's walk) did not get there
+    assert crosses_notch.sum() > n // 4
+    if expect_reference:
+        assert_flux_close(eng.flux, orc.flux, "non-convex relocation")
+        np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
+        np.testing.assert_allclose(eng.positions, orc.positions, rtol=0, atol=1e-12)
+    else:
+        reached = (eng.positions == d).all(1)
+        assert reached[crosses_notch].mean() > 0.9  # the shortcut gets (nearly) everybody to the new position
+    return eng, orc
 
 
 def box_case(cells, n, **kw):

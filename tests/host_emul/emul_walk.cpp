@@ -159,6 +159,8 @@ void ptb_emul_grid_dims(void *h, int32_t *out) {
   auto *e = static_cast<Emul *>(h);
   out[0] = e->grid.nx; out[1] = e->grid.ny; out[2] = e->grid.nz;
 }
+int ptb_emul_hull_convex(void *h) { return static_cast<Emul *>(h)->mesh.hull_convex ? 1 : 0; }
+
 void ptb_emul_sizes(void *h, int64_t *out) {
   auto *e = static_cast<Emul *>(h);
   out[0] = e->mesh.nverts; out[1] = e->mesh.ntets;

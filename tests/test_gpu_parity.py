@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 from helpers import (ROOT, assert_flux_close, box_case, edge_case_scenario, lattice_track_scenario,
-                     non_finite_input_scenario, run_workload, unstructured_special_point_scenario)
+                     non_convex_relocation_scenario, non_finite_input_scenario, run_workload,
+                     unstructured_special_point_scenario)
 from oracle.oracle import OraclePumiTally
 from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, save_raw_mesh, tet_volumes
 from pumiumtally_b200.tally import PumiTally
@@ -35,7 +36,7 @@ def gpu_engine(variant, block=128, chunk=None, seed_grid=True):
         e = PumiTally.from_arrays(coords, t2v, n)
         e.set_option("variant", variant)
         e.set_option("block", block)
-        e.set_option("seed_grid", 1 if seed_grid else 0)
+        e.set_option("seed_grid", int(seed_grid))  # 0 never, 1 where the hull is convex, 2 always
         if chunk:
             e.set_option("chunk", chunk)
         return e
@@ -70,7 +71,7 @@ def test_out_of_mesh_origin_falls_back_to_reference_walk(seed_grid):
     n = 4096
     rng = np.random.default_rng(5)
     init = rng.uniform(0.2, 3.8, size=(n, 3))
-    eng, orc = gpu_engine(3, seed_grid=seed_grid)(coords, t2v, n), OraclePumiTally(coords, t2v, n)
+    eng, orc = gpu_engine(8, seed_grid=seed_grid)(coords, t2v, n), OraclePumiTally(coords, t2v, n)
     for e in (eng, orc):
         e.CopyInitialPosition(init.reshape(-1).copy())
     np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
@@ -83,6 +84,19 @@ def test_out_of_mesh_origin_falls_back_to_reference_walk(seed_grid):
     np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
     np.testing.assert_allclose(eng.positions, orc.positions, atol=1e-12)
     assert eng.stats()["lost"] == 0
+
+
+@pytest.mark.parametrize("variant", [0, 8, 16, 24])
+def test_non_convex_mesh_relocation_is_the_reference_walk_unless_the_shortcut_is_forced(variant):
+    """On a mesh whose hull is not convex the engine does not take the seed-grid shortcut on its own
+    (ADVICE r01): relocation across the notch of an L-shaped mesh stops at the hull exactly like the
+    reference's straight walk; seed_grid=2 forces the shortcut and the particles arrive."""
+    eng, _ = non_convex_relocation_scenario(gpu_engine(variant, seed_grid=1))
+    assert eng.get_option("hull_convex") == 0 and eng.get_option("seed_grid_active") == 0
+    eng2, _ = non_convex_relocation_scenario(gpu_engine(variant, seed_grid=2), expect_reference=False)
+    assert eng2.get_option("seed_grid_active") == 1
+    convex = gpu_engine(variant)(*kuhn_box(2, 2, 2), 4)
+    assert convex.get_option("hull_convex") == 1 and convex.get_option("seed_grid_active") == 1
 
 
 def test_binning_groups_flying_particles_by_cell():
@@ -122,7 +136,7 @@ def test_seed_grid_cuts_relocation_work_not_results():
     res = []
     for sg in (False, True):
         wl_i = SyntheticWorkload(box=(12.0, 12.0, 12.0), num_particles=wl.n)
-        e = gpu_engine(3, seed_grid=sg)(coords, t2v, wl.n)
+        e = gpu_engine(8, seed_grid=sg)(coords, t2v, wl.n)
         e.CopyInitialPosition(wl_i.initial_positions().reshape(-1))
         for _ in range(3):
             o, d, f, w = wl_i.next_step()
@@ -382,6 +396,7 @@ def test_pinned_caller_path_matches_oracle(kind, variant):
     coords, t2v, wl = box_case((6, 6, 5), 60_007)
     n = wl.n
     e = gpu_engine(variant, chunk=8192)(coords, t2v, n)
+    e.set_option("pinned_path", 1)
     if kind == "registered":
         e.set_option("register_host", 1)
     orc = OraclePumiTally(coords, t2v, n)
@@ -430,6 +445,7 @@ def test_pinned_caller_path_every_origin_changed_and_none_changed():
     n = 30_000
     rng = np.random.default_rng(3)
     e = gpu_engine(8, chunk=4096)(coords, t2v, n)
+    e.set_option("pinned_path", 1)
     orc = OraclePumiTally(coords, t2v, n)
     pos = rng.uniform(0.05, 4.95, size=(n, 3))
     for x in (e, orc):

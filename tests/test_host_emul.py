@@ -8,8 +8,9 @@ import os
 import numpy as np
 import pytest
 
-from helpers import (HostEmulTally, assert_flux_close, box_case, edge_case_scenario, lattice_track_scenario,
-                     non_finite_input_scenario, run_workload, unstructured_special_point_scenario)
+from helpers import (HostEmulTally, assert_flux_close, box_case, carve, edge_case_scenario, l_shaped_mesh,
+                     lattice_track_scenario, non_convex_relocation_scenario, non_finite_input_scenario, run_workload,
+                     unstructured_special_point_scenario)
 from oracle.oracle import OraclePumiTally
 from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, tet_volumes
 from pumiumtally_b200.workload import SyntheticWorkload
@@ -456,3 +457,22 @@ def test_extreme_meshes_and_batches_parity(fma):
                 np.testing.assert_array_equal(eng.elem_ids, orc.elem_ids)
                 assert np.abs(eng.positions - orc.positions).max() <= 1e-9 * max(1.0, hi.max())
                 assert eng.stats()["lost"] == 0
+
+
+def test_hull_convexity_is_recognised():
+    """Convex: Kuhn boxes (also jittered inside), Delaunay meshes of a point cloud.  Not convex: an L-shaped
+    prism, a box with a void, two boxes touching along an edge."""
+    for c, t in (kuhn_box(3, 2, 2), jitter_interior(*kuhn_box(4, 3, 3), amplitude=0.2), delaunay_box(200, seed=4)):
+        assert HostEmulTally(c, t, 1).hull_convex
+    assert not HostEmulTally(*l_shaped_mesh(), 1).hull_convex
+    c, t = kuhn_box(5, 5, 5)
+    cen = c[t].mean(1)
+    void = (np.abs(cen - 2.5) < 0.5).all(1)
+    assert not HostEmulTally(*carve(c, t, ~void), 1).hull_convex
+    two = ((cen[:, 0] < 2) & (cen[:, 1] < 2)) | ((cen[:, 0] > 2) & (cen[:, 1] > 2))
+    assert not HostEmulTally(*carve(c, t, two), 1).hull_convex
+
+
+def test_relocation_across_a_concavity_follows_the_reference_walk():
+    """No seed grid in the host build by default: the plain walk is the reference's."""
+    non_convex_relocation_scenario(lambda c, t, n: HostEmulTally(c, t, n))

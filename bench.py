@@ -413,12 +413,18 @@ class GpuArm:
                                   "staged path: pinned per-particle slots refilled by the engine's worker pool, "
                                   "only changed origins travel"}
             if e2e_modes and pregen:
-                ks, kw = min(steps, 5), min(warmup, 2)
+                # side numbers: caller arrays the engine may page-lock (register_host=1, what an OpenMC
+                # integration sets: its vectors live for the whole run) with the engine choosing between
+                # staged and direct uploads; pinned caller arrays; and the direct paths on their own
+                ks, kw = min(steps, 6), min(warmup, 5)  # the automatic choice has probed both paths after 4 moves
+                modes = [("registered_auto", "pageable", {"register_host": 1})]
+                if world == 1:
+                    modes += [("pinned_buffers", "pinned", {}),
+                              ("direct_registered", "pageable", {"host_path": 0, "register_host": 1}),
+                              ("direct_pageable", "pageable", {"host_path": 0})]
                 out["e2e"]["other_modes"] = {
                     name: {k: v for k, v in run_e2e(kind, opts, ks, kw).items() if k != "host_threads"}
-                    for name, kind, opts in (("pinned_buffers", "pinned", {}),
-                                             ("direct_registered", "pageable", {"host_path": 0, "register_host": 1}),
-                                             ("direct_pageable", "pageable", {"host_path": 0}))}
+                    for name, kind, opts in modes}
         return out
 
     def cpu_baseline(self, cfg_name, n, nsteps):
@@ -460,7 +466,7 @@ def run_gpu(args, rank, local_rank, world):
     if world == 1 and cfg.get("gpus", 1) > 1 and not args.particles:
         n = cfg["particles"] // cfg["gpus"] if args.per_gpu_share else cfg["particles"]
     main = arm.measure(args.config, n, args.steps, args.warmup, e2e=not args.no_e2e,
-                       e2e_modes=not args.no_e2e_modes and world == 1, clocks=True)
+                       e2e_modes=not args.no_e2e_modes, clocks=True)
 
     # ---- the multi-GPU configurations BASELINE.json names, measured beside the headline ----------
     # c4 on 4 GPUs (1 M particles / 4), c5 on 8 GPUs (100 M particles / 8), and c5 strong scaling

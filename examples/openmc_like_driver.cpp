@@ -8,10 +8,12 @@
 //
 // Physics is a toy: isotropic flights with exponential lengths inside a box; a particle that leaks is
 // "absorbed" and re-sampled at a new source site, which is what exercises the relocate-to-origin phase.
-// Only <pumitally/PumiTally.h> and -lpumitally are needed.
+// Only <pumitally/PumiTally.h> and -lpumitally are needed for the reference's four calls; the optional
+// batches / per-source normalisation below (what the reference leaves as TODOs, PumiTallyImpl.h:170-171)
+// use the additive <pumitally/PumiTallyExtras.h>.
 //
 //   g++ -std=c++17 -I include examples/openmc_like_driver.cpp -L pumiumtally_b200/lib -lpumitally \
-//       -Wl,-rpath,$PWD/pumiumtally_b200/lib -o driver && ./driver box:20,20,20 1000000 20
+//       -Wl,-rpath,$PWD/pumiumtally_b200/lib -o driver && ./driver box:20,20,20 1000000 20 [inactive_batches]
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -21,6 +23,7 @@
 #include <vector>
 
 #include "pumitally/PumiTally.h"
+#include "pumitally/PumiTallyExtras.h"
 
 namespace {
 struct Rng {  // SplitMix64
@@ -38,6 +41,7 @@ int main(int argc, char **argv) {
   const std::string mesh = argc > 1 ? argv[1] : "box:20,20,20";
   const int n = argc > 2 ? std::atoi(argv[2]) : 100000;
   const int sweeps = argc > 3 ? std::atoi(argv[3]) : 10;
+  const int inactive = argc > 4 ? std::atoi(argv[4]) : 0;  // batches of `sweeps` sweeps run and discarded first
   double box[3] = {20, 20, 20};
   if (mesh.rfind("box:", 0) == 0) std::sscanf(mesh.c_str() + 4, "%lf,%lf,%lf", &box[0], &box[1], &box[2]);
 
@@ -52,8 +56,15 @@ int main(int argc, char **argv) {
   for (int i = 0; i < n; ++i) sample_site(&pos[3 * size_t(i)]);
   tally.CopyInitialPosition(pos.data(), 3 * n);  // process_init_events
 
+  // per-source-particle normalisation: divide the normalised flux by the total weight of the batch's first tracks
+  if (inactive > 0) pumitally::SetSourceNormalization(tally, 3);
   const auto t0 = std::chrono::steady_clock::now();
   long long flights = 0, leaks = 0;
+  for (int batch = 0; batch <= inactive; ++batch) {
+  if (batch > 0) {  // an inactive batch ends: discard its tally, keep the particles where they are
+    pumitally::ResetTally(tally);
+    flights = leaks = 0;
+  }
   for (int s = 0; s < sweeps; ++s) {  // process_advance_particle_events
     for (int i = 0; i < n; ++i) {
       double *p = &pos[3 * size_t(i)], *o = &origin[3 * size_t(i)], *d = &dest[3 * size_t(i)];
@@ -73,9 +84,11 @@ int main(int argc, char **argv) {
     }
     tally.MoveToNextLocation(origin.data(), dest.data(), flying.data(), weight.data(), 3 * n);
   }
+  }
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   tally.WriteTallyResults();  // openmc_simulation_finalize
-  std::printf("DRIVER_OK %lld flights (%lld leaked and re-sampled) in %d sweeps, %.3f s host loop + tally calls\n",
-              flights, leaks, sweeps, secs);
+  std::printf("DRIVER_OK %lld flights (%lld leaked and re-sampled) in %d sweeps, %.3f s host loop + tally calls, "
+              "source normalisation %.6f\n",
+              flights, leaks, sweeps, secs, pumitally_get_source_normalization(pumitally::engine_of(tally)));
   return 0;
 }

@@ -109,10 +109,11 @@ int pumitally_get_stats(pumitally_engine *e, pumitally_stats *out);
 int pumitally_set_output_name(pumitally_engine *e, const char *filename);
 /* Options: "variant" (-1 = the engine picks the walk kernel from the mesh size, the default; 0, 8,
  * 16, 24 = the kernels of this library), "block", "chunk" (particles per upload/compute pipeline
- * stage), "seed_grid", "morton", "claim_run", "host_path" (1 = default: host-pointer moves are
- * staged through pinned per-particle slots by a small worker pool and only the origins that
- * differ from the previous call's destinations travel; 0 = direct copies of all four arrays from
- * the caller's memory), "host_threads" (workers of that pool, before the first host-pointer call;
+ * stage), "seed_grid", "morton", "claim_run", "host_path" (1 = host-pointer moves are staged
+ * through pinned per-particle slots by a small worker pool and only the origins that differ from
+ * the previous call's destinations travel; 0 = direct copies of all four arrays from the caller's
+ * memory; 2 = default: staged, except that for page-locked caller arrays the engine times both and
+ * keeps the faster), "host_threads" (workers of that pool, before the first host-pointer call;
  * default: CPU quota / ranks per node - 1; environment: PUMITALLY_HOST_THREADS,
  * PUMITALLY_HOST_PIN=0 keeps them off the GPU's NUMA node), "register_host" (direct path only:
  * 1 = page-lock the caller's pageable buffers with cudaHostRegister the first time they are

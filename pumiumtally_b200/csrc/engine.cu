@@ -434,7 +434,7 @@ int Engine::copy_initial_position(const double *xyz, int32_t size) {
   // first move and its origins need not travel either.
   const double *src = xyz;
   double *d_xyz = d_origin_;
-  if (host_path_ == 1 && n_ > 0 && ensure_stage_buffers(xyz, size_t(size) * sizeof(double)) == 0) {
+  if (host_path_ != 0 && n_ > 0 && ensure_stage_buffers(xyz, size_t(size) * sizeof(double)) == 0) {
     HostPool *pool_ = &stager_->pool();
     const int T = pool_->size();
     const int64_t total = int64_t(size);
@@ -604,15 +604,34 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
     PTB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     chunk_events_.push_back(e);
   }
-  const bool staged = host_path_ == 1 && n_ > 0 && ensure_stage_buffers(dest, size_t(size) * sizeof(double)) == 0 &&
-                      ensure_patch_buffers(nchunks) == 0;
-  if (!staged) return move_direct(origin, dest, flying, weights, nchunks);
-  follow_caller_memory(dest, size_t(size) * sizeof(double));
   if (register_host_) {  // opt-in: page-lock the caller's arrays the first time they are seen
     maybe_register(origin, 3 * size_t(n_) * sizeof(double));
     maybe_register(dest, 3 * size_t(n_) * sizeof(double));
     maybe_register(weights, size_t(n_) * sizeof(double));
+    maybe_register(flying, size_t(n_));
   }
+  // host_path 2 (default): staged, except that page-locked caller arrays (which the direct path can DMA
+  // at the full PCIe rate without any host work) get the faster of the two, measured: moves 2-3 of every
+  // 256 go direct, the others staged until the upload spans of both are known.  Where the host is the
+  // scarce resource -- several ranks sharing one socket's memory system -- direct wins; with cores and
+  // bandwidth to spare, staged does.
+  bool want_staged = host_path_ != 0;
+  int probe = -1;
+  if (host_path_ == 2 && host_is_pinned(origin) && host_is_pinned(dest) && host_is_pinned(weights) && host_is_pinned(flying)) {
+    collect_upload_span();
+    const uint64_t k = host_moves_ % 256;
+    if (k == 0) { span_ms_[0] = span_ms_[1] = 0.0; span_n_[0] = span_n_[1] = 0; }
+    if (k >= 2 && k <= 3) probe = 1;
+    else if (k <= 1 || span_n_[0] == 0 || span_n_[1] == 0) probe = 0;
+    else probe = (span_ms_[1] / span_n_[1] < 0.95 * span_ms_[0] / span_n_[0]) ? 1 : 0;
+    want_staged = probe == 0;
+  }
+  ++host_moves_;
+  span_tag_ = probe;
+  const bool staged = want_staged && n_ > 0 && ensure_stage_buffers(dest, size_t(size) * sizeof(double)) == 0 &&
+                      ensure_patch_buffers(nchunks) == 0;
+  if (!staged) return move_direct(origin, dest, flying, weights, nchunks);
+  follow_caller_memory(dest, size_t(size) * sizeof(double));
   // Caller arrays that are page-locked (by the caller, or just above) need no copy into the staging
   // slots: dest and weights go to the device straight from them, and the origins are compared with
   // the device's own particle positions, which each move sends back (move_pinned).
@@ -842,20 +861,35 @@ int Engine::move_pinned(const double *origin, const double *dest, int8_t *flying
   return 0;
 }
 
+// Device time the previous host move's uploads took (first copy could start -> last copy done), credited to
+// the path that move used; feeds the staged-vs-direct choice for page-locked caller arrays.
+void Engine::collect_upload_span() {
+  if (span_tag_ < 0 || !ev_copy0_) return;
+  float ms = 0.f;
+  if (cudaEventSynchronize(ev_copy1_) == cudaSuccess && cudaEventElapsedTime(&ms, ev_copy0_, ev_copy1_) == cudaSuccess) {
+    span_ms_[span_tag_] += ms;
+    ++span_n_[span_tag_];
+  } else {
+    cudaGetLastError();
+  }
+  span_tag_ = -1;
+}
+
 // Direct path: every array is copied from the caller's memory as it is.
 int Engine::move_direct(const double *origin, const double *dest, int8_t *flying, const double *weights,
                         int nchunks) {
   mirror_valid_ = false;  // the staging slots do not see this move
   pos_mirror_valid_ = false;
-  maybe_register(origin, 3 * size_t(n_) * sizeof(double));
-  maybe_register(dest, 3 * size_t(n_) * sizeof(double));
-  maybe_register(weights, size_t(n_) * sizeof(double));
-  maybe_register(flying, size_t(n_));
   cudaEvent_t ev_prev_done = chunk_events_[nchunks], ev_fly = chunk_events_[nchunks + 1];
   PTB_CUDA_OK(cudaStreamSynchronize(copy_));  // staged copies of an earlier move
   staged_chunks_ = 0;
   PTB_CUDA_OK(cudaEventRecord(ev_prev_done, compute_));
   PTB_CUDA_OK(cudaStreamWaitEvent(copy_, ev_prev_done, 0));
+  if (!ev_copy0_) {
+    PTB_CUDA_OK(cudaEventCreate(&ev_copy0_));
+    PTB_CUDA_OK(cudaEventCreate(&ev_copy1_));
+  }
+  PTB_CUDA_OK(cudaEventRecord(ev_copy0_, copy_));
   PTB_CUDA_OK(cudaMemcpyAsync(d_flying_, flying, size_t(n_), cudaMemcpyHostToDevice, copy_));
   PTB_CUDA_OK(cudaEventRecord(ev_fly, copy_));
   for (int k = 0; k < nchunks; ++k) {
@@ -868,7 +902,9 @@ int Engine::move_direct(const double *origin, const double *dest, int8_t *flying
     PTB_CUDA_OK(cudaStreamWaitEvent(compute_, chunk_events_[k], 0));
     if (launch_range(d_origin_, d_dest_, d_flying_, d_weights_, b, e, compute_, true)) return 1;
   }
+  PTB_CUDA_OK(cudaEventRecord(ev_copy1_, copy_));
   h2d_bytes_ += 57.0 * double(n_);
+  stage_sent_bytes_ = 57.0 * double(n_);
   // reset the caller's flags once they are on the device (PumiTallyImpl.cpp:169-172)
   PTB_CUDA_OK(cudaEventSynchronize(ev_fly));
   if (n_) std::memset(flying, 0, size_t(n_));
@@ -1079,6 +1115,7 @@ int64_t Engine::get_option(const std::string &name) const {
   if (name == "allreduce_us") return int64_t(allreduce_ms_ * 1e3);  // device time of the last batch-end exchange
   if (name == "d2h_bytes") return int64_t(d2h_bytes_);  // particle positions sent back by the pinned-caller path, cumulative
   if (name == "host_path") return host_path_;
+  if (name == "host_path_last") return span_tag_ == 1 ? 0 : 1;  // path of the last host move: 1 staged, 0 direct
   if (name == "pinned_path") return pinned_path_ ? 1 : 0;
   if (name == "position_mirror") return pos_mirror_valid_ ? 1 : 0;  // the last host move took the pinned-caller path
   if (name == "host_threads") return stager_ ? stager_->threads() : host_threads_;
@@ -1136,8 +1173,8 @@ int Engine::set_option(const std::string &name, int64_t v) {
   } else if (name == "l2_fetch") {  // bytes an L2 miss fetches from DRAM: 32, 64 or 128 (device-wide limit)
     if (v != 32 && v != 64 && v != 128) return 1;
     if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(v)) != cudaSuccess) { cudaGetLastError(); return 1; }
-  } else if (name == "host_path") {  // 1 = staged through the pinned slots (default), 0 = direct copies
-    if (v != 0 && v != 1) return 1;
+  } else if (name == "host_path") {  // 2 = automatic (default), 1 = staged through the pinned slots, 0 = direct copies
+    if (v < 0 || v > 2) return 1;
     host_path_ = int(v);
     if (host_path_ == 0) mirror_valid_ = false;
   } else if (name == "pinned_path") {  // 0 = page-locked caller arrays also go through the staging slots

@@ -169,7 +169,12 @@ class Engine {
   // against; only origins that changed travel, as a patch list applied to the device's copy of the
   // previous destinations.  Invariant between moves (mirror_valid_): h_dest_ == the device array
   // d_dest_, bit for bit.
-  int host_path_ = 1;                 // 1 staged (default), 0 direct copies from the caller's arrays
+  int host_path_ = 2;                 // 2 automatic (default), 1 staged, 0 direct copies from the caller's arrays
+  uint64_t host_moves_ = 0;           // host-pointer moves so far (schedule of the staged-vs-direct probe)
+  double span_ms_[2] = {0.0, 0.0};    // upload span per path: [0] staged, [1] direct
+  int span_n_[2] = {0, 0};
+  int span_tag_ = -1;                 // path of the move whose span has not been collected yet
+  void collect_upload_span();
   int host_threads_ = 0;              // 0 = default_host_threads() - 1
   std::unique_ptr<HostStager> stager_;  // worker pool + per-chunk stage pass
   void *stage_base_ = nullptr;

@@ -200,13 +200,13 @@ def non_convex_relocation_scenario(make_engine, expect_reference=True):
     old position to the new one and stops at the hull when that segment leaves the mesh, the flight then
     starts from where the relocation stopped (PumiTallyImpl.cpp:71-145) -- so must this engine, unless the
     seed-grid shortcut is forced on, in which case the new position is reached."""
-    coords, t2v = l_shaped_mesh()
+    coords, t2v = l_shaped_mesh(16, 16, 4)  # fine enough for the far-relocation threshold of the seed grid
     n = 400
     rng = np.random.default_rng(2)
-    a = np.column_stack([rng.uniform(2.2, 3.8, n), rng.uniform(0.2, 1.8, n), rng.uniform(0.2, 1.8, n)])  # one arm
-    b = np.column_stack([rng.uniform(0.2, 1.8, n), rng.uniform(2.2, 3.8, n), rng.uniform(0.2, 1.8, n)])  # the other arm
+    a = np.column_stack([rng.uniform(9.2, 15.8, n), rng.uniform(0.2, 6.8, n), rng.uniform(0.2, 3.8, n)])  # one arm
+    b = np.column_stack([rng.uniform(0.2, 6.8, n), rng.uniform(9.2, 15.8, n), rng.uniform(0.2, 3.8, n)])  # the other arm
     d = b + rng.normal(0, 0.2, (n, 3))
-    d[:, 2] = np.clip(d[:, 2], 0.05, 1.95)
+    d[:, 2] = np.clip(d[:, 2], 0.05, 3.95)
     w = rng.uniform(0.5, 1.0, n)
     eng, orc = make_engine(coords, t2v, n), OraclePumiTally(coords, t2v, n)
     for e in (eng, orc):

@@ -397,6 +397,7 @@ def test_pinned_caller_path_matches_oracle(kind, variant):
     n = wl.n
     e = gpu_engine(variant, chunk=8192)(coords, t2v, n)
     e.set_option("pinned_path", 1)
+    e.set_option("host_path", 1)  # not the automatic choice between staged and direct uploads
     if kind == "registered":
         e.set_option("register_host", 1)
     orc = OraclePumiTally(coords, t2v, n)
@@ -446,6 +447,7 @@ def test_pinned_caller_path_every_origin_changed_and_none_changed():
     rng = np.random.default_rng(3)
     e = gpu_engine(8, chunk=4096)(coords, t2v, n)
     e.set_option("pinned_path", 1)
+    e.set_option("host_path", 1)
     orc = OraclePumiTally(coords, t2v, n)
     pos = rng.uniform(0.05, 4.95, size=(n, 3))
     for x in (e, orc):
@@ -468,6 +470,31 @@ def test_pinned_caller_path_every_origin_changed_and_none_changed():
     assert_flux_close(e.flux, orc.flux, "pinned path: overflow / no-change extremes")
     np.testing.assert_array_equal(e.elem_ids, orc.elem_ids)
     np.testing.assert_array_equal(e.positions, orc.positions)
+
+
+def test_page_locked_caller_arrays_get_the_faster_of_staged_and_direct_uploads():
+    """host_path=2 (default): with page-locked caller arrays moves 2-3 of every 256 are uploaded directly,
+    the rest staged, and the faster path is kept; results are the oracle's whichever path a move took."""
+    coords, t2v, wl = box_case((6, 6, 5), 80_000)
+    n = wl.n
+    e = gpu_engine(8, chunk=16384)(coords, t2v, n)
+    orc = OraclePumiTally(coords, t2v, n)
+    init = wl.initial_positions()
+    for x in (e, orc):
+        x.CopyInitialPosition(init.reshape(-1).copy())
+    O, D, F, W = _host_buffers(n, "pinned")
+    paths = []
+    for step in range(8):
+        o, d, f, w = wl.next_step()
+        O[:], D[:], W[:], F[:] = o.reshape(-1), d.reshape(-1), w, f
+        e.MoveToNextLocation(O, D, F, W)
+        paths.append(e.get_option("host_path_last"))
+        orc.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy())
+        assert not F.any()
+        assert_flux_close(e.flux, orc.flux, f"auto host path, step {step}")
+        np.testing.assert_array_equal(e.elem_ids, orc.elem_ids)
+    assert paths[:4] == [1, 1, 0, 0]  # staged, staged, direct, direct; then whichever was faster
+    assert e.stats()["segments"] == orc.n_segments
 
 
 def test_error_behaviour():
@@ -552,8 +579,9 @@ def test_normalized_flux_reset_and_vtk_output(tmp_path):
     coords, t2v, wl = box_case((4, 3, 2), 5000)
     e = gpu_engine(0)(coords, t2v, wl.n)
     e.CopyInitialPosition(wl.initial_positions().reshape(-1))
-    o, d, f, w = wl.next_step()
-    e.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
+    o, d, f0, w = wl.next_step()
+    f = f0.copy()
+    e.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f0, w)
     nf, vol = e.normalized_flux()
     np.testing.assert_allclose(vol, tet_volumes(coords, t2v), rtol=1e-13)
     np.testing.assert_allclose(nf, e.flux / vol, rtol=1e-14)
@@ -564,10 +592,32 @@ def test_normalized_flux_reset_and_vtk_output(tmp_path):
     cells = read_vtu_cell_data(os.path.join(out, "pieces", "piece_0.vtu"))
     np.testing.assert_array_equal(cells["flux"], nf)
     np.testing.assert_array_equal(cells["volume"], vol)
-    np.testing.assert_array_equal(cells["connectivity"].reshape(-1, 4), t2v)
+    conn = cells["connectivity"].reshape(-1, 4)
+    np.testing.assert_array_equal(np.sort(conn, axis=1), np.sort(t2v, axis=1))  # same tets, caller's order ...
+    v = coords[conn]
+    assert (np.einsum("ij,ij->i", np.cross(v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]), v[:, 3] - v[:, 0]) > 0).all()  # ... positively oriented
     assert os.path.exists(os.path.join(out, "pieces.pvtu"))
+    # per-source normalisation of the normalised flux (the reference's unfinished total_initial_weight,
+    # PumiTallyImpl.h:170-171): the raw flux never changes
+    raw = e.flux.copy()
+    for mode, value, div in ((1, 0.0, float(wl.n)), (2, 123.5, 123.5), (0, 0.0, 1.0)):
+        e.set_source_normalization(mode, value)
+        assert e.source_normalization() == div
+        np.testing.assert_allclose(e.normalized_flux()[0], raw / vol / div, rtol=1e-14)
+        np.testing.assert_array_equal(e.flux, raw)
+    with pytest.raises(ValueError):
+        e.set_source_normalization(2, 0.0)
     e.reset_tally()
     assert not e.flux.any() and e.stats()["segments"] == 0
+    # mode 3: total weight of the first tracks after the reset, summed on the device
+    e.set_source_normalization(3)
+    o2, d2, f2, w2 = wl.next_step()
+    want = float(w2[f2 == 1].sum())
+    e.MoveToNextLocation(o2.reshape(-1), d2.reshape(-1), f2, w2)
+    o3, d3, f3, w3 = wl.next_step()
+    e.MoveToNextLocation(o3.reshape(-1), d3.reshape(-1), f3, w3)  # later moves do not add to it
+    np.testing.assert_allclose(e.source_normalization(), want, rtol=1e-12)
+    np.testing.assert_allclose(e.normalized_flux()[0], e.flux / vol / want, rtol=1e-13)
 
 
 def test_cxx_facade_program(tmp_path):
@@ -605,9 +655,18 @@ def test_openmc_like_driver_example(tmp_path):
     cells = read_vtu_cell_data(str(tmp_path / "fluxresult.vtk" / "pieces" / "piece_0.vtu"))
     total = float((cells["flux"] * cells["volume"]).sum())
     assert 0.5 * 80000 * 0.75 < total < 3.0 * 80000 * 0.75 * 1.5  # ~ flights * <w> * <in-box length>
+    # with an inactive batch first (tally reset) and per-source normalisation by the total weight of the
+    # active batch's first tracks (PumiTallyExtras.h): the written flux is the raw one over that weight
+    out = subprocess.check_output([exe, "box:8,8,8", "20000", "4", "1"], cwd=str(tmp_path), text=True)
+    assert "DRIVER_OK 80000 flights" in out
+    norm = float(out.split("source normalisation")[1].split()[0])
+    assert 0.7 * 20000 * 0.75 < norm < 1.3 * 20000 * 0.75  # ~ particles * <w>
+    cells = read_vtu_cell_data(str(tmp_path / "fluxresult.vtk" / "pieces" / "piece_0.vtu"))
+    total2 = float((cells["flux"] * cells["volume"]).sum()) * norm
+    assert 0.5 * 80000 * 0.75 < total2 < 3.0 * 80000 * 0.75 * 1.5
 
 
-def _two_gpu_worker(rank, world, port, q):
+def _two_gpu_worker(rank, world, port, q, outdir=None):
     import torch
     import torch.distributed as dist
 
@@ -631,14 +690,17 @@ def _two_gpu_worker(rank, world, port, q):
         # an exchange after every batch: each must give the sum over ranks of everything tallied so
         # far, never counting an earlier exchange's result again
         eng.allreduce_tally()
+    if outdir:  # every rank writes its slice of the (global) result: pieces/piece_<rank>.vtu, rank 0 the .pvtu
+        eng.WriteTallyResults(outdir)
     if rank == 0:
         q.put(eng.flux)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_gpu_stripes_allreduce_equals_single_gpu():
-    """Particle stripes on two GPUs + ncclAllReduce of the tally == one GPU with all particles."""
+def test_two_gpu_stripes_allreduce_equals_single_gpu(tmp_path):
+    """Particle stripes on two GPUs + ncclAllReduce of the tally == one GPU with all particles; the two
+    ranks' VTK pieces tile the mesh and hold the global normalised flux."""
     import torch
 
     if torch.cuda.device_count() < 2:
@@ -648,7 +710,8 @@ def test_two_gpu_stripes_allreduce_equals_single_gpu():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + os.getpid() % 1000
-    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    outdir = str(tmp_path / "fluxresult.vtk")
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, port, q, outdir)) for r in range(2)]
     for p in procs:
         p.start()
     flux2 = q.get(timeout=180)
@@ -662,6 +725,15 @@ def test_two_gpu_stripes_allreduce_equals_single_gpu():
         o, d, f, w = wl.next_step()
         one.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
     assert_flux_close(flux2, one.flux, "2-GPU allreduce vs 1 GPU")
+    from vtk_reader import read_vtu_cell_data
+
+    pieces = [read_vtu_cell_data(os.path.join(outdir, "pieces", f"piece_{r}.vtu")) for r in range(2)]
+    nf, vol = one.normalized_flux()
+    assert len(pieces[0]["flux"]) + len(pieces[1]["flux"]) == len(nf) and len(pieces[0]["flux"]) == len(nf) // 2
+    np.testing.assert_allclose(np.concatenate([p["flux"] for p in pieces]), nf, rtol=1e-9, atol=1e-12 * nf.sum())
+    np.testing.assert_array_equal(np.concatenate([p["volume"] for p in pieces]), vol)
+    pvtu = open(os.path.join(outdir, "pieces.pvtu")).read()
+    assert "pieces/piece_0.vtu" in pvtu and "pieces/piece_1.vtu" in pvtu
 
 
 def test_two_gpu_spatial_partition_equals_replicas():

@@ -339,7 +339,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
     PTB_CUDA_OK(cudaEventRecord(t.a, stream));
   }
   int variant = move_variant_;
-  const bool packed = variant == kVariantPacked || variant == kVariantPackedL1 || variant == kVariantPackedL1Occ6;
+  const bool packed = variant_is_packed(variant);
   if (packed && !(d_dest && d_weights)) variant = kVariantPersistRefill8;  // localisation
   bool use_packed = packed && variant == move_variant_;
   if (use_packed && !d_rows_ &&
@@ -368,8 +368,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
     p.flying = nullptr;  // only flying particles have rows
     launches_ += 5;  // count, 3-kernel scan, pack
   }
-  if (variant == kVariantPersistGather || variant == kVariantPersistGatherL1 ||
-      variant == kVariantPersistGatherPlain || variant == kVariantEdgeGather || variant == kVariantGatherAggTally) {
+  if (variant_is_gather(variant)) {
     // counting sort of the range's flying particles by seed-grid cell of their origin
     unsigned int *wc = d_work_count_ + (ticket_next_ % kTicketRing);
     const double *key = d_origin;  // no origin array (pinned-caller host path): the stored position

@@ -291,6 +291,13 @@ cudaError_t launch_walk_experiment(const WalkParams &p, int variant, int block, 
       if (block == 64) return launch_tworays<128, 3, 8>(p, n, stream);   // block=64 selects 3 resident blocks
       if (block == 256) return launch_tworays<128, 5, 8>(p, n, stream);  // block=256 selects 5
       return launch_tworays<128, 4, 8>(p, n, stream);
+    case kVariantLean:
+      return launch_persist<128, kFetchLean, 7, 8>(p, n, stream);
+    case kVariantLeanGather:
+      return launch_persist<128, kFetchLeanL1, 6, 8, true, 40>(p, n, stream);
+    case kVariantLeanPacked:
+      if (!p.rows) return cudaErrorInvalidValue;
+      return launch_persist<128, kFetchLean, 7, 8, 2>(p, n, stream);
     case kVariantPersistAggTally:
       return launch_persist<128, kFetchPolicyAgg, 7, 8>(p, n, stream);
     case kVariantGatherAggTally:

@@ -38,8 +38,20 @@ enum WalkVariant : int {
   kVariantTwoRays = 27,        // 8 with two rays per lane in flight (software-pipelined walk)
   kVariantPersistAggTally = 28,  // 8 with the warp-aggregated tally (match.any + shuffles)
   kVariantGatherAggTally = 29,   // 16 with the warp-aggregated tally
-  kNumVariants = 30
+  kVariantLean = 30,        // 8 with the lean crossing step (three loads as one block, payload decoded once, target re-read)
+  kVariantLeanGather = 31,  // 16 with the lean crossing step
+  kVariantLeanPacked = 32,  // 24 with the lean crossing step
+  kNumVariants = 33
 };
+
+// how a variant gets its particles: through order[] from the binning pass / through packed rows
+inline bool variant_is_gather(int v) {
+  return v == kVariantPersistGather || v == kVariantPersistGatherL1 || v == kVariantPersistGatherPlain ||
+         v == kVariantEdgeGather || v == kVariantGatherAggTally || v == kVariantLeanGather;
+}
+inline bool variant_is_packed(int v) {
+  return v == kVariantPacked || v == kVariantPackedL1 || v == kVariantPackedL1Occ6 || v == kVariantLeanPacked;
+}
 
 
 cudaError_t launch_walk(const WalkParams &p, int variant, int block, cudaStream_t stream);

@@ -186,8 +186,10 @@ __device__ __forceinline__ int begin_from_row(const WalkParams &P, const PackedR
 //   6  compact layout + edge-function exit test (walk_compact.cuh): one 32-byte TetLinks sector and
 //      one 32-byte vertex per crossing, both L2-resident; degenerate rays finish on the plane records
 //   7, 8  as 1 and 5 with the warp-aggregated tally of walk_core.cuh (experiment)
+//   9, 10 as 1 and 5 with the lean crossing step (plane_step_lean: the three record loads issued as one
+//         block, payload decoded once, ray target re-read at the end of the ray instead of held in registers)
 enum : int { kFetchPlain = 0, kFetchPolicy = 1, kFetchPolicy128 = 2, kFetchBulk = 3, kFetchPolicyL1 = 5, kFetchEdge = 6,
-             kFetchPolicyAgg = 7, kFetchPolicyL1Agg = 8 };
+             kFetchPolicyAgg = 7, kFetchPolicyL1Agg = 8, kFetchLean = 9, kFetchLeanL1 = 10 };
 
 __device__ __forceinline__ uint64_t l2_policy_keep() {
   uint64_t p;
@@ -319,6 +321,60 @@ __device__ __forceinline__ void plane_step(const WalkParams &P, int my_i, Ray &r
     scan_face(sc, q3[0], q3[1], q3[2], q3[3], nb, bk, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
   }
   advance<false, FETCH == kFetchPolicyAgg || FETCH == kFetchPolicyL1Agg>(P, my_i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
+}
+
+// Lean crossing step.  ncu's source view of plane_step() (profiles/r02/README.md, section kernel) shows the
+// compiler sinking the third record load below the arithmetic on the first two -- its latency is then
+// paid a second time (14 % of all stall samples) -- and ~330 warp instructions per warp step.  Here the
+// three loads are one asm block (issued back to back, before any use), the neighbour is decoded once,
+// the parallel-face tolerance is computed once per step, and the ray target is not carried in registers
+// (end_ray<true> re-reads it from the caller's array), which makes room for the loads in flight.
+template <bool L1ALLOC>
+__device__ __forceinline__ void load_faces3(const double *p0, const double *p1, const double *p2, uint64_t pol,
+                                            double (&q)[3][4]) {
+  if constexpr (L1ALLOC)
+    asm volatile(
+        "ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%12], %15;\n\t"
+        "ld.global.nc.L2::cache_hint.v4.f64 {%4,%5,%6,%7}, [%13], %15;\n\t"
+        "ld.global.nc.L2::cache_hint.v4.f64 {%8,%9,%10,%11}, [%14], %15;"
+        : "=d"(q[0][0]), "=d"(q[0][1]), "=d"(q[0][2]), "=d"(q[0][3]), "=d"(q[1][0]), "=d"(q[1][1]), "=d"(q[1][2]),
+          "=d"(q[1][3]), "=d"(q[2][0]), "=d"(q[2][1]), "=d"(q[2][2]), "=d"(q[2][3])
+        : "l"(p0), "l"(p1), "l"(p2), "l"(pol));
+  else
+    asm volatile(
+        "ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%12], %15;\n\t"
+        "ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%4,%5,%6,%7}, [%13], %15;\n\t"
+        "ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%8,%9,%10,%11}, [%14], %15;"
+        : "=d"(q[0][0]), "=d"(q[0][1]), "=d"(q[0][2]), "=d"(q[0][3]), "=d"(q[1][0]), "=d"(q[1][1]), "=d"(q[1][2]),
+          "=d"(q[1][3]), "=d"(q[2][0]), "=d"(q[2][1]), "=d"(q[2][2]), "=d"(q[2][3])
+        : "l"(p0), "l"(p1), "l"(p2), "l"(pol));
+}
+
+template <int FETCH>
+__device__ __forceinline__ void plane_step_lean(const WalkParams &P, int my_i, Ray &r, Counters &c, uint64_t pol) {
+  constexpr bool L1 = FETCH == kFetchLeanL1;
+  const double *rec = P.tets[r.e].d;
+  const int en = r.entry;
+  // faces 0,1,2 with the entry face skipped: offsets (en<=0), (en<=1)+1, (en<=2)+2 for en >= 0; 0,1,2 for en < 0
+  const int f0 = (en == 0) ? 1 : 0, f1 = (en >= 0 && en <= 1) ? 2 : 1, f2 = (en >= 0 && en <= 2) ? 3 : 2;
+  double q[3][4], q3[4];
+  load_faces3<L1>(rec + 4 * f0, rec + 4 * f1, rec + 4 * f2, pol, q);
+  if (en < 0) load_face<L1 ? kFetchPolicyL1 : kFetchPolicy>(rec + 12, pol, q3[0], q3[1], q3[2], q3[3]);
+  const double tol = kParallelTol * (fabs(r.ux) + fabs(r.uy) + fabs(r.uz));
+  LeanScan sc;
+  scan_face_lean(sc, q[0][0], q[0][1], q[0][2], q[0][3], f0, tol, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
+  scan_face_lean(sc, q[1][0], q[1][1], q[1][2], q[1][3], f1, tol, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
+  scan_face_lean(sc, q[2][0], q[2][1], q[2][2], q[2][3], f2, tol, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
+  if (en < 0) scan_face_lean(sc, q3[0], q3[1], q3[2], q3[3], 3, tol, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz);
+  int32_t nb, bk;
+  decode_lean(sc, r.e, nb, bk);
+  // The next tet is known here, ~80 instructions (a division, the tally, the loop overhead) before its
+  // record is asked for: start the line on its way from DRAM to L2 now.  Half of the record fetches miss
+  // in L2 on config c2 and a warp issues only one instruction every ~14 cycles, so the prefetch has
+  // roughly a DRAM latency of head start.
+  if (nb >= 0 && sc.bnum < sc.bden)
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(P.tets + nb));
+  advance<true>(P, my_i, r, exit_parameter(sc), nb, bk, c, true);
 }
 
 // ---- compact layout (kFetchEdge) ----------------------------------------------------------
@@ -616,6 +672,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) walk_persist_kernel(const WalkPar
                        : "r"(row + 16 * j));
         scan_record(raw, r.e, r.ox, r.oy, r.oz, r.ux, r.uy, r.uz, sc);
         advance(P, my_i, r, exit_parameter(sc), sc.nbr, sc.back, c, true);
+      } else if constexpr (FETCH == kFetchLean || FETCH == kFetchLeanL1) {
+        plane_step_lean<FETCH>(P, my_i, r, c, keep);
       } else {
         plane_step<FETCH>(P, my_i, r, c, keep);
       }

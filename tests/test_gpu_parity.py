@@ -1077,3 +1077,16 @@ def test_lattice_tracks_on_hull_faces_edges_and_vertices(variant):
 @pytest.mark.parametrize("variant", [0, 8, 16, 24] + _X)
 def test_tracks_through_vertices_and_along_edges_of_unstructured_meshes(variant):
     unstructured_special_point_scenario(gpu_engine(variant), range(6))
+
+
+@pytest.mark.skipif(not EXPERIMENTS, reason="needs libpumitally_exp.so (PUMITALLY_LIB)")
+@pytest.mark.parametrize("variant", [9, 27, 28, 29, 30, 31, 32])
+def test_round2_experiment_kernels_match_oracle(variant):
+    """The round-2 experiments (64-register build, two rays per lane, aggregated tally, lean step with
+    prefetch) through the same parity scenarios as the product kernels."""
+    golden_scenario(gpu_engine(variant))
+    edge_case_scenario(gpu_engine(variant))
+    coords, t2v, wl = box_case((6, 6, 5), 30_000)
+    eng, orc = gpu_engine(variant)(coords, t2v, wl.n), OraclePumiTally(coords, t2v, wl.n)
+    run_workload(eng, orc, wl, steps=3, label=f"experiment v{variant}")
+    assert eng.stats()["segments"] == orc.n_segments and eng.stats()["lost"] == 0

@@ -91,6 +91,26 @@ def bind_to_gpu_node(torch, index):
     return None
 
 
+def cpu_thread_candidates():
+    """Thread counts worth trying for the CPU arm: every hardware thread, one per core, and what the
+    container's CPU quota allows (more threads than that only get throttled)."""
+    logical = os.cpu_count() or 1
+    try:
+        import psutil
+
+        physical = psutil.cpu_count(logical=False) or logical
+    except Exception:
+        physical = logical
+    quota = logical
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = max(1, int(round(float(q) / float(per))))
+    except Exception:
+        pass
+    return sorted({logical, physical, min(quota, logical), min(2 * quota, logical)}, reverse=True)
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
 
@@ -156,16 +176,9 @@ def run_reference(args, rank):
                            mean_length=cfg["mean_length"], mu_min=cfg["mu_min"])
     orc = OraclePumiTally(coords, t2v, n, per_particle=True)
     orc.CopyInitialPosition(wl.initial_positions().reshape(-1))
-    # give the CPU arm the thread count it runs fastest with: all hardware threads or one per core
-    logical = os.cpu_count() or 1
-    try:
-        import psutil
-
-        physical = psutil.cpu_count(logical=False) or logical
-    except Exception:
-        physical = logical
+    # give the CPU arm the thread count it runs fastest with
     best = None
-    for nt in sorted({logical, physical}, reverse=True):
+    for nt in cpu_thread_candidates():
         set_num_threads(nt)
         o, d, f, w = wl.next_step()
         s_before, t0 = orc.n_segments, time.perf_counter()
@@ -445,14 +458,27 @@ class GpuArm:
                                    mean_length=cfg["mean_length"], mu_min=cfg["mu_min"])
         orc.CopyInitialPosition(wl_cpu.initial_positions().reshape(-1))
         cpu_steps = min(args.cpu_steps, nsteps)
-        t_cpu = 0.0
+        from oracle.oracle import set_num_threads
+
+        best = None  # the thread count the oracle runs fastest with on this box (untimed trial moves)
+        for nt in cpu_thread_candidates():
+            set_num_threads(nt)
+            o, d, f, w = wl_cpu.next_step()
+            s_before, t0 = orc.n_segments, time.perf_counter()
+            orc.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
+            rate = (orc.n_segments - s_before) / (time.perf_counter() - t0)
+            if best is None or rate > best[0]:
+                best = (rate, nt)
+        set_num_threads(best[1])
+        s0, t_cpu = orc.n_segments, 0.0
         for _ in range(cpu_steps):
             o, d, f, w = wl_cpu.next_step()
             t0 = time.perf_counter()
             orc.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
             t_cpu += time.perf_counter() - t0
-        return {"value": orc.n_segments / t_cpu, "unit": UNIT, "cores": num_threads(), "kind": "port",
-                "sample": f"first {ns} particles of the first {cpu_steps} batches ({orc.n_segments} segments, "
+        segs_cpu = orc.n_segments - s0
+        return {"value": segs_cpu / t_cpu, "unit": UNIT, "cores": num_threads(), "kind": "port",
+                "sample": f"first {ns} particles of {cpu_steps} batches ({segs_cpu} segments, "
                           f"{t_cpu:.1f} s) on the full mesh; reference-algorithm restatement, OpenMP"}
 
 

@@ -90,15 +90,20 @@ def face_adjacency(t2v, nverts):
     """t2t[e, f] = tet across the face opposite local vertex f, -1 on the hull."""
     t2v = np.asarray(t2v, dtype=np.int64)
     E = len(t2v)
-    keys = np.empty((E, 4), dtype=np.int64)
-    V = int(nverts)
-    assert V ** 3 < 2 ** 62, "vertex ids too large for the packed face key"
-    for f in range(4):
-        tri = np.sort(np.delete(t2v, f, axis=1), axis=1)
-        keys[:, f] = (tri[:, 0] * V + tri[:, 1]) * V + tri[:, 2]
-    flat = keys.ravel()
-    order = np.argsort(flat, kind="stable")
-    s = flat[order]
+    bits = max(int(nverts - 1).bit_length(), 1)
+    tris = [np.sort(np.delete(t2v, f, axis=1), axis=1) for f in range(4)]
+    if 3 * bits <= 63:  # the sorted vertex triple packs into one 64-bit key
+        keys = np.empty((E, 4), dtype=np.int64)
+        for f in range(4):
+            keys[:, f] = (tris[f][:, 0] << (2 * bits)) | (tris[f][:, 1] << bits) | tris[f][:, 2]
+        flat = keys.ravel()
+        order = np.argsort(flat, kind="stable")
+        s = flat[order]
+    else:  # huge meshes: sort on the three columns
+        tri = np.stack(tris, axis=1).reshape(-1, 3)
+        order = np.lexsort((tri[:, 2], tri[:, 1], tri[:, 0]))
+        t = tri[order]
+        s = np.concatenate([[0], np.cumsum((t[1:] != t[:-1]).any(1))])  # equal triples get equal ranks
     same = s[1:] == s[:-1]
     t2t = np.full(4 * E, -1, dtype=np.int64)
     a, b = order[:-1][same], order[1:][same]

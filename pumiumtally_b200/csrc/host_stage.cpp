@@ -162,14 +162,18 @@ double cgroup_cpu_quota() {
 int default_host_threads() {
   const int forced = env_int("PUMITALLY_HOST_THREADS", 0);
   if (forced > 0) return std::min(forced, 256);
+  // this rank's share of the machine (hardware threads and CPU quota divided by the ranks on the node),
+  // but never more than its own affinity mask offers (a rank bound to its GPU's NUMA node shares that
+  // node only with the ranks of the node's other GPUs, so the mask itself is not divided)
   cpu_set_t set;
-  int avail = int(std::thread::hardware_concurrency());
+  const int hw = std::max(1, int(std::thread::hardware_concurrency()));
+  int avail = hw;
   if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = CPU_COUNT(&set);
-  double n = std::min<double>(std::max(avail, 1), cgroup_cpu_quota());
   int local = env_int("LOCAL_WORLD_SIZE", 0);
   if (local <= 0) local = env_int("OMPI_COMM_WORLD_LOCAL_SIZE", 0);
   if (local <= 0) local = env_int("SLURM_NTASKS_PER_NODE", 0);
-  if (local > 1) n /= local;
+  if (local <= 0) local = 1;
+  const double n = std::min({double(avail), cgroup_cpu_quota() / local, double(hw) / local});
   return std::max(1, std::min(32, int(n + 0.5)));
 }
 

@@ -8,8 +8,8 @@ A "step" is one MoveToNextLocation over one synthetic batch of BASELINE.json's
 config c2 (998,250-tet Kuhn box, 10M particles per GPU).
 Per-GPU work is fixed as N grows (weak scaling); every rank holds the whole
 mesh (full-buffer picpart) and its own particle stripe, and the per-rank
-tallies are summed once at batch end with ncclAllReduce inside the timed
-region.  One JSON line is printed by rank 0.
+tallies are summed once at batch end inside the timed region (ncclReduceScatter
+to the owners of the element shares; gathered when the result is read).  One JSON line is printed by rank 0.
 
 `value` is device-resident throughput; `e2e` is the same metric through the
 reference-facing call on pageable host arrays (host->device copies inside the
@@ -317,7 +317,7 @@ class GpuArm:
                 eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
             if world > 1:
                 torch.cuda.current_stream().synchronize()
-                eng.allreduce_tally()  # batch-end exchange of the ghost tallies over NVLink
+                eng.reduce_tally_to_owners()  # batch-end exchange of the ghost tallies over NVLink (reduce-scatter)
             ev1.record()
             self.barrier()
             ms = ev0.elapsed_time(ev1)
@@ -330,7 +330,7 @@ class GpuArm:
                 eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
                 if world > 1 and k == nsteps - 1:
                     torch.cuda.current_stream().synchronize()
-                    eng.allreduce_tally()
+                    eng.reduce_tally_to_owners()
                 ev1.record()
                 torch.cuda.synchronize()
                 ms += ev0.elapsed_time(ev1)
@@ -349,8 +349,10 @@ class GpuArm:
             "relocation_crossings_per_step": (st1["relocations"] - st0["relocations"]) / max(steps, 1),
             "flux_sum": float(eng.flux.sum()), "variant": eng.get_option("variant"),
             "gpu_launches": eng.get_option("launches") - launches0,  # kernels the engine launched in the timed region
-            "allreduce_ms": (eng.get_option("allreduce_us") / 1e3) if world > 1 else None,
+            "allreduce_ms": (eng.get_option("allreduce_us") / 1e3) if world > 1 else None,  # the batch-end exchange
             "allreduce_bytes": 8 * eng.num_elements if world > 1 else None,
+            "exchange": "ncclReduceScatter of the flux at batch end; shares gathered once when the result is read"
+                        if world > 1 else None,
             "pregen": pregen, "clocks": clocks_out, "bytes_per_step": bytes_per_step,
         }
         peak, peak_src = measured_peak()
@@ -530,11 +532,11 @@ def run_gpu(args, rank, local_rank, world):
                    "l2": f"inputs larger than L2 ({main['bytes_per_step'] / 1e6:.0f} MB of fresh particle data per step)",
                    "timing": "K steps back to back between two CUDA events" if main["pregen"] else
                              "per-step CUDA-event times summed (batches generated between steps, untimed)",
-                   "parallelism": f"particle stripes x{world}, full-buffer picparts, 1 ncclAllReduce(flux) per batch",
+                   "parallelism": f"particle stripes x{world}, full-buffer picparts, 1 ncclReduceScatter(flux) per batch",
                    "segments_per_track": main["segments_per_track"], "lost": main["lost"],
                    "relocation_crossings_per_step": main["relocation_crossings_per_step"],
                    "flux_sum": main["flux_sum"], "allreduce_ms": main["allreduce_ms"],
-                   "allreduce_bytes": main["allreduce_bytes"]},
+                   "allreduce_bytes": main["allreduce_bytes"], "exchange": main["exchange"]},
         "roofline": roof,
         "cpu_baseline": cpu,
         "e2e": main.get("e2e"),

@@ -161,6 +161,12 @@ int pumitally_synchronize(pumitally_engine *e);
 int pumitally_nccl_unique_id(uint8_t out_id[128]);
 int pumitally_comm_init(pumitally_engine *e, int32_t rank, int32_t nranks, const uint8_t id[128]);
 int pumitally_allreduce_tally(pumitally_engine *e);
+/* The cheaper batch-end exchange (half the NVLink traffic): ncclReduceScatter -- every rank receives
+ * the sum over ranks of its own share of the elements only.  The shares are gathered (ncclAllGather,
+ * COLLECTIVE: every rank must make the call) the first time pumitally_get_flux,
+ * pumitally_get_normalized_flux, pumitally_get_flux_device or pumitally_write_tally_results needs
+ * the whole array, i.e. normally once, at the end of the run. */
+int pumitally_reduce_tally_to_owners(pumitally_engine *e);
 
 /* test hook: processing order produced by the last binning pass (ids of flying particles
  * grouped by seed-grid cell); returns the number of entries, copies at most n of them */

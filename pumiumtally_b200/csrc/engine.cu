@@ -35,6 +35,7 @@ void cuda_or_throw(cudaError_t e, const char *what) {
 }
 
 constexpr unsigned kTicketRing = 256;
+constexpr size_t kFluxPad = 1024;  // most ranks a communicator may have (padding of the flux arrays)
 
 template <typename T>
 void dev_alloc(T **p, size_t count, const char *what) {
@@ -60,7 +61,7 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
 
   const size_t E = size_t(mesh_.ntets), N = size_t(n_);
   dev_alloc(&d_tets_, E, "tet records");
-  dev_alloc(&d_flux_, E, "flux");
+  dev_alloc(&d_flux_, E + kFluxPad, "flux");  // padded: the reduce-scatter exchange sends nranks equal shares
   dev_alloc(&d_volume_, E, "volume");
   dev_alloc(&d_scratch_, E, "scratch");
   dev_alloc(&d_state_, N, "particle state");
@@ -80,7 +81,7 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
 
   cuda_or_throw(cudaMemcpy(d_tets_, mesh_.records.data(), E * sizeof(TetRecord), cudaMemcpyHostToDevice), "upload tets");
   cuda_or_throw(cudaMemcpy(d_volume_, mesh_.volume.data(), E * sizeof(double), cudaMemcpyHostToDevice), "upload volume");
-  cuda_or_throw(cudaMemset(d_flux_, 0, E * sizeof(double)), "memset");
+  cuda_or_throw(cudaMemset(d_flux_, 0, (E + kFluxPad) * sizeof(double)), "memset");
   cuda_or_throw(cudaMemset(d_stats_, 0, sizeof(DeviceStats)), "memset");
   // InitializeParticlesInElement0 (PumiTallyImpl.cpp:492-528)
   cuda_or_throw(launch_init_particles(d_state_, n_, mesh_.centroid0[0], mesh_.centroid0[1],
@@ -299,7 +300,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   }
   last_stream_ = stream;
   last_stream_set_ = true;
-  if (d_dest) flux_global_valid_ = false;  // the local tally moves on; the last exchange no longer describes it
+  if (d_dest) flux_global_valid_ = flux_owned_only_ = false;  // the local tally moves on; the last exchange no longer describes it
   if (d_dest && d_weights && initial_weight_pending_)  // first tracks of the batch: their total weight
     PTB_CUDA_OK(launch_sum_flying_weights(d_flying, d_weights, begin, end, d_initial_weight_, stream));
   WalkParams p{};
@@ -973,14 +974,14 @@ int Engine::get_state_device(double *d_xyz, int32_t *d_elem, int32_t first, int3
 
 int Engine::get_flux_device(double *d_out, cudaStream_t stream) {
   PTB_CUDA_OK(cudaSetDevice(device_));
-  if (ensure_element_maps()) return 1;
+  if (ensure_element_maps() || gather_shares()) return 1;
   PTB_CUDA_OK(launch_flux_to_caller_order(flux_view(), d_orig_of_internal_, d_out, mesh_.ntets, stream));
   return 0;
 }
 
 int Engine::get_flux(double *out, int64_t n) {
   if (n != mesh_.ntets) return 1;
-  if (synchronize()) return 1;
+  if (synchronize() || gather_shares()) return 1;
   std::vector<double> tmp(static_cast<size_t>(n));
   PTB_CUDA_OK(cudaMemcpy(tmp.data(), flux_view(), size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < n; ++i) out[mesh_.orig_of_internal[i]] = tmp[i];  // caller's numbering
@@ -990,7 +991,7 @@ int Engine::get_flux(double *out, int64_t n) {
 // NormalizeFlux (PumiTallyImpl.cpp:382-409)
 int Engine::get_normalized_flux(double *out_flux, double *out_volume, int64_t n) {
   if (n != mesh_.ntets) return 1;
-  if (synchronize()) return 1;
+  if (synchronize() || gather_shares()) return 1;
   if (out_flux) {
     const double per_source = source_normalization();
     if (!(per_source > 0.0)) {
@@ -1056,9 +1057,9 @@ int Engine::reset_tally() {
   collect_timers(true);
   PTB_CUDA_OK(cudaMemset(d_initial_weight_, 0, sizeof(double)));
   initial_weight_pending_ = true;
-  PTB_CUDA_OK(cudaMemset(d_flux_, 0, size_t(mesh_.ntets) * sizeof(double)));
+  PTB_CUDA_OK(cudaMemset(d_flux_, 0, (size_t(mesh_.ntets) + kFluxPad) * sizeof(double)));
   PTB_CUDA_OK(cudaMemset(d_stats_, 0, sizeof(DeviceStats)));
-  flux_global_valid_ = false;
+  flux_global_valid_ = flux_owned_only_ = false;
   kernel_ms_ = 0.0;
   h2d_bytes_ = 0.0;
   moves_ = 0;
@@ -1225,7 +1226,9 @@ int Engine::comm_init(int rank, int nranks, const uint8_t id[128]) {
   nranks_ = nranks;
   // NCCL sets up its NVLink connections lazily inside the first collective: pay that here,
   // on the scratch array, not in the first batch-end exchange
-  PTB_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&d_flux_global_), std::max<size_t>(size_t(mesh_.ntets), 1) * sizeof(double)));
+  if (nranks < 1 || size_t(nranks) > kFluxPad) return 1;
+  share_ = (size_t(mesh_.ntets) + size_t(nranks) - 1) / size_t(nranks);
+  PTB_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&d_flux_global_), std::max<size_t>(share_ * size_t(nranks), 1) * sizeof(double)));
   PTB_CUDA_OK(cudaEventCreate(&ev_ar0_));
   PTB_CUDA_OK(cudaEventCreate(&ev_ar1_));
   PTB_CUDA_OK(cudaMemsetAsync(d_scratch_, 0, size_t(mesh_.ntets) * sizeof(double), compute_));
@@ -1249,6 +1252,32 @@ int Engine::allreduce_tally() {
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, ev_ar0_, ev_ar1_) == cudaSuccess) allreduce_ms_ = ms;
   flux_global_valid_ = true;
+  flux_owned_only_ = false;
+  return 0;
+}
+
+int Engine::reduce_tally_to_owners() {
+  if (!nccl_comm_) return nranks_ == 1 ? 0 : 1;
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  PTB_CUDA_OK(cudaDeviceSynchronize());
+  PTB_CUDA_OK(cudaEventRecord(ev_ar0_, compute_));
+  if (nccl_reduce_scatter_sum_f64(nccl_comm_, d_flux_, d_flux_global_ + size_t(rank_) * share_, share_, compute_)) return 1;
+  PTB_CUDA_OK(cudaEventRecord(ev_ar1_, compute_));
+  PTB_CUDA_OK(cudaStreamSynchronize(compute_));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ev_ar0_, ev_ar1_) == cudaSuccess) allreduce_ms_ = ms;
+  flux_global_valid_ = true;
+  flux_owned_only_ = true;
+  return 0;
+}
+
+// Collective: every rank contributes its share, every rank ends up with the whole (summed) array.
+int Engine::gather_shares() {
+  if (!flux_global_valid_ || !flux_owned_only_) return 0;
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  if (nccl_all_gather_f64(nccl_comm_, d_flux_global_ + size_t(rank_) * share_, d_flux_global_, share_, compute_)) return 1;
+  PTB_CUDA_OK(cudaStreamSynchronize(compute_));
+  flux_owned_only_ = false;
   return 0;
 }
 

@@ -66,7 +66,7 @@ class Engine {
   double source_normalization();  // the divisor currently in effect (1 for mode 0)
   int get_stats(EngineStats *out);
   int synchronize();
-  double *flux_device_ptr() { return flux_view(); }
+  double *flux_device_ptr() { return gather_shares() ? nullptr : flux_view(); }
   int set_option(const std::string &name, int64_t value);
   int64_t get_option(const std::string &name) const;
   void set_output_name(const std::string &s) { output_name_ = s; }
@@ -76,6 +76,10 @@ class Engine {
   // multi-GPU exchange step
   int comm_init(int rank, int nranks, const uint8_t id[128]);
   int allreduce_tally();
+  // The cheaper batch-end exchange: every rank ends up with the sum over ranks of ITS share of the
+  // elements only (ncclReduceScatter: half the traffic of the all-reduce); the shares are gathered
+  // (ncclAllGather, collective) the first time a flux accessor or WriteTallyResults needs the whole array.
+  int reduce_tally_to_owners();
 
  private:
   int launch_range(const double *d_origin, const double *d_dest, const int8_t *d_flying,
@@ -217,6 +221,9 @@ class Engine {
   // twice.  The accessors return this array until the next move or reset changes the local tally.
   double *d_flux_global_ = nullptr;
   bool flux_global_valid_ = false;
+  bool flux_owned_only_ = false;  // d_flux_global_ holds only this rank's share (after reduce_tally_to_owners)
+  size_t share_ = 0;              // elements per rank in the scattered layout = ceil(E / nranks)
+  int gather_shares();
   double *flux_view() { return flux_global_valid_ ? d_flux_global_ : d_flux_; }
   double allreduce_ms_ = 0.0;  // device time of the last exchange
   cudaEvent_t ev_ar0_ = nullptr, ev_ar1_ = nullptr;
@@ -226,6 +233,8 @@ class Engine {
 int nccl_get_unique_id(uint8_t out[128]);
 int nccl_comm_init_rank(void **comm, int nranks, const uint8_t id[128], int rank);
 int nccl_allreduce_sum_f64(void *comm, const double *send, double *recv, size_t count, cudaStream_t stream);
+int nccl_reduce_scatter_sum_f64(void *comm, const double *send, double *recv, size_t count, cudaStream_t stream);
+int nccl_all_gather_f64(void *comm, const double *send, double *recv, size_t count, cudaStream_t stream);
 void nccl_comm_destroy(void *comm);
 
 }  // namespace ptb

@@ -24,6 +24,8 @@ struct Api {
   int (*GetUniqueId)(UniqueId *) = nullptr;
   int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, Comm, cudaStream_t) = nullptr;
   int (*CommDestroy)(Comm) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
@@ -44,6 +46,8 @@ Api *api() {
   a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(a.handle, "ncclGetUniqueId"));
   a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(a.handle, "ncclCommInitRank"));
   a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(a.handle, "ncclAllReduce"));
+  a.ReduceScatter = reinterpret_cast<decltype(a.ReduceScatter)>(dlsym(a.handle, "ncclReduceScatter"));
+  a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(a.handle, "ncclAllGather"));
   a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.handle, "ncclCommDestroy"));
   a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(a.handle, "ncclGetErrorString"));
   if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy) {
@@ -84,6 +88,20 @@ int nccl_allreduce_sum_f64(void *comm, const double *send, double *recv, size_t 
   Api *a = api();
   if (!a) return 1;
   return check(a, a->AllReduce(send, recv, count, kNcclFloat64, kNcclSum, comm, stream), "ncclAllReduce");
+}
+
+// recv[0..count) = sum over ranks of send[rank*count .. (rank+1)*count)
+int nccl_reduce_scatter_sum_f64(void *comm, const double *send, double *recv, size_t count, cudaStream_t stream) {
+  Api *a = api();
+  if (!a || !a->ReduceScatter) return 1;
+  return check(a, a->ReduceScatter(send, recv, count, kNcclFloat64, kNcclSum, comm, stream), "ncclReduceScatter");
+}
+
+// recv[r*count .. (r+1)*count) = rank r's send[0..count); in place when send == recv + rank*count
+int nccl_all_gather_f64(void *comm, const double *send, double *recv, size_t count, cudaStream_t stream) {
+  Api *a = api();
+  if (!a || !a->AllGather) return 1;
+  return check(a, a->AllGather(send, recv, count, kNcclFloat64, comm, stream), "ncclAllGather");
 }
 
 void nccl_comm_destroy(void *comm) {

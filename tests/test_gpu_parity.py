@@ -684,16 +684,24 @@ def _two_gpu_worker(rank, world, port, q, outdir=None):
     eng.comm_init(rank, world, broadcast_unique_id(dist, PumiTally.nccl_unique_id, device=torch.device("cuda", rank)))
     wl = SyntheticWorkload(box=(8.0, 8.0, 8.0), num_particles=e - b, mean_length=2.0, id_offset=b)
     eng.CopyInitialPosition(wl.initial_positions().reshape(-1))
-    for _ in range(3):
+    for k in range(3):
         o, d, f, w = wl.next_step()
         eng.MoveToNextLocation(o.reshape(-1), d.reshape(-1), f, w)
         # an exchange after every batch: each must give the sum over ranks of everything tallied so
-        # far, never counting an earlier exchange's result again
-        eng.allreduce_tally()
+        # far, never counting an earlier exchange's result again -- by all-reduce, or by the cheaper
+        # reduce-scatter whose shares are gathered when somebody asks for the flux
+        if k == 0:
+            eng.allreduce_tally()
+        else:
+            eng.reduce_tally_to_owners()
+        if k == 1:
+            part = eng.flux  # collective gather on every rank
+            assert np.isfinite(part).all()
     if outdir:  # every rank writes its slice of the (global) result: pieces/piece_<rank>.vtu, rank 0 the .pvtu
         eng.WriteTallyResults(outdir)
+    flux = eng.flux  # every rank: the accessor gathers the shares of the last reduce-scatter
     if rank == 0:
-        q.put(eng.flux)
+        q.put(flux)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -431,7 +431,8 @@ class GpuArm:
                 # side numbers: caller arrays the engine may page-lock (register_host=1, what an OpenMC
                 # integration sets: its vectors live for the whole run) with the engine choosing between
                 # staged and direct uploads; pinned caller arrays; and the direct paths on their own
-                ks, kw = min(steps, 6), min(warmup, 5)  # the automatic choice has probed both paths after 4 moves
+                kw = min(5, max(nsteps - 1, 0))  # the automatic choice has probed both upload paths after 4 moves
+                ks = max(1, min(6, nsteps - kw))
                 modes = [("registered_auto", "pageable", {"register_host": 1})]
                 if world == 1:
                     modes += [("pinned_buffers", "pinned", {}),

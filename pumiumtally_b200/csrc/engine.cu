@@ -620,10 +620,17 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
   if (host_path_ == 2 && host_is_pinned(origin) && host_is_pinned(dest) && host_is_pinned(weights) && host_is_pinned(flying)) {
     collect_upload_span();
     const uint64_t k = host_moves_ % 256;
-    if (k == 0) { span_ms_[0] = span_ms_[1] = 0.0; span_n_[0] = span_n_[1] = 0; }
-    if (k >= 2 && k <= 3) probe = 1;
-    else if (k <= 1 || span_n_[0] == 0 || span_n_[1] == 0) probe = 0;
-    else probe = (span_ms_[1] / span_n_[1] < 0.95 * span_ms_[0] / span_n_[0]) ? 1 : 0;
+    if (k == 0) { span_ms_[0] = span_ms_[1] = 0.0; span_n_[0] = span_n_[1] = 0; span_choice_ = -1; }
+    if (k >= 2 && k <= 3) {
+      probe = 1;
+    } else if (k <= 1 || span_n_[0] == 0 || span_n_[1] == 0) {
+      probe = 0;
+    } else {
+      // decided once per epoch, from the probe moves only: changing paths is not free (the first staged move
+      // after a direct one has no mirror and sends every origin)
+      if (span_choice_ < 0) span_choice_ = (span_ms_[1] / span_n_[1] < 0.9 * span_ms_[0] / span_n_[0]) ? 1 : 0;
+      probe = span_choice_;
+    }
     want_staged = probe == 0;
   }
   ++host_moves_;
@@ -865,6 +872,7 @@ int Engine::move_pinned(const double *origin, const double *dest, int8_t *flying
 // the path that move used; feeds the staged-vs-direct choice for page-locked caller arrays.
 void Engine::collect_upload_span() {
   if (span_tag_ < 0 || !ev_copy0_) return;
+  if (span_choice_ >= 0) { span_tag_ = -1; return; }  // decided for this epoch
   float ms = 0.f;
   if (cudaEventSynchronize(ev_copy1_) == cudaSuccess && cudaEventElapsedTime(&ms, ev_copy0_, ev_copy1_) == cudaSuccess) {
     span_ms_[span_tag_] += ms;

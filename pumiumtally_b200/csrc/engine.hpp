@@ -178,6 +178,7 @@ class Engine {
   double span_ms_[2] = {0.0, 0.0};    // upload span per path: [0] staged, [1] direct
   int span_n_[2] = {0, 0};
   int span_tag_ = -1;                 // path of the move whose span has not been collected yet
+  int span_choice_ = -1;              // this epoch's decision: 0 staged, 1 direct, -1 still probing
   void collect_upload_span();
   int host_threads_ = 0;              // 0 = default_host_threads() - 1
   std::unique_ptr<HostStager> stager_;  // worker pool + per-chunk stage pass

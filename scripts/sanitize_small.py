@@ -1,4 +1,5 @@
-"""Small end-to-end run of every shipped kernel variant for compute-sanitizer."""
+"""Small end-to-end run of every shipped kernel variant and host path for compute-sanitizer:
+   compute-sanitizer --tool memcheck python scripts/sanitize_small.py [variant ...]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -14,4 +15,39 @@ for v in variants:
     e.set_option("variant", v)
     e.set_option("chunk", 2048)  # several upload/compute ranges, ragged last chunk
     run_workload(e, OraclePumiTally(coords, t2v, wl.n), wl, steps=2, label=f"sanitize v{v}")
-    print("variant", v, "ok", e.stats()["segments"], flush=True)
+    print("variant", v, "staged host path ok", e.stats()["segments"], flush=True)
+    # direct host path, device-side state accessors, weight sum, normalisation, pinned-caller path
+    import torch
+    for opts, pinned in (({"host_path": 0}, False), ({"host_path": 1, "pinned_path": 1}, True)):
+        coords, t2v, wl = box_case((6, 6, 5), 5003)
+        e, orc = PumiTally.from_arrays(coords, t2v, wl.n), OraclePumiTally(coords, t2v, wl.n)
+        e.set_option("variant", v)
+        e.set_option("chunk", 1024)
+        for k_, v_ in opts.items():
+            e.set_option(k_, v_)
+        e.set_source_normalization(3)
+        init = wl.initial_positions()
+        for x in (e, orc):
+            x.CopyInitialPosition(init.reshape(-1).copy())
+        n = wl.n
+        if pinned:
+            O, D, F, W = [torch.empty(s_, dtype=d_, pin_memory=True).numpy() for s_, d_ in
+                          ((3 * n, torch.float64), (3 * n, torch.float64), (n, torch.int8), (n, torch.float64))]
+        else:
+            O, D, F, W = np.empty(3 * n), np.empty(3 * n), np.empty(n, dtype=np.int8), np.empty(n)
+        for _ in range(3):
+            o, d, f, w = wl.next_step()
+            O[:], D[:], F[:], W[:] = o.reshape(-1), d.reshape(-1), f, w
+            e.MoveToNextLocation(O, D, F, W)
+            orc.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy())
+        np.testing.assert_array_equal(e.elem_ids, orc.elem_ids)
+        np.testing.assert_allclose(e.flux, orc.flux, rtol=1e-9, atol=1e-12)
+        pos = torch.empty((n, 3), dtype=torch.float64, device="cuda"); el = torch.empty(n, dtype=torch.int32, device="cuda")
+        e.get_state_device(pos.data_ptr(), el.data_ptr(), 0, n)
+        e.set_state_device(pos.data_ptr(), el.data_ptr(), 0, n)
+        fl = torch.empty(e.num_elements, dtype=torch.float64, device="cuda")
+        e.get_flux_device(fl.data_ptr())
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(fl.cpu().numpy(), e.flux, rtol=0, atol=0)
+        e.normalized_flux()
+        print("variant", v, opts, "ok", flush=True)

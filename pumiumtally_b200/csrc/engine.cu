@@ -1,6 +1,9 @@
 // Engine: device state + batch orchestration (see engine.hpp).
 #include "engine.hpp"
 
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -521,8 +524,16 @@ int Engine::ensure_stage_buffers(const void *caller_mem, size_t caller_bytes) {
     // PUMITALLY_STAGE_NODE=<n> puts them on another node: on a two-socket host the pass then draws on
     // both sockets' memory controllers (caller arrays on one, slots + DMA reads on the other).
     const char *env_node = std::getenv("PUMITALLY_STAGE_NODE");
-    const std::vector<int> there = env_node ? numa_node_cpus(std::atoi(env_node)) : std::vector<int>();
-    if (!there.empty()) pool_->repin(there);
+    const std::vector<int> there;  // (placement is done with mbind below: the other node's CPUs may not be in the mask)
+    if (env_node) {
+      unsigned long mask[16] = {0};
+      const int node = std::atoi(env_node);
+      if (node >= 0 && node < 1024) {
+        mask[node / 64] = 1ul << (node % 64);
+        if (syscall(SYS_mbind, base, total, 2 /* MPOL_BIND */, mask, 1024ul, 0u) != 0)
+          fprintf(stderr, "[pumitally] WARNING: mbind of the staging slots to node %d failed\n", node);
+      }
+    }
     pool_->run([&](int t) {  // first touch on the workers' NUMA node
       const size_t lo = (total * size_t(t) / size_t(T)) & ~size_t(4095);
       const size_t hi = t == T - 1 ? total : (total * size_t(t + 1) / size_t(T)) & ~size_t(4095);

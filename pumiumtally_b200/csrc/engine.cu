@@ -1,6 +1,7 @@
 // Engine: device state + batch orchestration (see engine.hpp).
 #include "engine.hpp"
 
+#include <sys/mman.h>
 #include <sys/syscall.h>
 #include <unistd.h>
 
@@ -518,7 +519,8 @@ int Engine::ensure_stage_buffers(const void *caller_mem, size_t caller_bytes) {
   const size_t bytes_fly = (N + 4095) & ~size_t(4095);
   const size_t total = bytes_dest + bytes_w + bytes_fly;
   void *base = nullptr;
-  if (posix_memalign(&base, 4096, total) == 0) {
+  if (posix_memalign(&base, size_t(2) << 20, total) == 0) {
+    madvise(base, total, MADV_HUGEPAGE);  // 2 MB pages where the kernel offers them: three streams of TLB misses less
     const int T = pool_->size();
     // Where the staging slots live.  Default: on the workers' node (= the caller's arrays' node).
     // PUMITALLY_STAGE_NODE=<n> puts them on another node: on a two-socket host the pass then draws on

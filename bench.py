@@ -8,8 +8,10 @@ A "step" is one MoveToNextLocation over one synthetic batch of BASELINE.json's
 config c2 (998,250-tet Kuhn box, 10M particles per GPU).
 Per-GPU work is fixed as N grows (weak scaling); every rank holds the whole
 mesh (full-buffer picpart) and its own particle stripe, and the per-rank
-tallies are summed once at batch end inside the timed region (ncclReduceScatter
-to the owners of the element shares; gathered when the result is read).  One JSON line is printed by rank 0.
+tallies are summed once at batch end inside the timed region (ncclAllReduce, or
+ncclReduceScatter to the owners of the element shares with the gather deferred
+to read time -- whichever the engine measured to be quicker on this mesh when
+the communicator was set up).  One JSON line is printed by rank 0.
 
 `value` is device-resident throughput; `e2e` is the same metric through the
 reference-facing call on pageable host arrays (host->device copies inside the
@@ -216,6 +218,13 @@ def run_reference(args, rank):
 
 # ------------------------------------------------------------------------- GPU arm
 
+def exchange_description(eng):
+    rs = eng.get_option("exchange_choice") == 1
+    return {"collective": "ncclReduceScatter (shares gathered once when the result is read)" if rs else "ncclAllReduce",
+            "measured_at_comm_init_ms": {"allreduce": eng.get_option("exchange_allreduce_us") / 1e3,
+                                         "reduce_scatter": eng.get_option("exchange_reduce_scatter_us") / 1e3}}
+
+
 class GpuArm:
     """One rank of the CUDA arm: measures one configuration at a time (device-resident `value`,
     end-to-end `e2e`) with every rank taking part; rank 0 assembles the JSON line."""
@@ -302,6 +311,9 @@ class GpuArm:
         for k in range(warmup):
             o, d, f, w = batch(k)
             eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
+        if world > 1 and warmup:
+            torch.cuda.current_stream().synchronize()
+            eng.exchange_tally()  # the warm-up steps are a batch too: its exchange is outside the timed region
         self.barrier()
         st0 = eng.stats()
         launches0 = eng.get_option("launches")
@@ -317,7 +329,7 @@ class GpuArm:
                 eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
             if world > 1:
                 torch.cuda.current_stream().synchronize()
-                eng.reduce_tally_to_owners()  # batch-end exchange of the ghost tallies over NVLink (reduce-scatter)
+                eng.exchange_tally()  # batch-end exchange of the ghost tallies over NVLink
             ev1.record()
             self.barrier()
             ms = ev0.elapsed_time(ev1)
@@ -330,7 +342,7 @@ class GpuArm:
                 eng.move_device(o.data_ptr(), d.data_ptr(), f.data_ptr(), w.data_ptr(), stream)
                 if world > 1 and k == nsteps - 1:
                     torch.cuda.current_stream().synchronize()
-                    eng.reduce_tally_to_owners()
+                    eng.exchange_tally()
                 ev1.record()
                 torch.cuda.synchronize()
                 ms += ev0.elapsed_time(ev1)
@@ -351,8 +363,7 @@ class GpuArm:
             "gpu_launches": eng.get_option("launches") - launches0,  # kernels the engine launched in the timed region
             "allreduce_ms": (eng.get_option("allreduce_us") / 1e3) if world > 1 else None,  # the batch-end exchange
             "allreduce_bytes": 8 * eng.num_elements if world > 1 else None,
-            "exchange": "ncclReduceScatter of the flux at batch end; shares gathered once when the result is read"
-                        if world > 1 else None,
+            "exchange": exchange_description(eng) if world > 1 else None,
             "pregen": pregen, "clocks": clocks_out, "bytes_per_step": bytes_per_step,
         }
         peak, peak_src = measured_peak()
@@ -533,7 +544,7 @@ def run_gpu(args, rank, local_rank, world):
                    "l2": f"inputs larger than L2 ({main['bytes_per_step'] / 1e6:.0f} MB of fresh particle data per step)",
                    "timing": "K steps back to back between two CUDA events" if main["pregen"] else
                              "per-step CUDA-event times summed (batches generated between steps, untimed)",
-                   "parallelism": f"particle stripes x{world}, full-buffer picparts, 1 ncclReduceScatter(flux) per batch",
+                   "parallelism": f"particle stripes x{world}, full-buffer picparts, 1 NCCL exchange of the flux per batch",
                    "segments_per_track": main["segments_per_track"], "lost": main["lost"],
                    "relocation_crossings_per_step": main["relocation_crossings_per_step"],
                    "flux_sum": main["flux_sum"], "allreduce_ms": main["allreduce_ms"],

@@ -167,6 +167,13 @@ int pumitally_allreduce_tally(pumitally_engine *e);
  * pumitally_get_normalized_flux, pumitally_get_flux_device or pumitally_write_tally_results needs
  * the whole array, i.e. normally once, at the end of the run. */
 int pumitally_reduce_tally_to_owners(pumitally_engine *e);
+/* Which of the two is quicker depends on the size of the flux array and on the algorithm NCCL picks for
+ * it (8 B200s: 8 MB -- all-reduce 0.10 ms, reduce-scatter 4.3 ms; 79 MB -- 0.9 ms and 0.43 ms), so
+ * pumitally_comm_init times both on the engine's own mesh, agrees on the result across the ranks, and
+ * this call -- the one a driver should make at batch end -- runs the quicker one.  Read the decision
+ * with pumitally_get_option("exchange_choice") (0 all-reduce, 1 reduce-scatter) and the two times with
+ * "exchange_allreduce_us" / "exchange_reduce_scatter_us". */
+int pumitally_exchange_tally(pumitally_engine *e);
 
 /* test hook: processing order produced by the last binning pass (ids of flying particles
  * grouped by seed-grid cell); returns the number of entries, copies at most n of them */

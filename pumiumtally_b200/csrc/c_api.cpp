@@ -222,6 +222,9 @@ int pumitally_comm_init(pumitally_engine *e, int32_t rank, int32_t nranks, const
 int pumitally_allreduce_tally(pumitally_engine *e) {
   return guarded(e, [&](ptb::Engine &g) { return g.allreduce_tally(); });
 }
+int pumitally_exchange_tally(pumitally_engine *e) {
+  return guarded(e, [&](ptb::Engine &g) { return g.exchange_tally(); });
+}
 int pumitally_reduce_tally_to_owners(pumitally_engine *e) {
   return guarded(e, [&](ptb::Engine &g) { return g.reduce_tally_to_owners(); });
 }

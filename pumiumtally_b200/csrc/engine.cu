@@ -137,6 +137,7 @@ Engine::~Engine() {
   if (nccl_comm_) nccl_comm_destroy(nccl_comm_);
   cudaFree(d_flux_global_);
   if (ev_order_) cudaEventDestroy(ev_order_);
+  if (ev_done_) cudaEventDestroy(ev_done_);
   if (ev_copy0_) cudaEventDestroy(ev_copy0_);
   if (ev_copy1_) cudaEventDestroy(ev_copy1_);
   if (ev_ar0_) cudaEventDestroy(ev_ar0_);
@@ -641,7 +642,12 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
     } else {
       // decided once per epoch, from the probe moves only: changing paths is not free (the first staged move
       // after a direct one has no mirror and sends every origin)
-      if (span_choice_ < 0) span_choice_ = (span_ms_[1] / span_n_[1] < 0.9 * span_ms_[0] / span_n_[0]) ? 1 : 0;
+      if (span_choice_ < 0) {
+        span_choice_ = (span_ms_[1] / span_n_[1] < 0.9 * span_ms_[0] / span_n_[0]) ? 1 : 0;
+        if (std::getenv("PUMITALLY_DEBUG_SPANS"))
+          fprintf(stderr, "[pumitally] staged %.3f ms, direct %.3f ms per move -> %s\n", span_ms_[0] / span_n_[0],
+                  span_ms_[1] / span_n_[1], span_choice_ ? "direct" : "staged");
+      }
       probe = span_choice_;
     }
     want_staged = probe == 0;
@@ -727,6 +733,7 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
     if (launch_range(d_origin_, d_dest_, d_flying_, d_weights_, b, e, compute_, true)) return 1;
   }
   PTB_CUDA_OK(cudaEventRecord(ev_copy1_, copy_));
+  if (mark_move_done()) return 1;
   // origin slices that went whole were read from the caller's own memory (asynchronously, if it is
   // pinned): they must be on the device before the caller gets its arrays back
   if (caller_memory_on_the_wire) PTB_CUDA_OK(cudaStreamSynchronize(copy_));
@@ -866,6 +873,7 @@ int Engine::move_pinned(const double *origin, const double *dest, int8_t *flying
     PTB_CUDA_OK(cudaEventRecord(pos_events_[k], d2h_));
   }
   PTB_CUDA_OK(cudaEventRecord(ev_copy1_, copy_));
+  if (mark_move_done()) return 1;
   // dest and weights are read from the caller's own arrays: they must be on the device before the
   // caller gets them back (reference: blocking deep_copy)
   PTB_CUDA_OK(cudaStreamSynchronize(copy_));
@@ -887,13 +895,23 @@ void Engine::collect_upload_span() {
   if (span_tag_ < 0 || !ev_copy0_) return;
   if (span_choice_ >= 0) { span_tag_ = -1; return; }  // decided for this epoch
   float ms = 0.f;
-  if (cudaEventSynchronize(ev_copy1_) == cudaSuccess && cudaEventElapsedTime(&ms, ev_copy0_, ev_copy1_) == cudaSuccess) {
+  if (ev_done_ && cudaEventSynchronize(ev_done_) == cudaSuccess && cudaEventElapsedTime(&ms, ev_copy0_, ev_done_) == cudaSuccess) {
     span_ms_[span_tag_] += ms;
     ++span_n_[span_tag_];
+    if (std::getenv("PUMITALLY_DEBUG_SPANS"))
+      fprintf(stderr, "[pumitally] host move %llu: %s path, uploads + walk %.3f ms on the device\n",
+              (unsigned long long)host_moves_ - 1, span_tag_ ? "direct" : "staged", ms);
   } else {
     cudaGetLastError();
   }
   span_tag_ = -1;
+}
+
+// marks the end of a host move's device work (after its last kernel): what collect_upload_span() measures up to
+int Engine::mark_move_done() {
+  if (!ev_done_) PTB_CUDA_OK(cudaEventCreate(&ev_done_));
+  PTB_CUDA_OK(cudaEventRecord(ev_done_, compute_));
+  return 0;
 }
 
 // Direct path: every array is copied from the caller's memory as it is.
@@ -924,6 +942,7 @@ int Engine::move_direct(const double *origin, const double *dest, int8_t *flying
     if (launch_range(d_origin_, d_dest_, d_flying_, d_weights_, b, e, compute_, true)) return 1;
   }
   PTB_CUDA_OK(cudaEventRecord(ev_copy1_, copy_));
+  if (mark_move_done()) return 1;
   h2d_bytes_ += 57.0 * double(n_);
   stage_sent_bytes_ = 57.0 * double(n_);
   // reset the caller's flags once they are on the device (PumiTallyImpl.cpp:169-172)
@@ -1134,6 +1153,9 @@ int64_t Engine::get_option(const std::string &name) const {
     return cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity) == cudaSuccess ? int64_t(g) : -1;
   }
   if (name == "allreduce_us") return int64_t(allreduce_ms_ * 1e3);  // device time of the last batch-end exchange
+  if (name == "exchange_choice") return exchange_choice_;  // what exchange_tally() does: 0 all-reduce, 1 reduce-scatter
+  if (name == "exchange_allreduce_us") return int64_t(exchange_ms_[0] * 1e3);  // comm_init's measurement of the two
+  if (name == "exchange_reduce_scatter_us") return int64_t(exchange_ms_[1] * 1e3);
   if (name == "d2h_bytes") return int64_t(d2h_bytes_);  // particle positions sent back by the pinned-caller path, cumulative
   if (name == "host_path") return host_path_;
   if (name == "host_path_last") return span_tag_ == 1 ? 0 : 1;  // path of the last host move: 1 staged, 0 direct
@@ -1182,6 +1204,8 @@ int Engine::set_option(const std::string &name, int64_t v) {
   } else if (name == "chunk") {
     if (v < 1024) return 1;
     chunk_ = int32_t(std::min<int64_t>(v, INT_MAX)) & ~1023;  // keeps every range 16-byte aligned
+  } else if (name == "exchange_choice") {
+    exchange_choice_ = v ? 1 : 0;  // the caller must set the same value on every rank
   } else if (name == "seed_grid") {
     if (v < 0 || v > 2) return 1;
     seed_grid_mode_ = int(v);
@@ -1254,9 +1278,43 @@ int Engine::comm_init(int rank, int nranks, const uint8_t id[128]) {
   PTB_CUDA_OK(cudaEventCreate(&ev_ar1_));
   PTB_CUDA_OK(cudaMemsetAsync(d_scratch_, 0, size_t(mesh_.ntets) * sizeof(double), compute_));
   if (nccl_allreduce_sum_f64(nccl_comm_, d_scratch_, d_flux_global_, size_t(mesh_.ntets), compute_)) return 1;
+  // ... and so does every other collective the first time it is used (measured: 0.86 s for the first
+  // ncclReduceScatter on 8 GPUs): warm up the reduce-scatter / all-gather pair of reduce_tally_to_owners too.
+  // d_flux_ is all zeros here or holds this rank's tally, which the exchange does not modify.
+  if (nccl_reduce_scatter_sum_f64(nccl_comm_, d_flux_, d_flux_global_ + size_t(rank_) * share_, share_, compute_)) return 1;
+  if (nccl_all_gather_f64(nccl_comm_, d_flux_global_ + size_t(rank_) * share_, d_flux_global_, share_, compute_)) return 1;
   PTB_CUDA_OK(cudaStreamSynchronize(compute_));
+  // Which of the two batch-end exchanges is quicker depends on the array size and on what NCCL picks for it
+  // (measured on 8 B200s: 8 MB of flux -- all-reduce 0.10 ms, reduce-scatter 4.3 ms; 79 MB -- 0.9 ms and 0.43 ms):
+  // time both on this mesh and let exchange_tally() use the quicker one.  The times are summed over the ranks
+  // so that every rank takes the same decision.
+  double t[2] = {1e30, 1e30};
+  for (int rep = 0; rep < 3; ++rep)
+    for (int which = 0; which < 2; ++which) {
+      PTB_CUDA_OK(cudaEventRecord(ev_ar0_, compute_));
+      if (which == 0 ? nccl_allreduce_sum_f64(nccl_comm_, d_flux_, d_flux_global_, size_t(mesh_.ntets), compute_)
+                     : nccl_reduce_scatter_sum_f64(nccl_comm_, d_flux_, d_flux_global_ + size_t(rank_) * share_, share_, compute_))
+        return 1;
+      PTB_CUDA_OK(cudaEventRecord(ev_ar1_, compute_));
+      PTB_CUDA_OK(cudaStreamSynchronize(compute_));
+      float ms = 0.f;
+      PTB_CUDA_OK(cudaEventElapsedTime(&ms, ev_ar0_, ev_ar1_));
+      t[which] = std::min(t[which], double(ms));
+    }
+  double *d_t = d_scratch_;  // E >= 2 doubles of scratch: meshes have more than two elements
+  if (mesh_.ntets < 4) { exchange_choice_ = 0; return 0; }
+  PTB_CUDA_OK(cudaMemcpyAsync(d_t, t, sizeof(t), cudaMemcpyHostToDevice, compute_));
+  if (nccl_allreduce_sum_f64(nccl_comm_, d_t, d_t + 2, 2, compute_)) return 1;
+  PTB_CUDA_OK(cudaMemcpyAsync(t, d_t + 2, sizeof(t), cudaMemcpyDeviceToHost, compute_));
+  PTB_CUDA_OK(cudaStreamSynchronize(compute_));
+  exchange_ms_[0] = t[0] / nranks;
+  exchange_ms_[1] = t[1] / nranks;
+  exchange_choice_ = t[1] < t[0] ? 1 : 0;
   return 0;
 }
+
+// The batch-end exchange this mesh and this machine do quickest (chosen in comm_init)
+int Engine::exchange_tally() { return exchange_choice_ == 1 ? reduce_tally_to_owners() : allreduce_tally(); }
 
 // Batch-end exchange: sum the per-rank tallies.  Every rank holds a full-buffer
 // picpart (all elements are ghosts of every other rank), so the ghost-layer

@@ -80,6 +80,8 @@ class Engine {
   // elements only (ncclReduceScatter: half the traffic of the all-reduce); the shares are gathered
   // (ncclAllGather, collective) the first time a flux accessor or WriteTallyResults needs the whole array.
   int reduce_tally_to_owners();
+  // whichever of the two comm_init measured to be quicker on this mesh (same choice on every rank)
+  int exchange_tally();
 
  private:
   int launch_range(const double *d_origin, const double *d_dest, const int8_t *d_flying,
@@ -180,6 +182,8 @@ class Engine {
   int span_tag_ = -1;                 // path of the move whose span has not been collected yet
   int span_choice_ = -1;              // this epoch's decision: 0 staged, 1 direct, -1 still probing
   void collect_upload_span();
+  int mark_move_done();
+  cudaEvent_t ev_done_ = nullptr;     // after the last kernel of the latest host move
   int host_threads_ = 0;              // 0 = default_host_threads() - 1
   std::unique_ptr<HostStager> stager_;  // worker pool + per-chunk stage pass
   void *stage_base_ = nullptr;
@@ -222,6 +226,8 @@ class Engine {
   // twice.  The accessors return this array until the next move or reset changes the local tally.
   double *d_flux_global_ = nullptr;
   bool flux_global_valid_ = false;
+  int exchange_choice_ = 0;           // 0 all-reduce, 1 reduce-scatter to owners
+  double exchange_ms_[2] = {0, 0};    // comm_init's measurement of both (mean over ranks)
   bool flux_owned_only_ = false;  // d_flux_global_ holds only this rank's share (after reduce_tally_to_owners)
   size_t share_ = 0;              // elements per rank in the scattered layout = ceil(E / nranks)
   int gather_shares();

@@ -68,6 +68,7 @@ C_API = {
     "pumitally_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _u8p]),
     "pumitally_allreduce_tally": (C.c_int, [C.c_void_p]),
     "pumitally_reduce_tally_to_owners": (C.c_int, [C.c_void_p]),
+    "pumitally_exchange_tally": (C.c_int, [C.c_void_p]),
     "pumitally_debug_order": (C.c_int64, [C.c_void_p, _ip, C.c_int64]),
     "pumitally_debug_stage": (C.c_int64, [_dp, _dp, _bp, _dp, _dp, _dp, _bp, C.c_int64, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_int64]),
@@ -293,6 +294,11 @@ class PumiTally:
     def allreduce_tally(self):
         if self._L.pumitally_allreduce_tally(self._h):
             raise RuntimeError("allreduce_tally failed")
+
+    def exchange_tally(self):
+        """Batch-end exchange: the quicker of the two below on this mesh, as measured by comm_init."""
+        if self._L.pumitally_exchange_tally(self._h):
+            raise RuntimeError("exchange_tally failed")
 
     def reduce_tally_to_owners(self):
         """Batch-end exchange by ncclReduceScatter; the flux accessors gather the shares (collective)."""

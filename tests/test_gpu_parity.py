@@ -692,8 +692,11 @@ def _two_gpu_worker(rank, world, port, q, outdir=None):
         # reduce-scatter whose shares are gathered when somebody asks for the flux
         if k == 0:
             eng.allreduce_tally()
-        else:
+        elif k == 1:
             eng.reduce_tally_to_owners()
+        else:
+            assert eng.get_option("exchange_choice") in (0, 1) and eng.get_option("exchange_allreduce_us") >= 0
+            eng.exchange_tally()  # whichever of the two comm_init measured to be quicker here
         if k == 1:
             part = eng.flux  # collective gather on every rank
             assert np.isfinite(part).all()

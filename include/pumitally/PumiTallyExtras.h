@@ -27,6 +27,15 @@ inline int SetSourceNormalization(const PumiTally &tally, int mode, double value
   return pumitally_set_source_normalization(engine_of(tally), mode, value);
 }
 
+// Score filter: `nbins` flux arrays; MoveToNextLocationBinned scores particle i into array bins[i]
+// (see pumitally_set_score_bins in pumitally_c.h).
+inline int SetScoreBins(const PumiTally &tally, int32_t nbins) { return pumitally_set_score_bins(engine_of(tally), nbins); }
+inline int MoveToNextLocationBinned(const PumiTally &tally, double *particle_origin, double *particle_destinations,
+                                    int8_t *flying, double *weights, const int32_t *bins, int32_t size) {
+  return pumitally_move_to_next_location_binned(engine_of(tally), particle_origin, particle_destinations, flying,
+                                                weights, bins, size);
+}
+
 }  // namespace pumitally
 
 #endif  // PUMITALLY_PUMITALLYEXTRAS_H

@@ -69,7 +69,8 @@ pumitally_engine *pumitally_create_from_arrays(const double *coords, int64_t nve
 
 int64_t pumitally_num_elements(const pumitally_engine *e);
 int32_t pumitally_num_particles(const pumitally_engine *e);
-/* raw (un-normalised) flux, double[num_elements] (handler->flux) */
+/* raw (un-normalised) flux, double[num_elements] (handler->flux); with score bins also
+ * n = nbins * num_elements, see pumitally_set_score_bins */
 int pumitally_get_flux(pumitally_engine *e, double *out, int64_t n);
 /* flux / volume and volume (NormalizeFlux, PumiTallyImpl.cpp:382-409); either may be NULL */
 int pumitally_get_normalized_flux(pumitally_engine *e, double *out_flux, double *out_volume,
@@ -174,6 +175,31 @@ int pumitally_reduce_tally_to_owners(pumitally_engine *e);
  * with pumitally_get_option("exchange_choice") (0 all-reduce, 1 reduce-scatter) and the two times with
  * "exchange_allreduce_us" / "exchange_reduce_scatter_us". */
 int pumitally_exchange_tally(pumitally_engine *e);
+
+/* ---- additive: score filter ---------------------------
+ * The reference tallies one flux array (PumiTallyImpl.h:142, flux[elem] += length * weight,
+ * PumiTallyImpl.cpp:376); an OpenMC tally usually carries a filter -- energy group, particle type,
+ * material -- that sends a score to one of several bins.  pumitally_set_score_bins(e, nbins)
+ * gives the engine nbins flux arrays (and resets the tally; on several GPUs call it before
+ * pumitally_comm_init), and the *_binned moves take one more per-particle array: the bin particle i
+ * scores into during this move.  A bin outside [0, nbins) means "no bin matches": the particle
+ * flies and is clipped like any other, unscored.  bins == NULL or nbins == 1 is the plain move.
+ * With nbins > 1, pumitally_get_flux / pumitally_get_normalized_flux accept n = num_elements (bin 0)
+ * or n = nbins * num_elements (every bin, bin-major); pumitally_get_flux_device always writes every
+ * bin; WriteTallyResults writes "flux" = the sum over the bins plus "flux_bin<k>" per bin; the
+ * batch-end exchange moves all bins.  The walk kernels are the unfiltered ones: a binned move walks
+ * the particle range once per bin with the flying flags masked to that bin (particles are independent
+ * and a particle that does not fly is not touched), so it costs one extra pass over the particle
+ * arrays per bin, not per segment. */
+int pumitally_set_score_bins(pumitally_engine *e, int32_t nbins);
+int32_t pumitally_get_score_bins(const pumitally_engine *e);
+int pumitally_move_to_next_location_binned(pumitally_engine *e, const double *particle_origin,
+                                           const double *particle_destinations, int8_t *flying,
+                                           const double *weights, const int32_t *bins, int32_t size);
+int pumitally_move_to_next_location_device_binned(pumitally_engine *e, const double *d_origin,
+                                                  const double *d_destinations, const int8_t *d_flying,
+                                                  const double *d_weights, const int32_t *d_bins,
+                                                  int32_t size, void *stream);
 
 /* test hook: processing order produced by the last binning pass (ids of flying particles
  * grouped by seed-grid cell); returns the number of entries, copies at most n of them */

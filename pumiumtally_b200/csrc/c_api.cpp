@@ -138,6 +138,29 @@ int pumitally_get_adjacency(const pumitally_engine *e, int32_t *out, int64_t n4)
   std::memcpy(out, adj.data(), size_t(n4) * sizeof(int32_t));
   return 0;
 }
+int pumitally_set_score_bins(pumitally_engine *e, int32_t nbins) {
+  return guarded(e, [&](ptb::Engine &g) { return g.set_score_bins(nbins); });
+}
+int32_t pumitally_get_score_bins(const pumitally_engine *e) {
+  return e ? int32_t(pumitally_get_option(e, "score_bins")) : 0;
+}
+int pumitally_move_to_next_location_binned(pumitally_engine *e, const double *origin, const double *dest,
+                                           int8_t *flying, const double *weights, const int32_t *bins, int32_t size) {
+  if (size > 0 && (!origin || !dest || !flying || !weights)) {
+    fprintf(stderr, "[pumitally] ERROR: MoveToNextLocation: null input array\n");
+    return 1;
+  }
+  return guarded(e, [&](ptb::Engine &g) { return g.move_to_next_location_binned(origin, dest, flying, weights, bins, size); });
+}
+int pumitally_move_to_next_location_device_binned(pumitally_engine *e, const double *d_origin, const double *d_dest,
+                                                  const int8_t *d_flying, const double *d_weights, const int32_t *d_bins,
+                                                  int32_t size, void *stream) {
+  return guarded(e, [&](ptb::Engine &g) {
+    return g.move_to_next_location_device_binned(d_origin, d_dest, d_flying, d_weights, d_bins, size,
+                                                 static_cast<cudaStream_t>(stream));
+  });
+}
+
 int pumitally_reset_tally(pumitally_engine *e) {
   return guarded(e, [&](ptb::Engine &g) { return g.reset_tally(); });
 }

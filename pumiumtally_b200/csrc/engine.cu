@@ -65,6 +65,7 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
 
   const size_t E = size_t(mesh_.ntets), N = size_t(n_);
   dev_alloc(&d_tets_, E, "tet records");
+  flux_alloc_ = E + kFluxPad;
   dev_alloc(&d_flux_, E + kFluxPad, "flux");  // padded: the reduce-scatter exchange sends nranks equal shares
   dev_alloc(&d_volume_, E, "volume");
   dev_alloc(&d_scratch_, E, "scratch");
@@ -138,6 +139,10 @@ Engine::~Engine() {
   cudaFree(d_flux_global_);
   if (ev_order_) cudaEventDestroy(ev_order_);
   if (ev_done_) cudaEventDestroy(ev_done_);
+  if (ev_bins_) cudaEventDestroy(ev_bins_);
+  if (ev_bins_free_) cudaEventDestroy(ev_bins_free_);
+  cudaFree(d_mask_);
+  cudaFree(d_bins_);
   if (ev_copy0_) cudaEventDestroy(ev_copy0_);
   if (ev_copy1_) cudaEventDestroy(ev_copy1_);
   if (ev_ar0_) cudaEventDestroy(ev_ar0_);
@@ -306,6 +311,22 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   last_stream_ = stream;
   last_stream_set_ = true;
   if (d_dest) flux_global_valid_ = flux_owned_only_ = false;  // the local tally moves on; the last exchange no longer describes it
+  if (!(cur_bins_ && d_dest)) return launch_range_into(d_flux_, d_origin, d_dest, d_flying, d_weights, begin, end, stream, timed);
+  // Score filter: particles are independent and a particle that does not fly is not touched, so the range
+  // is walked once per bin with the flying flags masked down to that bin's particles and the tally pointed
+  // at that bin's flux array -- the walk kernels themselves are the unfiltered ones.  One more pass (array
+  // nbins_, never reported) flies the particles whose bin is outside [0, nbins_): they move, unscored.
+  for (int32_t b = 0; b <= nbins_; ++b) {
+    PTB_CUDA_OK(launch_bin_mask(d_flying, cur_bins_, b, nbins_, d_mask_, begin, end, stream));
+    ++launches_;
+    if (launch_range_into(d_flux_ + size_t(b) * size_t(mesh_.ntets), d_origin, d_dest, d_mask_, d_weights, begin, end, stream, timed))
+      return 1;
+  }
+  return 0;
+}
+
+int Engine::launch_range_into(double *d_flux, const double *d_origin, const double *d_dest, const int8_t *d_flying,
+                              const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream, bool timed) {
   if (d_dest && d_weights && initial_weight_pending_)  // first tracks of the batch: their total weight
     PTB_CUDA_OK(launch_sum_flying_weights(d_flying, d_weights, begin, end, d_initial_weight_, stream));
   WalkParams p{};
@@ -313,7 +334,7 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   p.links = d_links_;
   p.verts = d_verts_;
   p.starts = d_starts_;
-  p.flux = d_flux_;
+  p.flux = d_flux;
   p.state = d_state_;
   p.origin = d_origin;
   p.dest = d_dest;
@@ -974,6 +995,66 @@ int Engine::move_to_next_location_device(const double *d_origin, const double *d
   return 0;
 }
 
+// Score filter (OpenMC: an energy / material / ... filter on the tally).  nbins flux
+// arrays of E doubles, bin-major, plus one unreported array for the particles no bin matches.
+int Engine::set_score_bins(int32_t nbins) {
+  if (nbins < 1 || nbins > 4096) return 1;
+  if (nccl_comm_) {
+    fprintf(stderr, "[pumitally] ERROR: set_score_bins after comm_init (the exchange buffers are sized by then)\n");
+    return 1;
+  }
+  if (synchronize()) return 1;
+  const size_t E = size_t(mesh_.ntets), len = size_t(nbins > 1 ? nbins + 1 : 1) * E + kFluxPad;
+  double *nf = nullptr;
+  PTB_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&nf), len * sizeof(double)));
+  cudaFree(d_flux_);
+  d_flux_ = nf;
+  flux_alloc_ = len;
+  nbins_ = nbins;
+  if (nbins > 1 && !d_mask_) {
+    PTB_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&d_mask_), std::max<size_t>(size_t(n_), 16)));
+    PTB_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&d_bins_), std::max<size_t>(size_t(n_), 4) * sizeof(int32_t)));
+  }
+  return reset_tally();  // a new set of arrays starts from zero
+}
+
+// MoveToNextLocation with a score bin per particle for this move (host pointers).  bins == nullptr or one
+// bin: the plain move.  The bins travel in one copy ahead of the particle data; everything else is the
+// ordinary host path (the pinned-caller variant excepted, whose relocation pass knows nothing of bins).
+int Engine::move_to_next_location_binned(const double *origin, const double *dest, int8_t *flying, const double *weights,
+                                         const int32_t *bins, int32_t size) {
+  if (!bins || nbins_ == 1) return move_to_next_location(origin, dest, flying, weights, size);
+  if (int64_t(size) != 3 * int64_t(n_) || !initialized_) return move_to_next_location(origin, dest, flying, weights, size);  // prints the error
+  PTB_CUDA_OK(cudaSetDevice(device_));
+  if (!ev_bins_) {
+    PTB_CUDA_OK(cudaEventCreateWithFlags(&ev_bins_, cudaEventDisableTiming));
+    PTB_CUDA_OK(cudaEventCreateWithFlags(&ev_bins_free_, cudaEventDisableTiming));
+  }
+  // d_bins_ is read by the mask kernels of the previous move until they are done
+  PTB_CUDA_OK(cudaEventRecord(ev_bins_free_, compute_));
+  PTB_CUDA_OK(cudaStreamWaitEvent(copy_, ev_bins_free_, 0));
+  PTB_CUDA_OK(cudaMemcpyAsync(d_bins_, bins, size_t(n_) * sizeof(int32_t), cudaMemcpyHostToDevice, copy_));
+  PTB_CUDA_OK(cudaEventRecord(ev_bins_, copy_));
+  h2d_bytes_ += 4.0 * double(n_);
+  cur_bins_ = d_bins_;
+  const bool pinned_path = pinned_path_;
+  pinned_path_ = false;
+  const int rc = move_to_next_location(origin, dest, flying, weights, size);
+  pinned_path_ = pinned_path;
+  cur_bins_ = nullptr;
+  PTB_CUDA_OK(cudaEventSynchronize(ev_bins_));  // the caller gets `bins` back with the other arrays
+  return rc;
+}
+
+int Engine::move_to_next_location_device_binned(const double *d_origin, const double *d_dest, const int8_t *d_flying,
+                                                const double *d_weights, const int32_t *d_bins, int32_t size,
+                                                cudaStream_t stream) {
+  cur_bins_ = (d_bins && nbins_ > 1) ? d_bins : nullptr;
+  const int rc = move_to_next_location_device(d_origin, d_dest, d_flying, d_weights, size, stream);
+  cur_bins_ = nullptr;
+  return rc;
+}
+
 int Engine::synchronize() {
   PTB_CUDA_OK(cudaSetDevice(device_));
   PTB_CUDA_OK(cudaDeviceSynchronize());
@@ -1012,25 +1093,32 @@ int Engine::get_state_device(double *d_xyz, int32_t *d_elem, int32_t first, int3
   return 0;
 }
 
+// (all score bins, bin-major: nbins * E values)
 int Engine::get_flux_device(double *d_out, cudaStream_t stream) {
   PTB_CUDA_OK(cudaSetDevice(device_));
   if (ensure_element_maps() || gather_shares()) return 1;
-  PTB_CUDA_OK(launch_flux_to_caller_order(flux_view(), d_orig_of_internal_, d_out, mesh_.ntets, stream));
+  const size_t E = size_t(mesh_.ntets);
+  for (int32_t b = 0; b < nbins_; ++b)
+    PTB_CUDA_OK(launch_flux_to_caller_order(flux_view() + size_t(b) * E, d_orig_of_internal_, d_out + size_t(b) * E, mesh_.ntets, stream));
   return 0;
 }
 
+// n == E: the first (or only) score bin; n == nbins * E: every bin, bin-major
 int Engine::get_flux(double *out, int64_t n) {
-  if (n != mesh_.ntets) return 1;
+  const int64_t E = mesh_.ntets;
+  if (n != E && n != int64_t(nbins_) * E) return 1;
   if (synchronize() || gather_shares()) return 1;
   std::vector<double> tmp(static_cast<size_t>(n));
   PTB_CUDA_OK(cudaMemcpy(tmp.data(), flux_view(), size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
-  for (int64_t i = 0; i < n; ++i) out[mesh_.orig_of_internal[i]] = tmp[i];  // caller's numbering
+  for (int64_t b = 0; b * E < n; ++b)
+    for (int64_t i = 0; i < E; ++i) out[b * E + mesh_.orig_of_internal[i]] = tmp[b * E + i];  // caller's numbering
   return 0;
 }
 
-// NormalizeFlux (PumiTallyImpl.cpp:382-409)
+// NormalizeFlux (PumiTallyImpl.cpp:382-409); n as for get_flux (the volumes are always E values)
 int Engine::get_normalized_flux(double *out_flux, double *out_volume, int64_t n) {
-  if (n != mesh_.ntets) return 1;
+  const int64_t E = mesh_.ntets;
+  if (n != E && n != int64_t(nbins_) * E) return 1;
   if (synchronize() || gather_shares()) return 1;
   if (out_flux) {
     const double per_source = source_normalization();
@@ -1038,14 +1126,16 @@ int Engine::get_normalized_flux(double *out_flux, double *out_volume, int64_t n)
       fprintf(stderr, "[pumitally] ERROR: source normalisation divisor is %g (no source weight seen yet?)\n", per_source);
       return 1;
     }
-    PTB_CUDA_OK(launch_normalize(flux_view(), d_volume_, d_scratch_, n, per_source, compute_));
-    PTB_CUDA_OK(cudaStreamSynchronize(compute_));
-    std::vector<double> tmp(static_cast<size_t>(n));
-    PTB_CUDA_OK(cudaMemcpy(tmp.data(), d_scratch_, size_t(n) * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int64_t i = 0; i < n; ++i) out_flux[mesh_.orig_of_internal[i]] = tmp[i];
+    std::vector<double> tmp(static_cast<size_t>(E));
+    for (int64_t b = 0; b * E < n; ++b) {
+      PTB_CUDA_OK(launch_normalize(flux_view() + size_t(b * E), d_volume_, d_scratch_, E, per_source, compute_));
+      PTB_CUDA_OK(cudaStreamSynchronize(compute_));
+      PTB_CUDA_OK(cudaMemcpy(tmp.data(), d_scratch_, size_t(E) * sizeof(double), cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < E; ++i) out_flux[b * E + mesh_.orig_of_internal[i]] = tmp[i];
+    }
   }
   if (out_volume)
-    for (int64_t i = 0; i < n; ++i) out_volume[mesh_.orig_of_internal[i]] = mesh_.volume[i];
+    for (int64_t i = 0; i < E; ++i) out_volume[mesh_.orig_of_internal[i]] = mesh_.volume[i];
   return 0;
 }
 
@@ -1097,7 +1187,7 @@ int Engine::reset_tally() {
   collect_timers(true);
   PTB_CUDA_OK(cudaMemset(d_initial_weight_, 0, sizeof(double)));
   initial_weight_pending_ = true;
-  PTB_CUDA_OK(cudaMemset(d_flux_, 0, (size_t(mesh_.ntets) + kFluxPad) * sizeof(double)));
+  PTB_CUDA_OK(cudaMemset(d_flux_, 0, flux_alloc_ * sizeof(double)));
   PTB_CUDA_OK(cudaMemset(d_stats_, 0, sizeof(DeviceStats)));
   flux_global_valid_ = flux_owned_only_ = false;
   kernel_ms_ = 0.0;
@@ -1153,6 +1243,7 @@ int64_t Engine::get_option(const std::string &name) const {
     return cudaDeviceGetLimit(&g, cudaLimitMaxL2FetchGranularity) == cudaSuccess ? int64_t(g) : -1;
   }
   if (name == "allreduce_us") return int64_t(allreduce_ms_ * 1e3);  // device time of the last batch-end exchange
+  if (name == "score_bins") return nbins_;
   if (name == "exchange_choice") return exchange_choice_;  // what exchange_tally() does: 0 all-reduce, 1 reduce-scatter
   if (name == "exchange_allreduce_us") return int64_t(exchange_ms_[0] * 1e3);  // comm_init's measurement of the two
   if (name == "exchange_reduce_scatter_us") return int64_t(exchange_ms_[1] * 1e3);
@@ -1251,10 +1342,22 @@ int64_t Engine::debug_order(int32_t *out, int64_t n) {
 
 // FinalizeTallies (PumiTallyImpl.cpp:411-416)
 int Engine::write_tally_results() {
-  std::vector<double> nf(static_cast<size_t>(mesh_.ntets)), vol(static_cast<size_t>(mesh_.ntets));
-  if (get_normalized_flux(nf.data(), vol.data(), mesh_.ntets)) return 1;  // caller's element order
+  const size_t E = size_t(mesh_.ntets);
+  std::vector<double> nf(E * size_t(nbins_)), vol(E);
+  if (get_normalized_flux(nf.data(), vol.data(), int64_t(nf.size()))) return 1;  // caller's element order
+  // filtered tally: "flux" is the sum over the bins (what the unfiltered tally would hold), and every
+  // bin is written as "flux_bin<k>" next to it
+  std::vector<std::pair<std::string, const double *>> extra;
+  std::vector<double> per_bin;
+  if (nbins_ > 1) {
+    per_bin.assign(nf.begin(), nf.end());
+    for (int32_t b = 0; b < nbins_; ++b) extra.emplace_back("flux_bin" + std::to_string(b), per_bin.data() + size_t(b) * E);
+    for (int32_t b = 1; b < nbins_; ++b)
+      for (size_t i = 0; i < E; ++i) nf[i] += nf[size_t(b) * E + i];
+    nf.resize(E);
+  }
   std::string err;
-  if (!write_vtk_dataset(output_name_, mesh_, nf, vol, rank_, nranks_, &err)) {
+  if (!write_vtk_dataset(output_name_, mesh_, nf, vol, rank_, nranks_, &err, extra)) {
     fprintf(stderr, "[pumitally] ERROR: %s\n", err.c_str());
     return 1;
   }
@@ -1272,7 +1375,7 @@ int Engine::comm_init(int rank, int nranks, const uint8_t id[128]) {
   // NCCL sets up its NVLink connections lazily inside the first collective: pay that here,
   // on the scratch array, not in the first batch-end exchange
   if (nranks < 1 || size_t(nranks) > kFluxPad) return 1;
-  share_ = (size_t(mesh_.ntets) + size_t(nranks) - 1) / size_t(nranks);
+  share_ = (flux_len() + size_t(nranks) - 1) / size_t(nranks);
   PTB_CUDA_OK(cudaMalloc(reinterpret_cast<void **>(&d_flux_global_), std::max<size_t>(share_ * size_t(nranks), 1) * sizeof(double)));
   PTB_CUDA_OK(cudaEventCreate(&ev_ar0_));
   PTB_CUDA_OK(cudaEventCreate(&ev_ar1_));
@@ -1292,7 +1395,7 @@ int Engine::comm_init(int rank, int nranks, const uint8_t id[128]) {
   for (int rep = 0; rep < 3; ++rep)
     for (int which = 0; which < 2; ++which) {
       PTB_CUDA_OK(cudaEventRecord(ev_ar0_, compute_));
-      if (which == 0 ? nccl_allreduce_sum_f64(nccl_comm_, d_flux_, d_flux_global_, size_t(mesh_.ntets), compute_)
+      if (which == 0 ? nccl_allreduce_sum_f64(nccl_comm_, d_flux_, d_flux_global_, flux_len(), compute_)
                      : nccl_reduce_scatter_sum_f64(nccl_comm_, d_flux_, d_flux_global_ + size_t(rank_) * share_, share_, compute_))
         return 1;
       PTB_CUDA_OK(cudaEventRecord(ev_ar1_, compute_));
@@ -1325,7 +1428,7 @@ int Engine::allreduce_tally() {
   PTB_CUDA_OK(cudaSetDevice(device_));
   PTB_CUDA_OK(cudaDeviceSynchronize());
   PTB_CUDA_OK(cudaEventRecord(ev_ar0_, compute_));
-  if (nccl_allreduce_sum_f64(nccl_comm_, d_flux_, d_flux_global_, size_t(mesh_.ntets), compute_)) return 1;
+  if (nccl_allreduce_sum_f64(nccl_comm_, d_flux_, d_flux_global_, flux_len(), compute_)) return 1;
   PTB_CUDA_OK(cudaEventRecord(ev_ar1_, compute_));
   PTB_CUDA_OK(cudaStreamSynchronize(compute_));
   float ms = 0.f;

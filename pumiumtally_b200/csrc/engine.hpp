@@ -48,6 +48,14 @@ class Engine {
                                    const int8_t *d_flying, const double *d_weights, int32_t size,
                                    cudaStream_t stream);
 
+  // Score filter: nbins flux arrays; a binned move tallies particle i into array bins[i] (outside
+  // [0, nbins): the particle flies unscored).  Resets the tally.  Before comm_init on multi-GPU runs.
+  int set_score_bins(int32_t nbins);
+  int32_t score_bins() const { return nbins_; }
+  int move_to_next_location_binned(const double *origin, const double *dest, int8_t *flying, const double *weights,
+                                   const int32_t *bins, int32_t size);
+  int move_to_next_location_device_binned(const double *d_origin, const double *d_dest, const int8_t *d_flying,
+                                          const double *d_weights, const int32_t *d_bins, int32_t size, cudaStream_t stream);
   int get_flux(double *out, int64_t n);
   // Device-side accessors, caller's element numbering, enqueued on `stream` (no synchronisation).
   int set_state_device(const double *d_xyz, const int32_t *d_elem, int32_t first, int32_t count, cudaStream_t stream);
@@ -87,6 +95,15 @@ class Engine {
   int launch_range(const double *d_origin, const double *d_dest, const int8_t *d_flying,
                    const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream,
                    bool timed);
+  int launch_range_into(double *d_flux, const double *d_origin, const double *d_dest, const int8_t *d_flying,
+                        const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream, bool timed);
+  int32_t nbins_ = 1;
+  size_t flux_alloc_ = 0;             // doubles allocated at d_flux_
+  size_t flux_len() const { return size_t(nbins_) * size_t(mesh_.ntets); }  // reported part of d_flux_
+  const int32_t *cur_bins_ = nullptr; // device array of the move being launched (binned moves only)
+  int8_t *d_mask_ = nullptr;          // [N] flying flags of one bin
+  int32_t *d_bins_ = nullptr;         // [N] bins of a host-pointer move
+  cudaEvent_t ev_bins_ = nullptr, ev_bins_free_ = nullptr;
   bool host_is_pinned(const void *p) const;
   void maybe_register(const void *p, size_t bytes);
   void collect_timers(bool wait);

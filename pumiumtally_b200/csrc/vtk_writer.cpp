@@ -25,7 +25,8 @@ struct Block {
 }  // namespace
 
 bool write_vtk_dataset(const std::string &path, const HostMesh &m, const std::vector<double> &flux,
-                       const std::vector<double> &volume, int rank, int nranks, std::string *err) {
+                       const std::vector<double> &volume, int rank, int nranks, std::string *err,
+                       const std::vector<std::pair<std::string, const double *>> &extra) {
   if (!make_dir(path, err) || !make_dir(path + "/pieces", err)) return false;
   const uint64_t V = uint64_t(m.nverts), Etot = uint64_t(m.ntets);
   // One piece per rank.  After the batch-end exchange every rank holds the same global tally, so
@@ -49,11 +50,13 @@ bool write_vtk_dataset(const std::string &path, const HostMesh &m, const std::ve
                        ab[2] * (ac[0] * ad[1] - ac[1] * ad[0]);
     if (det < 0.0) std::swap(v[2], v[3]);
   }
-  const Block blocks[6] = {{m.coords.data(), V * 24}, {conn.data() + 4 * e0, E * 16},
-                           {offsets.data(), E * 4},   {types.data(), E},
-                           {flux.data() + e0, E * 8}, {volume.data() + e0, E * 8}};
-  uint64_t off[6], acc = 0;
-  for (int i = 0; i < 6; ++i) { off[i] = acc; acc += 8 + blocks[i].bytes; }
+  std::vector<Block> blocks = {{m.coords.data(), V * 24}, {conn.data() + 4 * e0, E * 16},
+                               {offsets.data(), E * 4},   {types.data(), E},
+                               {flux.data() + e0, E * 8}, {volume.data() + e0, E * 8}};
+  for (const auto &x : extra) blocks.push_back({x.second + e0, E * 8});  // whole-mesh arrays, caller's element order
+  std::vector<uint64_t> off(blocks.size());
+  uint64_t acc = 0;
+  for (size_t i = 0; i < blocks.size(); ++i) { off[i] = acc; acc += 8 + blocks[i].bytes; }
 
   const std::string piece = path + "/pieces/piece_" + std::to_string(rank) + ".vtu";
   std::ofstream f(piece, std::ios::binary);
@@ -70,10 +73,12 @@ bool write_vtk_dataset(const std::string &path, const HostMesh &m, const std::ve
     << "</Cells>\n"
     << "<CellData>\n"
     << "<DataArray type=\"Float64\" Name=\"flux\" NumberOfComponents=\"1\" format=\"appended\" offset=\"" << off[4] << "\"/>\n"
-    << "<DataArray type=\"Float64\" Name=\"volume\" NumberOfComponents=\"1\" format=\"appended\" offset=\"" << off[5] << "\"/>\n"
-    << "</CellData>\n"
+    << "<DataArray type=\"Float64\" Name=\"volume\" NumberOfComponents=\"1\" format=\"appended\" offset=\"" << off[5] << "\"/>\n";
+  for (size_t i = 0; i < extra.size(); ++i)
+    f << "<DataArray type=\"Float64\" Name=\"" << extra[i].first << "\" NumberOfComponents=\"1\" format=\"appended\" offset=\"" << off[6 + i] << "\"/>\n";
+  f << "</CellData>\n"
     << "</Piece>\n</UnstructuredGrid>\n<AppendedData encoding=\"raw\">\n_";
-  for (int i = 0; i < 6; ++i) {
+  for (size_t i = 0; i < blocks.size(); ++i) {
     f.write(reinterpret_cast<const char *>(&blocks[i].bytes), 8);
     f.write(reinterpret_cast<const char *>(blocks[i].data), std::streamsize(blocks[i].bytes));
   }
@@ -90,8 +95,9 @@ bool write_vtk_dataset(const std::string &path, const HostMesh &m, const std::ve
       << "<PPoints>\n<PDataArray type=\"Float64\" Name=\"coordinates\" NumberOfComponents=\"3\"/>\n</PPoints>\n"
       << "<PCellData>\n"
       << "<PDataArray type=\"Float64\" Name=\"flux\" NumberOfComponents=\"1\"/>\n"
-      << "<PDataArray type=\"Float64\" Name=\"volume\" NumberOfComponents=\"1\"/>\n"
-      << "</PCellData>\n";
+      << "<PDataArray type=\"Float64\" Name=\"volume\" NumberOfComponents=\"1\"/>\n";
+    for (const auto &x : extra) p << "<PDataArray type=\"Float64\" Name=\"" << x.first << "\" NumberOfComponents=\"1\"/>\n";
+    p << "</PCellData>\n";
     for (int r = 0; r < nranks; ++r) p << "<Piece Source=\"pieces/piece_" << r << ".vtu\"/>\n";
     p << "</PUnstructuredGrid>\n</VTKFile>\n";
   }

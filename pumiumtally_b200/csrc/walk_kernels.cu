@@ -170,6 +170,17 @@ __global__ void normalize_kernel(const double *flux, const double *volume, doubl
   if (e < n) out[e] = flux[e] / volume[e] / per_source;  // per_source == 1: bit-identical to flux / volume
 }
 
+// Score filter (engine.cu, launch_range): the flying flags of the particles whose score bin is `bin`
+// (bin == nbins: of those whose bin is outside [0, nbins) -- they fly, unscored)
+__global__ void bin_mask_kernel(const int8_t *flying, const int32_t *bins, int32_t bin, int32_t nbins, int8_t *mask,
+                                int32_t begin, int32_t end) {
+  const int i = begin + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= end) return;
+  const int32_t b = bins[i];
+  const bool mine = (b >= 0 && b < nbins) ? b == bin : bin == nbins;
+  mask[i] = (mine && (!flying || flying[i] == 1)) ? 1 : 0;
+}
+
 // Total weight of the particles that fly in this range (the reference's total_initial_weight,
 // PumiTallyImpl.h:170-171: declared "needed for normalization", never filled in).
 __global__ void sum_flying_weights_kernel(const int8_t *flying, const double *weights, int32_t begin, int32_t end,
@@ -295,6 +306,13 @@ cudaError_t launch_normalize(const double *flux, const double *volume, double *o
                              double per_source, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   normalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(flux, volume, out, n, per_source);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bin_mask(const int8_t *flying, const int32_t *bins, int32_t bin, int32_t nbins, int8_t *mask,
+                            int32_t begin, int32_t end, cudaStream_t stream) {
+  if (end <= begin) return cudaSuccess;
+  bin_mask_kernel<<<(end - begin + 255) / 256, 256, 0, stream>>>(flying, bins, bin, nbins, mask, begin, end);
   return cudaGetLastError();
 }
 

@@ -97,6 +97,9 @@ cudaError_t launch_export_positions(const ParticleState *state, double *xyz, int
 cudaError_t launch_normalize(const double *flux, const double *volume, double *out, int64_t n,
                              double per_source, cudaStream_t stream);
 // *total += sum of weights[i] over flying particles of [begin, end)
+// mask[i] = flying[i] && bins[i] == bin  (bin == nbins selects the particles outside [0, nbins))
+cudaError_t launch_bin_mask(const int8_t *flying, const int32_t *bins, int32_t bin, int32_t nbins, int8_t *mask,
+                            int32_t begin, int32_t end, cudaStream_t stream);
 cudaError_t launch_sum_flying_weights(const int8_t *flying, const double *weights, int32_t begin, int32_t end,
                                       double *total, cudaStream_t stream);
 

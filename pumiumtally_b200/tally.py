@@ -39,6 +39,11 @@ C_API = {
     "pumitally_create": (C.c_void_p, [C.c_char_p, C.c_int32, C.POINTER(C.c_int), C.c_void_p]),
     "pumitally_copy_initial_position": (C.c_int, [C.c_void_p, _dp, C.c_int32]),
     "pumitally_move_to_next_location": (C.c_int, [C.c_void_p, _dp, _dp, _bp, _dp, C.c_int32]),
+    "pumitally_move_to_next_location_binned": (C.c_int, [C.c_void_p, _dp, _dp, _bp, _dp, _ip, C.c_int32]),
+    "pumitally_move_to_next_location_device_binned": (
+        C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "pumitally_set_score_bins": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pumitally_get_score_bins": (C.c_int32, [C.c_void_p]),
     "pumitally_write_tally_results": (C.c_int, [C.c_void_p]),
     "pumitally_destroy": (None, [C.c_void_p]),
     "pumitally_create_from_arrays": (C.c_void_p, [_dp, C.c_int64, _ip, C.c_int64, C.c_int32, C.c_int32]),
@@ -173,6 +178,49 @@ class PumiTally:
         if self._L.pumitally_move_to_next_location(self._h, o.ctypes.data_as(_dp), d.ctypes.data_as(_dp),
                                                    flying.ctypes.data_as(_bp), w.ctypes.data_as(_dp), size):
             raise RuntimeError("MoveToNextLocation failed")
+
+    # ---- score filter ----------------------------------------------------------
+    def set_score_bins(self, nbins: int):
+        """nbins flux arrays (resets the tally); binned moves score particle i into array bins[i]."""
+        if self._L.pumitally_set_score_bins(self._h, int(nbins)):
+            raise ValueError(f"set_score_bins({nbins}) failed")
+
+    @property
+    def score_bins(self) -> int:
+        return int(self._L.pumitally_get_score_bins(self._h))
+
+    def MoveToNextLocationBinned(self, particle_origin, particle_destinations, flying, weights, bins, size=None):
+        o = _host_f64(particle_origin, "particle_origin")
+        d = _host_f64(particle_destinations, "particle_destinations")
+        w = _host_f64(weights, "weights")
+        if not (isinstance(flying, np.ndarray) and flying.dtype == np.int8 and flying.flags.c_contiguous):
+            raise TypeError("flying must be a contiguous int8 numpy array (the engine zeroes it)")
+        if not (isinstance(bins, np.ndarray) and bins.dtype == np.int32 and bins.flags.c_contiguous and bins.size == w.size):
+            raise TypeError("bins must be a contiguous int32 numpy array, one entry per particle")
+        size = o.size if size is None else int(size)
+        if self._L.pumitally_move_to_next_location_binned(self._h, o.ctypes.data_as(_dp), d.ctypes.data_as(_dp),
+                                                          flying.ctypes.data_as(_bp), w.ctypes.data_as(_dp),
+                                                          bins.ctypes.data_as(_ip), size):
+            raise RuntimeError("MoveToNextLocationBinned failed")
+
+    def move_device_binned(self, d_origin, d_dest, d_flying, d_weights, d_bins, stream=None):
+        if self._L.pumitally_move_to_next_location_device_binned(self._h, d_origin, d_dest, d_flying, d_weights, d_bins,
+                                                                 3 * self.num_particles, stream):
+            raise RuntimeError("MoveToNextLocationBinned(device) failed")
+
+    @property
+    def flux_bins(self):
+        """Raw flux of every score bin: array [nbins, num_elements]."""
+        out = np.empty((self.score_bins, self.num_elements))
+        if self._L.pumitally_get_flux(self._h, out.ctypes.data_as(_dp), out.size):
+            raise RuntimeError("get_flux failed")
+        return out
+
+    def normalized_flux_bins(self):
+        f, v = np.empty((self.score_bins, self.num_elements)), np.empty(self.num_elements)
+        if self._L.pumitally_get_normalized_flux(self._h, f.ctypes.data_as(_dp), v.ctypes.data_as(_dp), f.size):
+            raise RuntimeError("get_normalized_flux failed")
+        return f, v
 
     def WriteTallyResults(self, filename=None):
         if filename is not None:

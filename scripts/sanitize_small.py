@@ -51,3 +51,28 @@ for v in variants:
         np.testing.assert_allclose(fl.cpu().numpy(), e.flux, rtol=0, atol=0)
         e.normalized_flux()
         print("variant", v, opts, "ok", flush=True)
+
+# score filter: per-bin masked passes (mask kernel + the unfiltered walk kernels), host and device entry points
+import torch
+from helpers import oracle_binned_move
+coords, t2v, wl = box_case((5, 5, 4), 4001)
+e, orc = PumiTally.from_arrays(coords, t2v, wl.n), OraclePumiTally(coords, t2v, wl.n)
+e.set_option("chunk", 1024)
+e.set_score_bins(3)
+init = wl.initial_positions()
+for x in (e, orc):
+    x.CopyInitialPosition(init.reshape(-1).copy())
+want = np.zeros((3, len(t2v)))
+for step in range(2):
+    o, d, f, w = wl.next_step()
+    bins = (np.arange(wl.n, dtype=np.int32) * 7 + step) % 5 - 1  # -1 .. 3: some outside [0, 3)
+    if step == 0:
+        e.MoveToNextLocationBinned(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy(), bins)
+    else:
+        t = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (o, d, f, w, bins)]
+        e.move_device_binned(*(x.data_ptr() for x in t), None)
+        torch.cuda.synchronize()
+    oracle_binned_move(orc, want, o, d, f, w, bins)
+np.testing.assert_allclose(e.flux_bins, want, rtol=1e-9, atol=1e-12)
+np.testing.assert_array_equal(e.elem_ids, orc.elem_ids)
+print("score bins ok", flush=True)

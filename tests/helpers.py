@@ -59,6 +59,22 @@ def run_workload(engine, oracle, workload, steps, check_each_step=True, label=""
             assert_positions_close(engine.positions, oracle.positions, f"{label} step {s}")
 
 
+def oracle_binned_move(oracle, flux_bins, o, d, f, w, bins):
+    """A binned move on the (unfiltered) oracle: particles are independent and non-flying particles are not
+    touched, so one oracle move per bin with the flying flags masked to that bin is the filtered tally; the
+    flux each of them adds goes to flux_bins[bin].  Bins outside [0, nbins) fly unscored."""
+    nb = flux_bins.shape[0]
+    inside = (bins >= 0) & (bins < nb)
+    for b in list(range(nb)) + [nb]:
+        mask = ((f == 1) & ((bins == b) if b < nb else ~inside)).astype(np.int8)
+        if not mask.any():
+            continue
+        before = oracle.flux.copy()
+        oracle.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), mask, w.copy())
+        if b < nb:
+            flux_bins[b] += oracle.flux - before
+
+
 # ---------------------------------------------------------------------------
 # test-only host build of the device walk logic (tests/host_emul/emul_walk.cpp)
 # ---------------------------------------------------------------------------

@@ -9,9 +9,9 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import (ROOT, assert_flux_close, box_case, edge_case_scenario, lattice_track_scenario,
-                     non_convex_relocation_scenario, non_finite_input_scenario, run_workload,
-                     unstructured_special_point_scenario)
+from helpers import (ROOT, assert_flux_close, assert_positions_close, box_case, edge_case_scenario,
+                     lattice_track_scenario, non_convex_relocation_scenario, non_finite_input_scenario,
+                     oracle_binned_move, run_workload, unstructured_special_point_scenario)
 from oracle.oracle import OraclePumiTally
 from pumiumtally_b200.mesh import delaunay_box, jitter_interior, kuhn_box, save_raw_mesh, tet_volumes
 from pumiumtally_b200.tally import PumiTally
@@ -620,6 +620,99 @@ def test_normalized_flux_reset_and_vtk_output(tmp_path):
     np.testing.assert_allclose(e.normalized_flux()[0], e.flux / vol / want, rtol=1e-13)
 
 
+def _bins_for_step(n, nbins, step):
+    rng = np.random.default_rng(1000 + step)
+    bins = rng.integers(0, nbins, n, dtype=np.int32)
+    bins[rng.random(n) < 0.07] = -1            # no bin matches: flies unscored
+    bins[rng.random(n) < 0.03] = nbins + 5     # likewise
+    return bins
+
+
+@pytest.mark.parametrize("variant", [-1, 0, 8, 16, 24])
+def test_score_bins_host_moves_match_the_oracle_bin_by_bin(variant, tmp_path):
+    """Score filter: particle i scores into flux array bins[i] of this move; the bins change
+    from move to move; particles outside every bin move like the others and score nowhere."""
+    nbins = 3
+    coords, t2v, wl = box_case((6, 6, 5), 20_000)
+    e = gpu_engine(variant, chunk=4096)(coords, t2v, wl.n)
+    e.set_score_bins(nbins)
+    assert e.score_bins == nbins
+    orc = OraclePumiTally(coords, t2v, wl.n)
+    init = wl.initial_positions()
+    e.CopyInitialPosition(init.reshape(-1).copy())
+    orc.CopyInitialPosition(init.reshape(-1).copy())
+    want = np.zeros((nbins, len(t2v)))
+    for step in range(3):
+        o, d, f, w = wl.next_step()
+        bins = _bins_for_step(wl.n, nbins, step)
+        f1 = f.copy()
+        e.MoveToNextLocationBinned(o.reshape(-1).copy(), d.reshape(-1).copy(), f1, w.copy(), bins)
+        assert not f1.any()
+        oracle_binned_move(orc, want, o, d, f, w, bins)
+        got = e.flux_bins
+        for b in range(nbins):
+            assert_flux_close(got[b], want[b], f"bin {b} step {step}")
+        np.testing.assert_array_equal(e.flux, got[0])  # n = num_elements: the first bin
+        np.testing.assert_array_equal(e.elem_ids, orc.elem_ids)
+        assert_positions_close(e.positions, orc.positions, f"step {step}")
+    assert want.sum() < orc.flux.sum()  # the unscored particles did fly (the oracle tallied them)
+    nf, vol = e.normalized_flux_bins()
+    np.testing.assert_allclose(nf, got / vol, rtol=1e-14)
+    out = str(tmp_path / "fluxresult.vtk")
+    e.WriteTallyResults(out)
+    from vtk_reader import read_vtu_cell_data
+
+    cells = read_vtu_cell_data(os.path.join(out, "pieces", "piece_0.vtu"))
+    for b in range(nbins):
+        np.testing.assert_array_equal(cells[f"flux_bin{b}"], nf[b])
+    np.testing.assert_allclose(cells["flux"], nf.sum(axis=0), rtol=1e-14)
+    # a plain move on a binned engine scores into the first bin; bins=None is the plain move
+    o, d, f, w = wl.next_step()
+    before = e.flux_bins
+    e.MoveToNextLocation(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy())
+    after = e.flux_bins
+    np.testing.assert_array_equal(after[1:], before[1:])
+    assert after[0].sum() > before[0].sum()
+    e.reset_tally()
+    assert not e.flux_bins.any()
+
+
+def test_score_bins_device_moves_and_single_bin():
+    import torch
+
+    nbins = 4
+    coords, t2v, wl = box_case((5, 5, 5), 15_000)
+    host, dev, plain = (gpu_engine(-1)(coords, t2v, wl.n) for _ in range(3))
+    host.set_score_bins(nbins)
+    dev.set_score_bins(nbins)
+    plain.set_score_bins(1)  # one bin is the unfiltered tally
+    init = wl.initial_positions()
+    for x in (host, dev, plain):
+        x.CopyInitialPosition(init.reshape(-1).copy())
+    s = torch.cuda.current_stream().cuda_stream
+    for step in range(3):
+        o, d, f, w = wl.next_step()
+        bins = _bins_for_step(wl.n, nbins, step)
+        inside = (bins >= 0) & (bins < nbins)
+        host.MoveToNextLocationBinned(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy(), bins)
+        t = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (o, d, f, w, bins)]
+        dev.move_device_binned(*(x.data_ptr() for x in t), s)
+        torch.cuda.synchronize()
+        # the unfiltered engine with the unscored particles' weights set to zero tallies the sum of the bins
+        plain.MoveToNextLocationBinned(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), np.where(inside, w, 0.0), bins)
+    np.testing.assert_allclose(dev.flux_bins, host.flux_bins, rtol=1e-12)
+    np.testing.assert_array_equal(dev.elem_ids, host.elem_ids)
+    np.testing.assert_array_equal(dev.positions, host.positions)
+    np.testing.assert_array_equal(plain.elem_ids, host.elem_ids)
+    assert_flux_close(host.flux_bins.sum(axis=0), plain.flux, "sum over bins vs unfiltered")
+    d_out = torch.empty(nbins * len(t2v), dtype=torch.float64, device="cuda")
+    host.get_flux_device(d_out.data_ptr(), s)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d_out.cpu().numpy().reshape(nbins, -1), host.flux_bins)
+    with pytest.raises(ValueError):
+        host.set_score_bins(0)
+
+
 def test_cxx_facade_program(tmp_path):
     """Link a C++ caller against include/pumitally/PumiTally.h + libpumitally.so, the way the
     OpenMC fork does, and replay the reference's known-answer scenario."""
@@ -664,6 +757,66 @@ def test_openmc_like_driver_example(tmp_path):
     cells = read_vtu_cell_data(str(tmp_path / "fluxresult.vtk" / "pieces" / "piece_0.vtu"))
     total2 = float((cells["flux"] * cells["volume"]).sum()) * norm
     assert 0.5 * 80000 * 0.75 < total2 < 3.0 * 80000 * 0.75 * 1.5
+
+
+def _two_gpu_bins_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    sys_path = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import sys
+    sys.path.insert(0, sys_path)
+    from pumiumtally_b200.distributed import broadcast_unique_id, particle_stripe
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    n_total, nbins = 30_000, 3
+    b, e = particle_stripe(n_total, rank, world)
+    eng = PumiTally.from_spec("box:7,7,7", e - b, device=rank)
+    eng.set_score_bins(nbins)  # before comm_init: the exchange buffers are sized for all bins
+    eng.comm_init(rank, world, broadcast_unique_id(dist, PumiTally.nccl_unique_id, device=torch.device("cuda", rank)))
+    wl = SyntheticWorkload(box=(7.0, 7.0, 7.0), num_particles=e - b, mean_length=2.0, id_offset=b)
+    eng.CopyInitialPosition(wl.initial_positions().reshape(-1))
+    for k in range(2):
+        o, d, f, w = wl.next_step()
+        bins = _bins_for_step(n_total, nbins, k)[b:e].copy()
+        eng.MoveToNextLocationBinned(o.reshape(-1), d.reshape(-1), f, w, bins)
+        (eng.allreduce_tally if k == 0 else eng.reduce_tally_to_owners)()
+    flux = eng.flux_bins
+    if rank == 0:
+        q.put(flux)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_score_bins_exchange_equals_single_gpu():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 1000
+    procs = [ctx.Process(target=_two_gpu_bins_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    flux2 = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n_total, nbins = 30_000, 3
+    coords, t2v, wl = box_case((7, 7, 7), n_total, mean_length=2.0)
+    one = PumiTally.from_spec("box:7,7,7", n_total)
+    one.set_score_bins(nbins)
+    one.CopyInitialPosition(wl.initial_positions().reshape(-1))
+    for k in range(2):
+        o, d, f, w = wl.next_step()
+        one.MoveToNextLocationBinned(o.reshape(-1), d.reshape(-1), f, w, _bins_for_step(n_total, nbins, k))
+    for b in range(nbins):
+        assert_flux_close(flux2[b], one.flux_bins[b], f"2-GPU bin {b} vs 1 GPU")
 
 
 def _two_gpu_worker(rank, world, port, q, outdir=None):

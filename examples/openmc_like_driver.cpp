@@ -13,7 +13,10 @@
 // use the additive <pumitally/PumiTallyExtras.h>.
 //
 //   g++ -std=c++17 -I include examples/openmc_like_driver.cpp -L pumiumtally_b200/lib -lpumitally \
-//       -Wl,-rpath,$PWD/pumiumtally_b200/lib -o driver && ./driver box:20,20,20 1000000 20 [inactive_batches]
+//       -Wl,-rpath,$PWD/pumiumtally_b200/lib -o driver && ./driver box:20,20,20 1000000 20 [inactive_batches [energy_groups]]
+//
+// energy_groups > 1 turns the tally into a filtered one (pumitally::SetScoreBins): each flight scores into the
+// flux array of the group it was sampled in; the VTK output then carries flux_bin<k> next to flux (their sum).
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -42,6 +45,7 @@ int main(int argc, char **argv) {
   const int n = argc > 2 ? std::atoi(argv[2]) : 100000;
   const int sweeps = argc > 3 ? std::atoi(argv[3]) : 10;
   const int inactive = argc > 4 ? std::atoi(argv[4]) : 0;  // batches of `sweeps` sweeps run and discarded first
+  const int groups = argc > 5 ? std::atoi(argv[5]) : 1;    // energy groups of the score filter
   double box[3] = {20, 20, 20};
   if (mesh.rfind("box:", 0) == 0) std::sscanf(mesh.c_str() + 4, "%lf,%lf,%lf", &box[0], &box[1], &box[2]);
 
@@ -50,6 +54,8 @@ int main(int argc, char **argv) {
   Rng rng{0x5EED};
   std::vector<double> pos(3 * size_t(n)), origin(3 * size_t(n)), dest(3 * size_t(n)), weight(n, 1.0);
   std::vector<int8_t> flying(n, 1);
+  std::vector<int32_t> group(n, 0);
+  if (groups > 1 && pumitally::SetScoreBins(tally, groups)) return 1;
   auto sample_site = [&](double *p) {
     for (int d = 0; d < 3; ++d) p[d] = (1e-6 + (1 - 2e-6) * rng.next()) * box[d];
   };
@@ -76,13 +82,17 @@ int main(int argc, char **argv) {
       d[2] = o[2] + len * mu;
       flying[i] = 1;
       weight[i] = 0.5 + 0.5 * rng.next();
+      if (groups > 1) group[i] = int32_t(rng.next() * groups);  // the "energy" after the last collision
       bool inside = true;
       for (int k = 0; k < 3; ++k) inside = inside && d[k] >= 0 && d[k] <= box[k];
       if (inside) { for (int k = 0; k < 3; ++k) p[k] = d[k]; }
       else { sample_site(p); ++leaks; }  // leaked: next flight starts at a fresh source site
       ++flights;
     }
-    tally.MoveToNextLocation(origin.data(), dest.data(), flying.data(), weight.data(), 3 * n);
+    if (groups > 1)
+      pumitally::MoveToNextLocationBinned(tally, origin.data(), dest.data(), flying.data(), weight.data(), group.data(), 3 * n);
+    else
+      tally.MoveToNextLocation(origin.data(), dest.data(), flying.data(), weight.data(), 3 * n);
   }
   }
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -757,6 +757,14 @@ def test_openmc_like_driver_example(tmp_path):
     cells = read_vtu_cell_data(str(tmp_path / "fluxresult.vtk" / "pieces" / "piece_0.vtu"))
     total2 = float((cells["flux"] * cells["volume"]).sum()) * norm
     assert 0.5 * 80000 * 0.75 < total2 < 3.0 * 80000 * 0.75 * 1.5
+    # three energy groups (score filter): every group gets about a third, the groups add up to "flux"
+    out = subprocess.check_output([exe, "box:8,8,8", "20000", "4", "0", "3"], cwd=str(tmp_path), text=True)
+    assert "DRIVER_OK 80000 flights" in out
+    cells = read_vtu_cell_data(str(tmp_path / "fluxresult.vtk" / "pieces" / "piece_0.vtu"))
+    groups = np.stack([cells[f"flux_bin{g}"] for g in range(3)])
+    np.testing.assert_allclose(groups.sum(axis=0), cells["flux"], rtol=1e-13)
+    share = (groups * cells["volume"]).sum(axis=1) / float((cells["flux"] * cells["volume"]).sum())
+    assert (np.abs(share - 1 / 3) < 0.02).all(), share
 
 
 def _two_gpu_bins_worker(rank, world, port, q):

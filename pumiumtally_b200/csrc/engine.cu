@@ -143,6 +143,7 @@ Engine::~Engine() {
   if (ev_bins_free_) cudaEventDestroy(ev_bins_free_);
   cudaFree(d_mask_);
   cudaFree(d_bins_);
+  if (h_bins_) cudaFreeHost(h_bins_);
   if (ev_copy0_) cudaEventDestroy(ev_copy0_);
   if (ev_copy1_) cudaEventDestroy(ev_copy1_);
   if (ev_ar0_) cudaEventDestroy(ev_ar0_);
@@ -316,13 +317,23 @@ int Engine::launch_range(const double *d_origin, const double *d_dest, const int
   // is walked once per bin with the flying flags masked down to that bin's particles and the tally pointed
   // at that bin's flux array -- the walk kernels themselves are the unfiltered ones.  One more pass (array
   // nbins_, never reported) flies the particles whose bin is outside [0, nbins_): they move, unscored.
-  for (int32_t b = 0; b <= nbins_; ++b) {
-    PTB_CUDA_OK(launch_bin_mask(d_flying, cur_bins_, b, nbins_, d_mask_, begin, end, stream));
-    ++launches_;
-    if (launch_range_into(d_flux_ + size_t(b) * size_t(mesh_.ntets), d_origin, d_dest, d_mask_, d_weights, begin, end, stream, timed))
-      return 1;
+  // The streaming kernel pays for every particle of the range in every pass, flying or not (measured on c2:
+  // 2.7 ms unfiltered, 5.5 ms with 4 bins, 10.3 ms with 8); the packed kernel's sort pass keeps only the flying
+  // ones, so its passes cost what their members cost.  Unless the caller has fixed the kernel, binned moves use it.
+  const int saved_variant = move_variant_, saved_tag = move_tag_;
+  if (auto_variant_ && d_weights) {
+    move_variant_ = kVariantPacked;
+    move_tag_ = -1;  // not one of the auto-tuner's exploration moves
   }
-  return 0;
+  int rc = 0;
+  for (int32_t b = 0; b <= nbins_ && !rc; ++b) {
+    if (launch_bin_mask(d_flying, cur_bins_, b, nbins_, d_mask_, begin, end, stream) != cudaSuccess) { rc = 1; break; }
+    ++launches_;
+    rc = launch_range_into(d_flux_ + size_t(b) * size_t(mesh_.ntets), d_origin, d_dest, d_mask_, d_weights, begin, end, stream, timed);
+  }
+  move_variant_ = saved_variant;
+  move_tag_ = saved_tag;
+  return rc;
 }
 
 int Engine::launch_range_into(double *d_flux, const double *d_origin, const double *d_dest, const int8_t *d_flying,
@@ -1033,7 +1044,32 @@ int Engine::move_to_next_location_binned(const double *origin, const double *des
   // d_bins_ is read by the mask kernels of the previous move until they are done
   PTB_CUDA_OK(cudaEventRecord(ev_bins_free_, compute_));
   PTB_CUDA_OK(cudaStreamWaitEvent(copy_, ev_bins_free_, 0));
-  PTB_CUDA_OK(cudaMemcpyAsync(d_bins_, bins, size_t(n_) * sizeof(int32_t), cudaMemcpyHostToDevice, copy_));
+  // through a pinned copy made by the worker pool (a pageable cudaMemcpyAsync of 40 MB blocks this thread for
+  // milliseconds before the staging of the particle data can even start); the previous move's DMA out of it
+  // was waited for before that move returned
+  const int32_t *src = bins;
+  if (!host_is_pinned(bins)) {
+    if (!h_bins_ && cudaHostAlloc(reinterpret_cast<void **>(&h_bins_), std::max<size_t>(size_t(n_), 1) * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      h_bins_ = nullptr;
+    }
+    if (h_bins_) {
+      int32_t *dst = h_bins_;
+      const size_t n = size_t(n_);
+      if (stager_) {  // (the pool exists from the first staged move on)
+        HostPool &pool = stager_->pool();
+        const int T = pool.size();
+        pool.run([&](int t) {
+          const size_t lo = n * size_t(t) / size_t(T), hi = n * size_t(t + 1) / size_t(T);
+          std::memcpy(dst + lo, bins + lo, (hi - lo) * sizeof(int32_t));
+        });
+      } else {
+        std::memcpy(dst, bins, n * sizeof(int32_t));
+      }
+      src = h_bins_;
+    }
+  }
+  PTB_CUDA_OK(cudaMemcpyAsync(d_bins_, src, size_t(n_) * sizeof(int32_t), cudaMemcpyHostToDevice, copy_));
   PTB_CUDA_OK(cudaEventRecord(ev_bins_, copy_));
   h2d_bytes_ += 4.0 * double(n_);
   cur_bins_ = d_bins_;

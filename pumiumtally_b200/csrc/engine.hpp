@@ -103,6 +103,7 @@ class Engine {
   const int32_t *cur_bins_ = nullptr; // device array of the move being launched (binned moves only)
   int8_t *d_mask_ = nullptr;          // [N] flying flags of one bin
   int32_t *d_bins_ = nullptr;         // [N] bins of a host-pointer move
+  int32_t *h_bins_ = nullptr;         // [N] pinned copy of the caller's bins on their way to the device
   cudaEvent_t ev_bins_ = nullptr, ev_bins_free_ = nullptr;
   bool host_is_pinned(const void *p) const;
   void maybe_register(const void *p, size_t bytes);

@@ -79,7 +79,7 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
   dev_alloc(&d_stats_, 1, "stats");
   dev_alloc(&d_initial_weight_, 1, "initial weight");
   cuda_or_throw(cudaMemset(d_initial_weight_, 0, sizeof(double)), "memset");
-  dev_alloc(&d_tickets_, kTicketRing, "tickets");
+  dev_alloc(&d_tickets_, 2 * kTicketRing, "tickets");  // second half: the other L2 partition's tickets (die split)
   dev_alloc(&d_pcell_, N, "particle cells");
   dev_alloc(&d_order_, N, "processing order");
   dev_alloc(&d_work_count_, kTicketRing, "work counts");
@@ -99,6 +99,9 @@ Engine::Engine(HostMesh &&mesh, int32_t num_particles, int device)
            "shortcut; option seed_grid=2 forces it)\n");
   variant_ = choose_variant();
   if (const char *env = std::getenv("PUMITALLY_REGISTER_HOST")) register_host_ = std::atoi(env) != 0;
+  if (const char *env = std::getenv("PUMITALLY_DIE_SPLIT")) {
+    if (std::atoi(env) != 0) set_option("die_split", 1);
+  }
   // the packed records are only needed on the device from here on
   std::vector<TetRecord>().swap(mesh_.records);
   printf("[INFO] pumitally-b200: %lld elements, %d particles on CUDA device %d\n",
@@ -359,6 +362,12 @@ int Engine::launch_range_into(double *d_flux, const double *d_origin, const doub
   p.cx = mesh_.center[0]; p.cy = mesh_.center[1]; p.cz = mesh_.center[2];
   if (!use_seed_grid_) p.grid.cell_tet = nullptr;
   p.work_counter = d_tickets_ + (ticket_next_++ % kTicketRing);
+  if (die_split_ && die0_sms_ > 0) {  // sorted kernels: each L2 partition's SMs on their own end of the sequence
+    for (int i = 0; i < 8; ++i) p.die_mask[i] = die_mask_[i];
+    p.die0_sms = die0_sms_;
+    p.nsms = nsms_;
+    p.work_counter2 = p.work_counter + kTicketRing;
+  }
   auto aligned16 = [](const void *q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
   p.bulk_ok = (begin % 16 == 0) && aligned16(d_origin) && aligned16(d_dest) && aligned16(d_flying) &&
               aligned16(d_weights);
@@ -1280,6 +1289,8 @@ int64_t Engine::get_option(const std::string &name) const {
   }
   if (name == "allreduce_us") return int64_t(allreduce_ms_ * 1e3);  // device time of the last batch-end exchange
   if (name == "score_bins") return nbins_;
+  if (name == "die_split") return die_split_ ? 1 : 0;
+  if (name == "l2_partition0_sms") return die0_sms_;  // SMs in the L2 partition of SM 0 (0: no map found)
   if (name == "exchange_choice") return exchange_choice_;  // what exchange_tally() does: 0 all-reduce, 1 reduce-scatter
   if (name == "exchange_allreduce_us") return int64_t(exchange_ms_[0] * 1e3);  // comm_init's measurement of the two
   if (name == "exchange_reduce_scatter_us") return int64_t(exchange_ms_[1] * 1e3);
@@ -1331,6 +1342,27 @@ int Engine::set_option(const std::string &name, int64_t v) {
   } else if (name == "chunk") {
     if (v < 1024) return 1;
     chunk_ = int32_t(std::min<int64_t>(v, INT_MAX)) & ~1023;  // keeps every range 16-byte aligned
+  } else if (name == "die_split") {
+    // Experiment, off by default (measured: c4 5 % slower, c5 1.6 % faster, c2 unchanged -- profiles/r02/README.md):
+    // the SMs of each L2 partition take the sorted particles from their own end of the sequence.
+    die_split_ = v != 0;
+    if (die_split_) {
+      // which SMs share an L2 partition: probed once per device and process (a few ms)
+      struct Cached { bool done = false; uint32_t mask[8]; int die0 = 0, nsms = 0; };
+      static Cached cache[64];
+      static std::mutex cache_mutex;
+      std::lock_guard<std::mutex> lock(cache_mutex);
+      Cached &c = cache[device_ & 63];
+      if (!c.done) {
+        PTB_CUDA_OK(cudaSetDevice(device_));
+        PTB_CUDA_OK(cudaDeviceSynchronize());
+        if (probe_l2_partitions(c.mask, &c.die0, &c.nsms, compute_) != 0) c.die0 = 0;
+        c.done = true;
+      }
+      for (int i = 0; i < 8; ++i) die_mask_[i] = c.mask[i];
+      die0_sms_ = c.die0;
+      nsms_ = c.nsms;
+    }
   } else if (name == "exchange_choice") {
     exchange_choice_ = v ? 1 : 0;  // the caller must set the same value on every rank
   } else if (name == "seed_grid") {

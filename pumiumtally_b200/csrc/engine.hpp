@@ -97,6 +97,10 @@ class Engine {
                    bool timed);
   int launch_range_into(double *d_flux, const double *d_origin, const double *d_dest, const int8_t *d_flying,
                         const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream, bool timed);
+  // L2 partition of every SM (l2_partitions.cu), probed when option die_split is switched on; die0_sms_ == 0: no usable map
+  uint32_t die_mask_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int die0_sms_ = 0, nsms_ = 0;
+  bool die_split_ = false;
   int32_t nbins_ = 1;
   size_t flux_alloc_ = 0;             // doubles allocated at d_flux_
   size_t flux_len() const { return size_t(nbins_) * size_t(mesh_.ntets); }  // reported part of d_flux_

@@ -97,6 +97,9 @@ cudaError_t launch_export_positions(const ParticleState *state, double *xyz, int
 cudaError_t launch_normalize(const double *flux, const double *volume, double *out, int64_t n,
                              double per_source, cudaStream_t stream);
 // *total += sum of weights[i] over flying particles of [begin, end)
+// l2_partitions.cu: which SMs share an L2 partition (mask bit s = partition of SM s); 0 = found two clear groups
+int probe_l2_partitions(uint32_t mask[8], int *die0_sms, int *nsms, cudaStream_t stream);
+
 // mask[i] = flying[i] && bins[i] == bin  (bin == nbins selects the particles outside [0, nbins))
 cudaError_t launch_bin_mask(const int8_t *flying, const int32_t *bins, int32_t bin, int32_t nbins, int8_t *mask,
                             int32_t begin, int32_t end, cudaStream_t stream);

@@ -1135,6 +1135,21 @@ def test_walks_cut_short_by_the_crossing_limit_are_reported_and_recoverable(vari
     np.testing.assert_array_equal(eng.elem_ids[moved], orc2.elem_ids[moved])
 
 
+@pytest.mark.parametrize("variant", [16, 24])
+def test_die_split_of_the_sorted_kernels_keeps_results(variant):
+    """Option die_split=1: the SMs of each L2 partition take the sorted particles from their own end of the
+    sequence (two ticket counters + work stealing); every particle is still walked exactly once."""
+    coords, t2v, wl = box_case((8, 8, 8), 60_000)
+    e = gpu_engine(variant, chunk=16384)(coords, t2v, wl.n)
+    e.set_option("die_split", 1)
+    assert e.get_option("die_split") == 1
+    n0 = e.get_option("l2_partition0_sms")
+    assert n0 == 0 or 40 <= n0 <= 108  # a B200: 76 of 148; 0 = no two groups found (the split then stays off)
+    run_workload(e, OraclePumiTally(coords, t2v, wl.n), wl, steps=3, label=f"die split v{variant}")
+    st = e.stats()
+    assert st["lost"] == 0 and st["tracks"] > 0
+
+
 def test_autotuner_switches_kernels_without_changing_results():
     """Default engine (variant chosen automatically): moves 1-4 alternate the streaming and the packed/sorted
     kernel, later moves use the faster one.  Whatever it picks, every move must match the oracle."""

@@ -612,8 +612,11 @@ int Engine::ensure_stage_buffers(const void *caller_mem, size_t caller_bytes) {
 }
 
 int Engine::ensure_patch_buffers(int nchunks) {
-  const size_t cap = size_t(double(std::min<int64_t>(chunk_, n_)) * kPatchMaxFraction) + 64;
-  if (h_patch_ && patch_cap_ == cap && patch_chunks_ >= nchunks) return 0;
+  size_t cap = size_t(double(std::min<int64_t>(chunk_, n_)) * kPatchMaxFraction) + 64;
+  if (h_patch_ && patch_cap_ >= cap && patch_chunks_ >= nchunks) return 0;
+  // (grow only, in both dimensions: moves with different stage sizes -- binned and plain -- may alternate)
+  cap = std::max(cap, patch_cap_);
+  nchunks = std::max(nchunks, patch_chunks_);
   PTB_CUDA_OK(cudaDeviceSynchronize());
   if (h_patch_) cudaFreeHost(h_patch_);
   if (d_patch_) cudaFree(d_patch_);
@@ -1084,7 +1087,12 @@ int Engine::move_to_next_location_binned(const double *origin, const double *des
   cur_bins_ = d_bins_;
   const bool pinned_path = pinned_path_;
   pinned_path_ = false;
+  // every pipeline stage is walked nbins + 1 times, seven small launches each, all enqueued by this thread between
+  // two stage passes: unless the caller chose the stage size, binned moves use stages of 2 Mi particles
+  const int32_t chunk = chunk_;
+  if (!chunk_user_set_) chunk_ = std::max(chunk_, int32_t(1) << 21);
   const int rc = move_to_next_location(origin, dest, flying, weights, size);
+  chunk_ = chunk;
   pinned_path_ = pinned_path;
   cur_bins_ = nullptr;
   PTB_CUDA_OK(cudaEventSynchronize(ev_bins_));  // the caller gets `bins` back with the other arrays
@@ -1342,6 +1350,7 @@ int Engine::set_option(const std::string &name, int64_t v) {
   } else if (name == "chunk") {
     if (v < 1024) return 1;
     chunk_ = int32_t(std::min<int64_t>(v, INT_MAX)) & ~1023;  // keeps every range 16-byte aligned
+    chunk_user_set_ = true;
   } else if (name == "die_split") {
     // Experiment, off by default (measured: c4 5 % slower, c5 1.6 % faster, c2 unchanged -- profiles/r02/README.md):
     // the SMs of each L2 partition take the sorted particles from their own end of the sequence.

@@ -140,6 +140,7 @@ class Engine {
   uint64_t launches_ = 0;  // kernels launched by the move / localisation entry points
   void begin_move();
   int block_ = 128;
+  bool chunk_user_set_ = false;
   int32_t chunk_ = 1 << 19;  // particles per H2D/compute pipeline stage (c2 from pageable arrays: 9.28 ms per move; 2^18: 10.0, 2^20: 9.5, 2^21: 10.9)
   // Seed grid for relocation / localisation.  The reference walks straight from the particle's old
   // position to the new one and stops at the hull if that segment leaves the mesh -- on a mesh with

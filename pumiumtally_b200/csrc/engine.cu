@@ -656,6 +656,18 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
   }
   PTB_CUDA_OK(cudaSetDevice(device_));
   begin_move();
+  // Pipeline stage size, unless the caller set it: 512 Ki particles for the streaming kernel (shortest tail); the
+  // sorted kernels pay a fixed price per launch (a scan over all seed-grid cells), so their stages are 2 Mi
+  // (c5 share, 50 M particles per GPU from pageable arrays: 58.6 ms per move with 1 Mi stages, 86.5 ms with 512 Ki).
+  const int32_t chunk = chunk_;
+  if (!chunk_user_set_ && (variant_is_gather(move_variant_) || variant_is_packed(move_variant_)))
+    chunk_ = std::max(chunk_, int32_t(1) << 21);
+  const int rc = move_host(origin, dest, flying, weights, size);
+  chunk_ = chunk;
+  return rc;
+}
+
+int Engine::move_host(const double *origin, const double *dest, int8_t *flying, const double *weights, int32_t size) {
   const int nchunks = n_ ? (n_ + chunk_ - 1) / chunk_ : 0;
   while (int(chunk_events_.size()) < nchunks + 2) {
     cudaEvent_t e;

@@ -95,6 +95,7 @@ class Engine {
   int launch_range(const double *d_origin, const double *d_dest, const int8_t *d_flying,
                    const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream,
                    bool timed);
+  int move_host(const double *origin, const double *dest, int8_t *flying, const double *weights, int32_t size);
   int launch_range_into(double *d_flux, const double *d_origin, const double *d_dest, const int8_t *d_flying,
                         const double *d_weights, int32_t begin, int32_t end, cudaStream_t stream, bool timed);
   // L2 partition of every SM (l2_partitions.cu), probed when option die_split is switched on; die0_sms_ == 0: no usable map

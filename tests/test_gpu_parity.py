@@ -682,12 +682,15 @@ def test_score_bins_device_moves_and_single_bin():
 
     nbins = 4
     coords, t2v, wl = box_case((5, 5, 5), 15_000)
-    host, dev, plain = (gpu_engine(-1)(coords, t2v, wl.n) for _ in range(3))
+    host, dev, plain, direct = (gpu_engine(-1)(coords, t2v, wl.n) for _ in range(4))
     host.set_score_bins(nbins)
     dev.set_score_bins(nbins)
+    direct.set_score_bins(nbins)
+    direct.set_option("host_path", 0)  # plain copies of the caller's arrays instead of the staging slots
+    direct.set_option("chunk", 4096)
     plain.set_score_bins(1)  # one bin is the unfiltered tally
     init = wl.initial_positions()
-    for x in (host, dev, plain):
+    for x in (host, dev, plain, direct):
         x.CopyInitialPosition(init.reshape(-1).copy())
     s = torch.cuda.current_stream().cuda_stream
     for step in range(3):
@@ -695,12 +698,15 @@ def test_score_bins_device_moves_and_single_bin():
         bins = _bins_for_step(wl.n, nbins, step)
         inside = (bins >= 0) & (bins < nbins)
         host.MoveToNextLocationBinned(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy(), bins)
+        direct.MoveToNextLocationBinned(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), w.copy(), bins)
         t = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (o, d, f, w, bins)]
         dev.move_device_binned(*(x.data_ptr() for x in t), s)
         torch.cuda.synchronize()
         # the unfiltered engine with the unscored particles' weights set to zero tallies the sum of the bins
         plain.MoveToNextLocationBinned(o.reshape(-1).copy(), d.reshape(-1).copy(), f.copy(), np.where(inside, w, 0.0), bins)
     np.testing.assert_allclose(dev.flux_bins, host.flux_bins, rtol=1e-12)
+    np.testing.assert_allclose(direct.flux_bins, host.flux_bins, rtol=1e-12)
+    np.testing.assert_array_equal(direct.positions, host.positions)
     np.testing.assert_array_equal(dev.elem_ids, host.elem_ids)
     np.testing.assert_array_equal(dev.positions, host.positions)
     np.testing.assert_array_equal(plain.elem_ids, host.elem_ids)

@@ -235,7 +235,7 @@ void Engine::collect_timers(bool wait) {
         explore_ms_[t.tag] += ms;
         if (--explore_pending_ == 0 && explore_complete_) {  // all four exploration moves measured
           // the streaming kernel keeps the job unless sorting buys more than 3 %
-          tuned_variant_ = explore_ms_[1] < 0.97 * explore_ms_[0] ? kVariantPacked : kVariantPersistRefill8;
+          tuned_variant_ = (explore_ms_[1] > 0.0 && explore_ms_[1] < 0.97 * explore_ms_[0]) ? kVariantPacked : kVariantPersistRefill8;
           explore_complete_ = false;
         }
       }
@@ -273,7 +273,7 @@ void Engine::begin_move() {
         if (t.tag >= 0) cudaEventSynchronize(t.b);
       collect_timers(false);
       if (explore_complete_ && explore_pending_ == 0) {
-        tuned_variant_ = explore_ms_[1] < 0.97 * explore_ms_[0] ? kVariantPacked : kVariantPersistRefill8;
+        tuned_variant_ = (explore_ms_[1] > 0.0 && explore_ms_[1] < 0.97 * explore_ms_[0]) ? kVariantPacked : kVariantPersistRefill8;
         explore_complete_ = false;
       }
     }
@@ -660,6 +660,14 @@ int Engine::move_to_next_location(const double *origin, const double *dest, int8
   // sorted kernels pay a fixed price per launch (a scan over all seed-grid cells), so their stages are 2 Mi
   // (c5 share, 50 M particles per GPU from pageable arrays: 58.6 ms per move with 1 Mi stages, 86.5 ms with 512 Ki).
   const int32_t chunk = chunk_;
+  // The auto-tuner compares kernel times; in a host move the sorted kernel it may prefer would also need the
+  // larger stages, whose longer tail costs more than the kernel wins (c2 from pageable arrays: 11.1 ms against
+  // 9.4 ms per move).  So a host move of more than one stage keeps the engine's base kernel and does not take
+  // part in the exploration; the tuner works for device-pointer moves and single-stage host moves (c4's 1 M tracks).
+  if (auto_variant_ && variant_is_packed(move_variant_) && !variant_is_packed(variant_) && n_ > chunk_) {
+    move_variant_ = variant_;
+    move_tag_ = -1;
+  }
   if (!chunk_user_set_ && (variant_is_gather(move_variant_) || variant_is_packed(move_variant_)))
     chunk_ = std::max(chunk_, int32_t(1) << 21);
   const int rc = move_host(origin, dest, flying, weights, size);
